@@ -1,0 +1,163 @@
+/*
+ * pd_b200.h — C-ABI of the B200-native Prompt-Diffusion denoising hot path.
+ *
+ * The reference (david3684/Prompt-Diffusion) is 100 % Python/PyTorch and has no
+ * FFI of its own; its "operator API" on this path is the set of torch ops that
+ * cldm/cldm.py, ldm/modules/diffusionmodules/openaimodel.py, ldm/modules/attention.py
+ * and cldm/ddim_hacked.py call.  Each entry point below replaces one such op (or
+ * a fused group of them) and cites the reference lines it stands in for.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch / C++ types.
+ *  - every pointer is a DEVICE pointer unless the name ends in _host.
+ *  - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it
+ *    and never synchronise, allocate or free (CUDA-graph capturable).
+ *  - activations are pixel-major ("NHWC"): element (b,y,x,c) of a [B,H,W,C]
+ *    tensor lives at base + ((b*H + y)*W + x)*ld + c, with row pitch ld >= C in
+ *    ELEMENTS (lets a producer write straight into a channel-concat slot).
+ *  - dtype codes: PD_F32 (fp32 mode: SIMT FFMA kernels, fp32 storage) and
+ *    PD_BF16 (bf16 storage, fp32 accumulation; tcgen05/TMEM/TMA GEMMs).
+ *  - return value: 0 on success, a negative PD_ERR_* / positive cudaError_t
+ *    otherwise; pd_last_error() gives a human-readable message.  There is no
+ *    CPU fallback anywhere behind this interface.
+ */
+#ifndef PD_B200_H_
+#define PD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_F32 0
+#define PD_BF16 1
+
+#define PD_ACT_NONE 0
+#define PD_ACT_SILU 1
+
+#define PD_ERR_BAD_ARG (-1)
+#define PD_ERR_UNSUPPORTED (-2)
+#define PD_ERR_NO_DEVICE (-3)
+
+/* engine selection for pd_conv2d */
+#define PD_ENGINE_AUTO 0   /* tcgen05 when dtype==BF16 and the shape qualifies, else SIMT */
+#define PD_ENGINE_SIMT 1   /* force the SIMT implicit-GEMM kernel (any shape, any dtype)    */
+#define PD_ENGINE_TC 2     /* force tcgen05; PD_ERR_UNSUPPORTED if the shape does not fit   */
+
+const char* pd_last_error(void);
+int pd_abi_version(void);
+/* number of kernels this library has launched since load (bench "gpu_launches") */
+uint64_t pd_launch_count(void);
+/* 1 when the current device is sm_100 (tcgen05/TMEM present) */
+int pd_device_is_sm100(void);
+
+/*
+ * Convolution / linear as one implicit GEMM.
+ *   replaces  nn.Conv2d 3x3 / 1x1 (conv_nd, util.py:221-231) as used by ResBlock
+ *             (openaimodel.py:200-240,254-274), Downsample (:150-159), Upsample's
+ *             conv (:106,116-117), SpatialTransformer.proj_in/proj_out
+ *             (attention.py:298-316,329,339), ControlNet hint stacks / zero convs
+ *             (cldm.py:147-181,299-300,320-323), UNet `out` conv (openaimodel.py:726-730);
+ *             and nn.Linear (time_embed, emb_layers, to_q/k/v, to_out, GEGLU proj,
+ *             ff.net.2: attention.py:52,72,154-161) with H=W=1.
+ *   out[b,yo,xo,n] = act( alpha * ( sum_k A[..] * Wt[n,k] + bias[n] ) + rowvec[b,n] + res[b,yo,xo,n] )
+ *   K runs over segment 0 (ksize x ksize taps of x, tap-major then channel) followed by
+ *   optional segment 1 (a 1x1 tap of x2 sampled at the OUTPUT pixel): this fuses
+ *   ResBlock's skip_connection 1x1 conv into out_layers' conv3x3 (openaimodel.py:274).
+ *   Weights are [Cout, ksize*ksize*C + C2] row-major (K contiguous), same dtype as x.
+ */
+typedef struct pd_conv_params {
+  const void* x;       /* [B,H,W,C] pitch ldx                               */
+  const void* x2;      /* optional [B,Ho,Wo,C2] pitch ldx2 (segment 1)      */
+  const void* w;       /* [Cout, Ktot]                                      */
+  const float* bias;   /* [Cout] fp32 or NULL                               */
+  const float* rowvec; /* optional [B, Cout] fp32, pitch ldrv (timestep emb) */
+  const void* res;     /* optional residual [B,Ho,Wo,Cout] pitch ldr, dtype = out dtype */
+  void* out;           /* [B,Ho,Wo,Cout] pitch ldo                          */
+  int32_t B, H, W, C;  /* input geometry of x (H, W BEFORE the optional upsample) */
+  int32_t C2;          /* channels of x2 (0 = no segment 1)                 */
+  int32_t Cout;
+  int32_t ksize;       /* 1 or 3 (padding = ksize/2)                        */
+  int32_t stride;      /* 1 or 2                                            */
+  int32_t upsample;    /* 1: x is read through a nearest x2 upsample (Upsample.forward) */
+  int32_t ldx, ldx2, ldr, ldo, ldrv;
+  int32_t act;         /* PD_ACT_*                                          */
+  int32_t dtype;       /* dtype of x, x2, w                                 */
+  int32_t out_dtype;   /* dtype of out and res                              */
+  int32_t engine;      /* PD_ENGINE_*                                       */
+  float alpha;
+} pd_conv_params;
+int pd_conv2d(const pd_conv_params* p, void* stream);
+
+/* Re-lay a reference OIHW fp32 conv weight (or [out,in] linear weight with kh=kw=1)
+ * into the [Cout, kh*kw*Cin] tap-major K-contiguous layout pd_conv2d expects,
+ * channel-padding Cin -> cin_pad with zeros, converting to `dtype`.
+ * (checkpoint layout: SURVEY.md appendix B; loader cldm/model.py:12-21) */
+int pd_repack_conv_weight(const float* w_oihw, void* w_out, int32_t cout, int32_t cin,
+                          int32_t kh, int32_t kw, int32_t cin_pad, int32_t ldk, int32_t k_offset,
+                          int32_t dtype, void* stream);
+
+/* GroupNorm(32 groups) + optional SiLU, fp32 statistics.
+ *   replaces GroupNorm32 (util.py:217-219) + nn.SiLU in ResBlock.in_layers/out_layers
+ *   (openaimodel.py:200-231), UNet `out` (:726-728) and Normalize (attention.py:88-89, eps 1e-6).
+ *   `partial` is caller-provided scratch of pd_group_norm_scratch_floats(B) floats. */
+int64_t pd_group_norm_scratch_floats(int32_t B);
+int pd_group_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const float* gamma,
+                  const float* beta, float* partial, int32_t B, int32_t HW, int32_t C,
+                  int32_t groups, float eps, int32_t act, int32_t dtype, int32_t out_dtype,
+                  void* stream);
+
+/* LayerNorm over the last dim (nn.LayerNorm, attention.py:263-265, eps 1e-5). */
+int pd_layer_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const float* gamma,
+                  const float* beta, int64_t rows, int32_t C, float eps, int32_t dtype,
+                  void* stream);
+
+/* GEGLU gate: out[m,f] = x[m,f] * gelu_erf(x[m,F+f])  (attention.py:54-56). */
+int pd_geglu(const void* x, int32_t ldx, void* out, int32_t ldo, int64_t rows, int32_t F,
+             int32_t dtype, void* stream);
+
+/* Multi-head softmax attention without materialising the score matrix.
+ *   replaces CrossAttention.forward's einsum/softmax/einsum (attention.py:171-193):
+ *   q [B,Nq,heads*d] pitch ldq, k/v [B,Nk,heads*d] pitch ldk/ldv, out [B,Nq,heads*d];
+ *   sim = q k^T * scale in fp32, softmax over Nk, out = sim v.  No mask (the path never
+ *   passes one). */
+int pd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
+                 int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
+                 int32_t Nk, int32_t d, float scale, int32_t dtype, void* stream);
+
+/* timestep_embedding (util.py:154-174): t [B] int64 -> [B, dim] = [cos(t f), sin(t f)]. */
+int pd_timestep_embedding(const int64_t* t, void* out, int32_t ldo, int32_t B, int32_t dim,
+                          float max_period, int32_t out_dtype, void* stream);
+
+/* elementwise SiLU (nn.SiLU between hint-stack convs is fused via pd_conv_params.act;
+ * this one serves emb_layers' leading SiLU, openaimodel.py:217-218). */
+int pd_silu(const void* x, void* out, int64_t n, int32_t dtype, void* stream);
+
+/* Layout / dtype bridges at the NCHW-fp32 boundary of the reference API
+ * (ControlLDM.apply_model tensors, cldm.py:369-382). */
+int pd_nchw_to_nhwc(const float* x, void* out, int32_t ldo, int32_t B, int32_t C, int32_t H,
+                    int32_t W, int32_t out_dtype, void* stream);
+int pd_nhwc_to_nchw(const void* x, int32_t ldx, float* out, int32_t B, int32_t C, int32_t H,
+                    int32_t W, int32_t dtype, float scale, void* stream);
+/* strided 2-D cast/copy: out[r, c] = (out_dtype) x[r, c], r < rows, c < cols */
+int pd_cast2d(const void* x, int32_t ldx, int32_t dtype, void* out, int32_t ldo,
+              int32_t out_dtype, int64_t rows, int32_t cols, void* stream);
+/* nearest-neighbour x2 upsample of a pixel-major tensor (F.interpolate, openaimodel.py:115). */
+int pd_upsample2x(const void* x, int32_t ldx, void* out, int32_t ldo, int32_t B, int32_t H,
+                  int32_t W, int32_t C, int32_t dtype, void* stream);
+
+/* Fused classifier-free guidance + DDIM update for one step
+ *   replaces cldm/ddim_hacked.py:193 (e = e_u + s (e_c - e_u)) and :211-233
+ *   (pred_x0, dir_xt, noise, x_prev).  `coef` points to 6 floats on the DEVICE:
+ *   {a_t, a_prev, sigma_t, sqrt_one_minus_at, cfg_scale, temperature}; eps_uncond may be
+ *   NULL (no guidance: e = eps_cond); noise may be NULL (treated as 0; valid when sigma_t == 0).
+ *   All tensors fp32, n elements, any (matching) layout. */
+int pd_cfg_ddim_step(const float* eps_uncond, const float* eps_cond, const float* x,
+                     const float* noise, const float* coef, float* x_prev, float* pred_x0,
+                     float* e_t, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PD_B200_H_ */

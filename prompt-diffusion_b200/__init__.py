@@ -1,0 +1,8 @@
+"""B200-native Prompt-Diffusion denoising hot path (ControlLDM.apply_model inside
+the DDIM loop) behind the reference's own Python signatures.
+
+Import as ``prompt_diffusion_b200`` (alias of this directory).  Heavy pieces
+(the CUDA C-ABI library) are loaded on first use by ``prompt_diffusion_b200._lib``
+and fail loudly if the in-tree ``libpd_b200.so`` is missing.
+"""
+__version__ = "0.1.0"
