@@ -1,0 +1,19 @@
+#!/bin/bash
+# Build the C-ABI library (sm_100a only) in-tree: prompt-diffusion_b200/libpd_b200.so
+set -e
+cd "$(dirname "$0")/prompt-diffusion_b200/csrc"
+OUT=../libpd_b200.so
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --use_fast_math"
+FLAGS_ACC="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
+mkdir -p ../../build
+pids=()
+for f in elementwise norm conv_simt attention_simt; do
+  nvcc $FLAGS_ACC -c $f.cu -o ../../build/$f.o & pids+=($!)
+done
+for f in attention_mma gemm_sm100; do
+  nvcc $FLAGS_ACC -c $f.cu -o ../../build/$f.o & pids+=($!)
+done
+for p in "${pids[@]}"; do wait $p; done
+nvcc -shared -o $OUT ../../build/elementwise.o ../../build/norm.o ../../build/conv_simt.o \
+  ../../build/attention_simt.o ../../build/attention_mma.o ../../build/gemm_sm100.o -lcudart_static -ldl -lrt -lpthread
+echo "built $(realpath $OUT)"

@@ -125,6 +125,10 @@ int pd_geglu(const void* x, int32_t ldx, void* out, int32_t ldo, int64_t rows, i
 int pd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
                  int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
                  int32_t Nk, int32_t d, float scale, int32_t dtype, void* stream);
+/* same, with an explicit engine: 0 auto, 1 SIMT (fp32 math, any dtype), 2 tensor-core (bf16) */
+int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
+                    int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
+                    int32_t Nk, int32_t d, float scale, int32_t dtype, int32_t engine, void* stream);
 
 /* timestep_embedding (util.py:154-174): t [B] int64 -> [B, dim] = [cos(t f), sin(t f)]. */
 int pd_timestep_embedding(const int64_t* t, void* out, int32_t ldo, int32_t B, int32_t dim,
@@ -136,8 +140,10 @@ int pd_silu(const void* x, void* out, int64_t n, int32_t dtype, void* stream);
 
 /* Layout / dtype bridges at the NCHW-fp32 boundary of the reference API
  * (ControlLDM.apply_model tensors, cldm.py:369-382). */
+/* accumulate != 0: out += x (adds an externally supplied NCHW control tensor in place,
+ * ControlledUnetModel.forward `h += control.pop()`, cldm.py:35,41) */
 int pd_nchw_to_nhwc(const float* x, void* out, int32_t ldo, int32_t B, int32_t C, int32_t H,
-                    int32_t W, int32_t out_dtype, void* stream);
+                    int32_t W, int32_t out_dtype, int32_t accumulate, void* stream);
 int pd_nhwc_to_nchw(const void* x, int32_t ldx, float* out, int32_t B, int32_t C, int32_t H,
                     int32_t W, int32_t dtype, float scale, void* stream);
 /* strided 2-D cast/copy: out[r, c] = (out_dtype) x[r, c], r < rows, c < cols */

@@ -6,3 +6,16 @@ Import as ``prompt_diffusion_b200`` (alias of this directory).  Heavy pieces
 and fail loudly if the in-tree ``libpd_b200.so`` is missing.
 """
 __version__ = "0.1.0"
+
+from .config import CLDM_V15, CLDMConfig  # noqa: E402,F401
+
+
+def __getattr__(name):
+    # heavy, CUDA-library-backed symbols are imported lazily
+    if name in ("ControlLDM", "ControlNet", "ControlledUnetModel", "DDIMSampler"):
+        from . import cldm as _cldm
+        return getattr(_cldm, name)
+    if name == "PromptDiffusionControlNetModel":
+        from .promptdiffusioncontrolnet import PromptDiffusionControlNetModel
+        return PromptDiffusionControlNetModel
+    raise AttributeError(name)

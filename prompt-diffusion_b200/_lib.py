@@ -1,0 +1,99 @@
+"""ctypes binding of the C-ABI in ``include/pd_b200.h`` (``libpd_b200.so``, built in-tree
+by ``build.sh`` / ``__graft_entry__.build()``).
+
+There is no CPU or PyTorch fallback: if the library is missing, importing this module
+raises, and every op raises ``RuntimeError`` with ``pd_last_error()`` on a non-zero return.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpd_b200.so")
+
+PD_F32, PD_BF16 = 0, 1
+PD_ACT_NONE, PD_ACT_SILU = 0, 1
+PD_ENGINE_AUTO, PD_ENGINE_SIMT, PD_ENGINE_TC = 0, 1, 2
+PD_ATTN_AUTO, PD_ATTN_SIMT, PD_ATTN_MMA = 0, 1, 2
+
+
+class ConvParams(C.Structure):
+    """Mirror of ``pd_conv_params`` (include/pd_b200.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("x2", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
+        ("rowvec", C.c_void_p), ("res", C.c_void_p), ("out", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("C2", C.c_int32), ("Cout", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
+        ("upsample", C.c_int32),
+        ("ldx", C.c_int32), ("ldx2", C.c_int32), ("ldr", C.c_int32), ("ldo", C.c_int32),
+        ("ldrv", C.c_int32),
+        ("act", C.c_int32), ("dtype", C.c_int32), ("out_dtype", C.c_int32), ("engine", C.c_int32),
+        ("alpha", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/pd_b200.h
+SIGNATURES = {
+    "pd_last_error": (C.c_char_p, []),
+    "pd_abi_version": (C.c_int, []),
+    "pd_launch_count": (C.c_uint64, []),
+    "pd_device_is_sm100": (C.c_int, []),
+    "pd_conv2d": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
+    "pd_repack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),
+    "pd_group_norm_scratch_floats": (C.c_int64, [C.c_int32]),
+    "pd_group_norm": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "pd_layer_norm": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "pd_geglu": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                           C.c_void_p]),
+    "pd_attention": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                               C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                               C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "pd_attention_ex": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
+    "pd_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_float, C.c_int32, C.c_void_p]),
+    "pd_silu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "pd_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "pd_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "pd_cast2d": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
+                            C.c_int32, C.c_void_p]),
+    "pd_upsample2x": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "pd_cfg_ddim_step": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_void_p]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with ./build.sh (or __graft_entry__.build()). "
+            "prompt_diffusion_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    return lib.pd_last_error().decode(errors="replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def launch_count() -> int:
+    return int(lib.pd_launch_count())

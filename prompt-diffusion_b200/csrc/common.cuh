@@ -1,0 +1,96 @@
+// Shared helpers for the pd_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pd_b200.h"
+
+namespace pd {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);  // cudaPeekAtLastError -> code + message
+
+#define PD_REQUIRE(cond, ...)                    \
+  do {                                           \
+    if (!(cond)) {                               \
+      pd::set_error(__VA_ARGS__);                \
+      return PD_ERR_BAD_ARG;                     \
+    }                                            \
+  } while (0)
+
+// ---- dtype traits ------------------------------------------------------------
+template <typename T> struct Dt;
+template <> struct Dt<float> {
+  static constexpr int code = PD_F32;
+  __device__ __forceinline__ static float ld(const float* p) { return *p; }
+  __device__ __forceinline__ static void st(float* p, float v) { *p = v; }
+};
+template <> struct Dt<bf16> {
+  static constexpr int code = PD_BF16;
+  __device__ __forceinline__ static float ld(const bf16* p) { return __bfloat162float(*p); }
+  __device__ __forceinline__ static void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// accurate variant for the fp32 mode (expf, IEEE divide)
+__device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// 8 x bf16 <-> 8 floats through one 16-byte access
+struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// entry points implemented per engine (dispatched by pd_conv2d in conv_simt.cu)
+int conv2d_simt(const pd_conv_params* p, cudaStream_t s);
+int conv2d_tc(const pd_conv_params* p, cudaStream_t s);       // gemm_sm100.cu
+bool conv2d_tc_supported(const pd_conv_params* p, const char** why);
+int attention_simt(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
+                   int ldo, int B, int heads, int Nq, int Nk, int d, float scale, int dtype,
+                   cudaStream_t s);
+int attention_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
+                  int ldo, int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
+
+}  // namespace pd

@@ -1,0 +1,487 @@
+// tcgen05 / TMEM / TMA implicit-GEMM engine for sm_100a: every conv3x3, conv1x1 and linear
+// of the UNet + ControlNet whose channel counts are multiples of 64.
+//
+//   D[128 x BN] (fp32, TMEM) += A[128 x 64] (bf16, smem, K-major, SWIZZLE_128B)
+//                             * B[BN  x 64]^T (bf16, smem, K-major, SWIZZLE_128B)
+//
+// * A is never materialised: a K block is 64 channels of ONE filter tap, fetched by a 4-D
+//   TMA box (64 ch, bw, bh, bn pixels) from the pixel-major activation at the tap's shifted
+//   coordinate; TMA's out-of-bounds zero fill IS the conv's zero padding.  Stride-2 convs
+//   use the tensor map's element strides.  An optional second K segment (1x1 tap of a
+//   second tensor) fuses ResBlock's skip_connection into out_layers' conv.
+// * Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+//   alloc), warps 2-5 = epilogue.  smem ring (full/empty mbarriers) between TMA and MMA,
+//   two TMEM accumulators (2 x 256 columns) between MMA and epilogue, so tile i's
+//   epilogue overlaps tile i+1's MMAs.
+// * Epilogue: tcgen05.ld -> alpha*(acc+bias) + timestep row-vector + residual (ControlNet
+//   zero-conv add / skip / guided hint) -> optional SiLU -> bf16 (or fp32) 16-byte stores
+//   with an arbitrary row pitch (writes land directly in channel-concat slots).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pd {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_SMEM_BUDGET = 227 * 1024 - 2048;
+
+struct TcArgs {
+  const float* bias; const float* rowvec; const void* res; void* out;
+  int ldr, ldo, ldrv, act, out_f32;
+  float alpha;
+  int B, Ho, Wo, Cout;
+  int hw_real;                  // pixels per image (rowvec row = m / hw_real; survives the 1x1 flattening)
+  int ksize, stride, C, C2;
+  int cpt0, nk0, nk1;           // 64-ch blocks per tap, k-blocks of segment 0 / 1
+  int bw, bh, bn;               // pixel box of one 128-row M tile
+  int tiles_x, tiles_y, tiles_b, m_tiles, n_tiles, BN, stages;
+  uint32_t idesc;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("pd_b200 conv_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14), LBO>>4 [16,30) (=1, unused for swizzled K-major), SBO>>4 [32,46) (= 1024 B:
+// eight 128-byte rows per swizzle atom), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+      "%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- the kernel ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_w, const TcArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full[2];
+  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // SWIZZLE_128B atoms need 1024-byte aligned stage bases
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = a.BN * TC_BK * 2;
+  const int stage_bytes = TC_A_BYTES + b_bytes;
+  const int nkb = a.nk0 + a.nk1;
+  const int num_tiles = a.m_tiles * a.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_w);
+    if (a.nk1 > 0) tma_prefetch_desc(&map_a1);
+    for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const int pad = a.ksize >> 1;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile / a.m_tiles, mt = tile - nt * a.m_tiles;
+        const int txi = mt % a.tiles_x;
+        const int tyi = (mt / a.tiles_x) % a.tiles_y;
+        const int tbi = mt / (a.tiles_x * a.tiles_y);
+        const int x0 = txi * a.bw, y0 = tyi * a.bh, b0 = tbi * a.bn, n0 = nt * a.BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+          unsigned char* sa = smem + stage * stage_bytes;
+          unsigned char* sb = sa + TC_A_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          if (kb < a.nk0) {
+            const int tap = kb / a.cpt0;
+            const int c0 = (kb - tap * a.cpt0) * TC_BK;
+            const int dy = tap / a.ksize, dx = tap - dy * a.ksize;
+            tma_load_4d(sa, &map_a0, &full_bar[stage], c0, x0 * a.stride + dx - pad, y0 * a.stride + dy - pad, b0);
+            tma_load_2d(sb, &map_w, &full_bar[stage], tap * a.C + c0, n0);
+          } else {
+            const int c0 = (kb - a.nk0) * TC_BK;
+            tma_load_4d(sa, &map_a1, &full_bar[stage], c0, x0, y0, b0);
+            tma_load_2d(sb, &map_w, &full_bar[stage], a.ksize * a.ksize * a.C + c0, n0);
+          }
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 200 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t sa = s_u32(smem + stage * stage_bytes);
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int qd = warp & 3;               // TMEM lane quadrant this warp may touch
+    const int r = qd * 32 + lane;          // accumulator row == tile pixel
+    const int rx = r % a.bw;
+    const int ry = (r / a.bw) % a.bh;
+    const int rb = r / (a.bw * a.bh);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int nt = tile / a.m_tiles, mt = tile - nt * a.m_tiles;
+      const int txi = mt % a.tiles_x;
+      const int tyi = (mt / a.tiles_x) % a.tiles_y;
+      const int tbi = mt / (a.tiles_x * a.tiles_y);
+      const int x = txi * a.bw + rx, y = tyi * a.bh + ry, b = tbi * a.bn + rb;
+      const bool row_ok = x < a.Wo && y < a.Ho && b < a.B;
+      const int64_t m = ((int64_t)b * a.Ho + y) * a.Wo + x;
+      const int n0 = nt * a.BN;
+
+      mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)acc * 256u;
+      for (int cc = 0; cc < a.BN; cc += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)cc, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + cc + g * 8;
+            if (n < a.Cout) {   // Cout % 8 == 0 (host-checked): an 8-column group is all-in or all-out
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+              if (a.bias != nullptr) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (a.alpha != 1.0f) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] *= a.alpha;
+              }
+              if (a.rowvec != nullptr) {
+                const float* rv = a.rowvec + (m / a.hw_real) * a.ldrv + n;
+                const float4 r0 = __ldg(reinterpret_cast<const float4*>(rv));
+                const float4 r1 = __ldg(reinterpret_cast<const float4*>(rv + 4));
+                f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+              }
+              if (a.out_f32) {
+                float* op = reinterpret_cast<float*>(a.out) + m * a.ldo + n;
+                if (a.res != nullptr) {
+                  const float* rp = reinterpret_cast<const float*>(a.res) + m * a.ldr + n;
+                  const float4 r0 = *reinterpret_cast<const float4*>(rp);
+                  const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+                  f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w;
+                  f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+                }
+                if (a.act == PD_ACT_SILU) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+                }
+                *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                bf16* op = reinterpret_cast<bf16*>(a.out) + m * a.ldo + n;
+                if (a.res != nullptr) {
+                  float rf[8];
+                  unpack8(*reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(a.res) + m * a.ldr + n), rf);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] += rf[e];
+                }
+                if (a.act == PD_ACT_SILU) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+                }
+                *reinterpret_cast<bf16x8*>(op) = pack8(f);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    else cudaGetLastError();
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, const uint32_t* estrides, const char* what) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return PD_ERR_NO_DEVICE; }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box,
+                  (const cuuint32_t*)estrides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv_tc: cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
+              what, (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1],
+              rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return PD_ERR_BAD_ARG;
+  }
+  return 0;
+}
+
+static inline int pow2_divisor(int v, int cap) {  // largest power of two dividing v, capped
+  int p = 1;
+  while (p * 2 <= cap && v % (p * 2) == 0) p *= 2;
+  return p;
+}
+
+bool conv2d_tc_supported(const pd_conv_params* p, const char** why) {
+  static int sm100 = -1;
+  if (sm100 < 0) sm100 = pd_device_is_sm100();
+#define PD_NO(msg) do { if (why) *why = msg; return false; } while (0)
+  if (!sm100) PD_NO("device is not sm_100");
+  if (p->dtype != PD_BF16) PD_NO("dtype is not bf16");
+  if (p->upsample) PD_NO("fused upsample not handled by the TMA gather (materialise with pd_upsample2x)");
+  if (p->C % 64 != 0 || p->C2 % 64 != 0) PD_NO("channel counts must be multiples of 64");
+  if (p->Cout % 8 != 0) PD_NO("Cout must be a multiple of 8");
+  if (p->ldx % 8 != 0 || (p->C2 > 0 && p->ldx2 % 8 != 0)) PD_NO("input pitch must be a multiple of 8 elements");
+  if ((uintptr_t)p->x % 16 != 0 || (uintptr_t)p->w % 16 != 0 || (p->C2 > 0 && (uintptr_t)p->x2 % 16 != 0))
+    PD_NO("input/weight pointers must be 16-byte aligned");
+  const int oe = p->out_dtype == PD_F32 ? 4 : 2;
+  if ((uintptr_t)p->out % 16 != 0 || (p->ldo * oe) % 16 != 0) PD_NO("output must be 16-byte aligned with 16-byte pitch");
+  if (p->res && ((uintptr_t)p->res % 16 != 0 || (p->ldr * oe) % 16 != 0)) PD_NO("residual must be 16-byte aligned");
+  if (p->bias && (uintptr_t)p->bias % 16 != 0) PD_NO("bias must be 16-byte aligned");
+  if (p->rowvec && ((uintptr_t)p->rowvec % 16 != 0 || p->ldrv % 4 != 0)) PD_NO("rowvec must be 16-byte aligned");
+  if (p->stride == 2 && p->ksize != 3) PD_NO("stride 2 only with 3x3");
+  if (p->stride == 2 && (p->H % 2 != 0 || p->W % 2 != 0)) PD_NO("stride 2 needs even H, W");
+#undef PD_NO
+  return true;
+}
+
+int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
+  TcArgs a;
+  const int pad = p->ksize / 2;
+  const int Ho = (p->H + 2 * pad - p->ksize) / p->stride + 1;
+  const int Wo = (p->W + 2 * pad - p->ksize) / p->stride + 1;
+  a.bias = p->bias; a.rowvec = p->rowvec; a.res = p->res; a.out = p->out;
+  a.ldr = p->ldr; a.ldo = p->ldo; a.ldrv = p->ldrv; a.act = p->act; a.out_f32 = p->out_dtype == PD_F32;
+  a.alpha = p->alpha;
+  a.ksize = p->ksize; a.stride = p->stride; a.C = p->C; a.C2 = p->C2; a.Cout = p->Cout;
+  a.cpt0 = p->C / TC_BK;
+  a.nk0 = p->ksize * p->ksize * a.cpt0;
+  a.nk1 = p->C2 / TC_BK;
+  const int Ktot = p->ksize * p->ksize * p->C + p->C2;
+
+  // ---- M-tile pixel box -------------------------------------------------------------------------
+  // 1x1 stride-1 layers are plain GEMMs over all B*H*W pixels (also with a row pitch): one long row.
+  int gB = p->B, gH = Ho, gW = Wo;           // output geometry as the kernel sees it
+  int iB = p->B, iH = p->H, iW = p->W;       // input geometry for the TMA map
+  if (p->ksize == 1 && p->stride == 1) {
+    gW = iW = p->B * p->H * p->W; gH = iH = 1; gB = iB = 1;
+  }
+  a.B = gB; a.Ho = gH; a.Wo = gW;
+  a.hw_real = Ho * Wo;
+  a.bw = pow2_divisor(gW, 128);
+  if (p->ksize == 1 && p->stride == 1) a.bw = 128;   // partial last tile is masked
+  a.bh = pow2_divisor(gH, 128 / a.bw);
+  a.bn = 128 / (a.bw * a.bh);
+  a.tiles_x = (gW + a.bw - 1) / a.bw;
+  a.tiles_y = (gH + a.bh - 1) / a.bh;
+  a.tiles_b = (gB + a.bn - 1) / a.bn;
+  a.m_tiles = a.tiles_x * a.tiles_y * a.tiles_b;
+
+  // ---- N tile: minimise waves x (BN + fixed per-k-block cost) -------------------------------------
+  const int sms = num_sms();
+  int best_bn = 64; double best_cost = 1e30;
+  for (int bn = 256; bn >= 32; bn -= 16) {
+    int n_tiles = (p->Cout + bn - 1) / bn;
+    int64_t tiles = (int64_t)a.m_tiles * n_tiles;
+    int64_t waves = (tiles + sms - 1) / sms;
+    double cost = (double)waves * (bn + 40.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; }
+  }
+  a.BN = best_bn;
+  a.n_tiles = (p->Cout + a.BN - 1) / a.BN;
+  const int stage_bytes = TC_A_BYTES + a.BN * TC_BK * 2;
+  a.stages = TC_SMEM_BUDGET / stage_bytes;
+  if (a.stages > TC_MAX_STAGES) a.stages = TC_MAX_STAGES;
+  if (a.stages < 2) { set_error("conv_tc: not enough shared memory for 2 stages"); return PD_ERR_UNSUPPORTED; }
+  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+  // ---- tensor maps ------------------------------------------------------------------------------
+  CUtensorMap map_a0, map_a1, map_w;
+  {
+    uint64_t dims[4] = {(uint64_t)p->C, (uint64_t)iW, (uint64_t)iH, (uint64_t)iB};
+    uint64_t strides[3] = {(uint64_t)p->ldx * 2, (uint64_t)iW * p->ldx * 2, (uint64_t)iH * iW * p->ldx * 2};
+    uint32_t box[4] = {TC_BK, (uint32_t)(a.bw * p->stride), (uint32_t)(a.bh * p->stride), (uint32_t)a.bn};
+    uint32_t es[4] = {1, (uint32_t)p->stride, (uint32_t)p->stride, 1};
+    int rc = encode_map(&map_a0, p->x, 4, dims, strides, box, es, "A0");
+    if (rc) return rc;
+  }
+  if (p->C2 > 0) {
+    uint64_t dims[4] = {(uint64_t)p->C2, (uint64_t)gW, (uint64_t)gH, (uint64_t)gB};
+    uint64_t strides[3] = {(uint64_t)p->ldx2 * 2, (uint64_t)gW * p->ldx2 * 2, (uint64_t)gH * gW * p->ldx2 * 2};
+    uint32_t box[4] = {TC_BK, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn};
+    uint32_t es[4] = {1, 1, 1, 1};
+    int rc = encode_map(&map_a1, p->x2, 4, dims, strides, box, es, "A1");
+    if (rc) return rc;
+  } else {
+    map_a1 = map_a0;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p->Cout};
+    uint64_t strides[1] = {(uint64_t)Ktot * 2};
+    uint32_t box[2] = {TC_BK, (uint32_t)a.BN};
+    uint32_t es[2] = {1, 1};
+    int rc = encode_map(&map_w, p->w, 2, dims, strides, box, es, "W");
+    if (rc) return rc;
+  }
+
+  const size_t smem = (size_t)a.stages * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+    if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  int64_t tiles = (int64_t)a.m_tiles * a.n_tiles;
+  int grid = (int)(tiles < sms ? tiles : sms);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(map_a0, map_a1, map_w, a);
+  return check_launch("conv_tc");
+}
+
+}  // namespace pd

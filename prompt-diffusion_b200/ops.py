@@ -1,0 +1,193 @@
+"""Thin torch-tensor wrappers over the C-ABI (``include/pd_b200.h``).
+
+PyTorch is plumbing only: it owns device memory and the current CUDA stream; every op
+below passes raw pointers / pitches to ``libpd_b200.so``.  Activations are 2-D views
+``[pixels, channels]`` with unit inner stride and an arbitrary row pitch (so a column
+slice of a wider concat buffer is a legal input or output).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (PD_ACT_NONE, PD_ACT_SILU, PD_BF16, PD_ENGINE_AUTO, PD_ENGINE_SIMT, PD_ENGINE_TC,
+                   PD_F32, ConvParams, check, lib)
+
+_DT = {torch.float32: PD_F32, torch.bfloat16: PD_BF16}
+
+
+def dt_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}") from None
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Row pitch (elements) of a 2-D pixel-major view."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"expected a 2-D view with unit inner stride, got shape {tuple(t.shape)} "
+                         f"strides {t.stride()}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("prompt_diffusion_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def conv2d(x, w, out, B, H, W, *, ksize=1, stride=1, upsample=False, bias=None, rowvec=None, res=None,
+           x2=None, act=PD_ACT_NONE, alpha=1.0, engine=PD_ENGINE_AUTO):
+    """out[B*Ho*Wo, Cout] = act(alpha*(conv(x) [+ x2 @ Wskip] + bias) + rowvec[b] + res)."""
+    _cuda(x, w, out, bias, rowvec, res, x2)
+    p = ConvParams()
+    p.x, p.x2, p.w, p.bias, p.rowvec, p.res, p.out = _p(x), _p(x2), _p(w), _p(bias), _p(rowvec), _p(res), _p(out)
+    p.B, p.H, p.W, p.C = B, H, W, x.shape[1]
+    p.C2 = 0 if x2 is None else x2.shape[1]
+    p.Cout = out.shape[1]
+    p.ksize, p.stride, p.upsample = ksize, stride, int(bool(upsample))
+    p.ldx = _ld(x)
+    p.ldx2 = 0 if x2 is None else _ld(x2)
+    p.ldr = 0 if res is None else _ld(res)
+    p.ldo = _ld(out)
+    p.ldrv = 0 if rowvec is None else _ld(rowvec)
+    p.act, p.dtype, p.out_dtype, p.engine, p.alpha = act, dt_code(x), dt_code(out), engine, float(alpha)
+    if w.dtype != x.dtype or (x2 is not None and x2.dtype != x.dtype):
+        raise TypeError("x, x2 and w must share a dtype")
+    if res is not None and res.dtype != out.dtype:
+        raise TypeError("res must have the output dtype")
+    ktot = ksize * ksize * p.C + p.C2
+    if w.dim() != 2 or w.shape[0] != p.Cout or w.shape[1] != ktot or not w.is_contiguous():
+        raise ValueError(f"weight must be contiguous [{p.Cout}, {ktot}], got {tuple(w.shape)}")
+    if x.shape[0] != B * H * W:
+        raise ValueError(f"x has {x.shape[0]} pixels, expected {B * H * W}")
+    check(lib.pd_conv2d(C.byref(p), _stream()), "pd_conv2d")
+    return out
+
+
+def linear(x, w, out, **kw):
+    return conv2d(x, w, out, 1, 1, x.shape[0], **kw)
+
+
+def repack_conv_weight(w_oihw: torch.Tensor, out: torch.Tensor, cin_pad: Optional[int] = None, k_offset: int = 0):
+    """fp32 OIHW (or [out,in]) -> rows of `out` ([Cout, ldk], K-major, tap-major), see pd_repack_conv_weight."""
+    _cuda(w_oihw, out)
+    if w_oihw.dim() == 2:
+        w_oihw = w_oihw[:, :, None, None]
+    cout, cin, kh, kw = w_oihw.shape
+    cin_pad = cin if cin_pad is None else cin_pad
+    w_oihw = w_oihw.contiguous().float()
+    check(lib.pd_repack_conv_weight(w_oihw.data_ptr(), out.data_ptr(), cout, cin, kh, kw, cin_pad,
+                                    out.stride(0), k_offset, dt_code(out), _stream()), "pd_repack_conv_weight")
+    return out
+
+
+_gn_scratch = {}
+
+
+def group_norm(x, out, gamma, beta, B, HW, *, groups=32, eps=1e-5, act=PD_ACT_NONE):
+    _cuda(x, out, gamma, beta)
+    key = (x.device.index, B)
+    scratch = _gn_scratch.get(key)
+    if scratch is None:
+        scratch = torch.empty(int(lib.pd_group_norm_scratch_floats(B)), dtype=torch.float32, device=x.device)
+        _gn_scratch[key] = scratch
+    check(lib.pd_group_norm(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), gamma.data_ptr(), beta.data_ptr(),
+                            scratch.data_ptr(), B, HW, x.shape[1], groups, float(eps), act, dt_code(x),
+                            dt_code(out), _stream()), "pd_group_norm")
+    return out
+
+
+def layer_norm(x, out, gamma, beta, eps=1e-5):
+    _cuda(x, out, gamma, beta)
+    check(lib.pd_layer_norm(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), gamma.data_ptr(), beta.data_ptr(),
+                            x.shape[0], x.shape[1], float(eps), dt_code(x), _stream()), "pd_layer_norm")
+    return out
+
+
+def geglu(x, out):
+    _cuda(x, out)
+    check(lib.pd_geglu(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), x.shape[0], out.shape[1], dt_code(x),
+                       _stream()), "pd_geglu")
+    return out
+
+
+def attention(q, k, v, out, B, heads, Nq, Nk, d, scale=None, engine=0):
+    _cuda(q, k, v, out)
+    scale = d ** -0.5 if scale is None else scale
+    check(lib.pd_attention_ex(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(),
+                              _ld(out), B, heads, Nq, Nk, d, float(scale), dt_code(q), engine, _stream()),
+          "pd_attention")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, out: torch.Tensor, max_period: float = 10000.0):
+    _cuda(t, out)
+    if t.dtype != torch.int64:
+        raise TypeError("timesteps must be int64")
+    check(lib.pd_timestep_embedding(t.data_ptr(), out.data_ptr(), _ld(out), t.shape[0], out.shape[1],
+                                    float(max_period), dt_code(out), _stream()), "pd_timestep_embedding")
+    return out
+
+
+def silu(x, out):
+    _cuda(x, out)
+    check(lib.pd_silu(x.data_ptr(), out.data_ptr(), x.numel(), dt_code(x), _stream()), "pd_silu")
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False):
+    """x fp32 [B,C,H,W] contiguous -> out [B*H*W, >=C] (dtype of out)."""
+    _cuda(x, out)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise TypeError("nchw_to_nhwc wants a contiguous fp32 NCHW tensor")
+    B, Cc, H, W = x.shape
+    check(lib.pd_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), _ld(out), B, Cc, H, W, dt_code(out),
+                              int(accumulate), _stream()), "pd_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, B, Cc, H, W, scale: float = 1.0, out: Optional[torch.Tensor] = None):
+    _cuda(x)
+    if out is None:
+        out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    check(lib.pd_nhwc_to_nchw(x.data_ptr(), _ld(x), out.data_ptr(), B, Cc, H, W, dt_code(x), float(scale),
+                              _stream()), "pd_nhwc_to_nchw")
+    return out
+
+
+def cast2d(x, out):
+    _cuda(x, out)
+    check(lib.pd_cast2d(x.data_ptr(), _ld(x), dt_code(x), out.data_ptr(), _ld(out), dt_code(out), x.shape[0],
+                        x.shape[1], _stream()), "pd_cast2d")
+    return out
+
+
+def upsample2x(x, out, B, H, W):
+    _cuda(x, out)
+    check(lib.pd_upsample2x(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), B, H, W, x.shape[1], dt_code(x),
+                            _stream()), "pd_upsample2x")
+    return out
+
+
+def cfg_ddim_step(eps_uncond, eps_cond, x, noise, coef, x_prev, pred_x0=None, e_t=None):
+    """Fused CFG + DDIM update; all fp32, same layout; coef = 6 device floats."""
+    _cuda(eps_cond, x, coef, x_prev)
+    for t in (eps_uncond, eps_cond, x, noise, x_prev, pred_x0, e_t):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise TypeError("cfg_ddim_step wants contiguous fp32 tensors")
+    check(lib.pd_cfg_ddim_step(_p(eps_uncond), eps_cond.data_ptr(), x.data_ptr(), _p(noise), coef.data_ptr(),
+                               x_prev.data_ptr(), _p(pred_x0), _p(e_t), x.numel(), _stream()), "pd_cfg_ddim_step")
+    return x_prev

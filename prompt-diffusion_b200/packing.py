@@ -1,0 +1,187 @@
+"""One-time checkpoint ingest: reference ``state_dict`` (OIHW / [out,in] fp32, key grammar
+of SURVEY.md appendix B, written by tool_add_control.py:36-48 and read by
+cldm/model.py:12-21) -> K-major tap-major device weights in the compute dtype, with the
+load-time fusions the kernels rely on:
+
+* ResBlock ``out_layers.3`` 3x3 conv and ``skip_connection`` 1x1 conv share one weight
+  matrix ``[Cout, 9*Cout + Cin]`` (second K segment) and one summed bias;
+* attn1 ``to_q|to_k|to_v`` -> one ``[3C, C]`` matrix; attn2 ``to_k|to_v`` -> ``[2C, ctx]``;
+* all ``emb_layers.1`` of a net -> one ``[sum Cout, 4*mc]`` matrix (one GEMM per step);
+* bf16 mode pads input channels that are >= 16 but not a multiple of 64 (hint stacks:
+  16, 32, 96) up to 64/128 so those convs also run on the tcgen05 engine.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Mapping, Optional
+
+import torch
+
+from . import ops
+from .config import CLDMConfig, Conv, Down, HINT_STACK, Res, ST, Up, build_topology
+
+
+def pad_channels(c: int, dt: torch.dtype) -> int:
+    if dt == torch.bfloat16 and c >= 16 and c % 64 != 0:
+        return (c + 63) // 64 * 64
+    return c
+
+
+class PConv:
+    __slots__ = ("w", "bias", "cin", "cin_pad", "cout", "ksize", "stride", "c2", "role")
+
+    def __init__(self, w, bias, cin, cin_pad, cout, ksize, stride, c2=0, role="conv"):
+        self.w, self.bias, self.cin, self.cin_pad, self.cout = w, bias, cin, cin_pad, cout
+        self.ksize, self.stride, self.c2, self.role = ksize, stride, c2, role
+
+
+class PNorm:
+    __slots__ = ("gamma", "beta")
+
+    def __init__(self, gamma, beta):
+        self.gamma, self.beta = gamma, beta
+
+
+class PRes:
+    __slots__ = ("key", "cin", "cout", "gn1", "conv1", "gn2", "conv2", "emb_off", "has_skip")
+
+
+class PST:
+    __slots__ = ("key", "ch", "heads", "d", "gn", "proj_in", "ln1", "wqkv", "out1", "ln2", "wq2", "wkv2",
+                 "out2", "ln3", "ff1", "ff2", "proj_out")
+
+
+class Packer:
+    def __init__(self, sd: Mapping[str, torch.Tensor], prefix: str, dt: torch.dtype, device):
+        self.sd, self.prefix, self.dt, self.device = sd, prefix, dt, device
+
+    def t(self, key: str) -> torch.Tensor:
+        try:
+            v = self.sd[self.prefix + key]
+        except KeyError:
+            raise KeyError(f"checkpoint is missing '{self.prefix + key}'") from None
+        return v.to(device=self.device, dtype=torch.float32, non_blocking=True)
+
+    def vec(self, key: str) -> torch.Tensor:
+        return self.t(key).contiguous()
+
+    def norm(self, key: str) -> PNorm:
+        return PNorm(self.vec(key + ".weight"), self.vec(key + ".bias"))
+
+    def conv(self, key: str, stride: int = 1, skip_key: Optional[str] = None, pad: bool = True) -> PConv:
+        w = self.t(key + ".weight")
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        cout, cin, kh, kw = w.shape
+        cin_pad = pad_channels(cin, self.dt) if pad else cin
+        ktot = kh * kw * cin_pad
+        c2 = 0
+        if skip_key is not None:
+            ws = self.t(skip_key + ".weight")
+            c2 = ws.shape[1]
+            ktot += c2
+        out = torch.empty((cout, ktot), dtype=self.dt, device=self.device)
+        ops.repack_conv_weight(w, out, cin_pad=cin_pad, k_offset=0)
+        bias = self.vec(key + ".bias") if (self.prefix + key + ".bias") in self.sd else None
+        if skip_key is not None:
+            ops.repack_conv_weight(ws, out, k_offset=kh * kw * cin_pad)
+            bias = (bias + self.vec(skip_key + ".bias")).contiguous()
+        return PConv(out, bias, cin, cin_pad, cout, kh, stride, c2)
+
+    def stacked_linear(self, keys: List[str], with_bias: bool) -> PConv:
+        ws = [self.t(k + ".weight") for k in keys]
+        cin = ws[0].shape[1]
+        cout = sum(w.shape[0] for w in ws)
+        out = torch.empty((cout, cin), dtype=self.dt, device=self.device)
+        r = 0
+        for w in ws:
+            ops.repack_conv_weight(w, out[r:r + w.shape[0]])
+            r += w.shape[0]
+        bias = torch.cat([self.vec(k + ".bias") for k in keys]).contiguous() if with_bias else None
+        return PConv(out, bias, cin, cin, cout, 1, 1)
+
+    def res(self, layer: Res) -> PRes:
+        k = layer.key
+        r = PRes()
+        r.key, r.cin, r.cout = k, layer.cin, layer.cout
+        r.gn1 = self.norm(k + ".in_layers.0")
+        r.conv1 = self.conv(k + ".in_layers.2")
+        r.gn2 = self.norm(k + ".out_layers.0")
+        r.has_skip = layer.cin != layer.cout
+        r.conv2 = self.conv(k + ".out_layers.3", skip_key=(k + ".skip_connection") if r.has_skip else None)
+        r.emb_off = -1
+        return r
+
+    def st(self, layer: ST) -> PST:
+        k = layer.key
+        tb = k + ".transformer_blocks.0"
+        s = PST()
+        s.key, s.ch, s.heads, s.d = k, layer.ch, layer.heads, layer.d_head
+        s.gn = self.norm(k + ".norm")
+        s.proj_in = self.conv(k + ".proj_in")
+        s.ln1, s.ln2, s.ln3 = self.norm(tb + ".norm1"), self.norm(tb + ".norm2"), self.norm(tb + ".norm3")
+        s.wqkv = self.stacked_linear([tb + ".attn1.to_q", tb + ".attn1.to_k", tb + ".attn1.to_v"], False)
+        s.out1 = self.conv(tb + ".attn1.to_out.0")
+        s.wq2 = self.conv(tb + ".attn2.to_q")
+        s.wkv2 = self.stacked_linear([tb + ".attn2.to_k", tb + ".attn2.to_v"], False)
+        s.out2 = self.conv(tb + ".attn2.to_out.0")
+        s.ff1 = self.conv(tb + ".ff.net.0.proj")
+        s.ff2 = self.conv(tb + ".ff.net.2")
+        s.proj_out = self.conv(k + ".proj_out")
+        return s
+
+    def layer(self, layer):
+        if isinstance(layer, Res):
+            return self.res(layer)
+        if isinstance(layer, ST):
+            return self.st(layer)
+        if isinstance(layer, Conv):
+            return self.conv(layer.key, stride=layer.stride)
+        if isinstance(layer, Down):
+            pc = self.conv(layer.key + ".op", stride=2)
+            pc.role = "down"
+            return pc
+        if isinstance(layer, Up):
+            pc = self.conv(layer.key + ".conv")
+            pc.role = "up"
+            return pc
+        raise TypeError(layer)
+
+
+class PackedNet:
+    """Packed weights of one net (UNet or ControlNet)."""
+
+    def __init__(self, cfg: CLDMConfig, sd: Mapping[str, torch.Tensor], prefix: str, decoder: bool,
+                 dt: torch.dtype, device):
+        pk = Packer(sd, prefix, dt, device)
+        topo = build_topology(cfg, with_decoder=decoder)
+        self.topo = topo
+        self.te0 = pk.conv("time_embed.0")
+        self.te2 = pk.conv("time_embed.2")
+        self.input_blocks = [[pk.layer(l) for l in blk] for blk in topo.input_blocks]
+        self.middle = [pk.layer(l) for l in topo.middle]
+        self.output_blocks = [[pk.layer(l) for l in blk] for blk in topo.output_blocks] if decoder else []
+        # batch every ResBlock's emb_layers.1 into one GEMM
+        res_layers = [l for blk in (self.input_blocks + [self.middle] + self.output_blocks) for l in blk
+                      if isinstance(l, PRes)]
+        off = 0
+        for r in res_layers:
+            r.emb_off = off
+            off += r.cout
+        self.emb_all = pk.stacked_linear([r.key + ".emb_layers.1" for r in res_layers], True)
+        self.emb_total = off
+        if decoder:
+            self.out_norm = pk.norm("out.0")
+            self.out_conv = pk.conv("out.2")
+        else:
+            self.zero_convs = [pk.conv(f"zero_convs.{i}.0") for i in range(len(topo.input_blocks))]
+            self.middle_out = pk.conv("middle_block_out.0")
+            self.hint_pair = self._hint(pk, "input_hint_block", cfg)
+            self.hint_query = self._hint(pk, "input_cond_block", cfg)
+
+    @staticmethod
+    def _hint(pk: Packer, stem: str, cfg: CLDMConfig) -> List[PConv]:
+        convs = []
+        for i, (_cout, stride) in enumerate(HINT_STACK):
+            convs.append(pk.conv(f"{stem}.{2 * i}", stride=stride))
+        convs.append(pk.conv(f"{stem}.{2 * len(HINT_STACK)}"))
+        return convs

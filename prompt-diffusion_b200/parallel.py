@@ -1,0 +1,70 @@
+"""Data-parallel sampling over the GPUs of one box: prompts are independent through the whole DDIM loop
+(GroupNorm / LayerNorm / attention are per-sample; the CFG pair of a prompt stays on one rank), so each
+rank runs its own loop on a contiguous shard and the ONLY collective is one all-gather of the final latents
+(NCCL over NVLink; gloo in the CPU tests).  Precedent in the reference: rank-strided ownership without a
+gather, eval/evaluate_gen.py:55.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced: the first n % world ranks own one extra item."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_conditioning(cond: Optional[Dict[str, list]], lo: int, hi: int):
+    """Slice every tensor of a reference-style conditioning dict ({'c_crossattn': [T], 'example_pair': [T],
+    'query': [T]}) along the batch dim."""
+    if cond is None:
+        return None
+    return {k: [t[lo:hi] for t in v] for k, v in cond.items()}
+
+
+def all_gather_latents(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
+    """One all-gather of the final latents; ragged shards are padded to the largest shard."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per = (total + world - 1) // world
+    padded = local
+    if local.shape[0] < per:
+        padded = torch.cat([local, local.new_zeros((per - local.shape[0],) + tuple(local.shape[1:]))])
+    padded = padded.contiguous()
+    outs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(outs, padded, group=group)
+    parts = []
+    for r, o in enumerate(outs):
+        lo, hi = shard_bounds(total, r, world)
+        parts.append(o[: hi - lo])
+    return torch.cat(parts)
+
+
+def sample_sharded(sample_fn: Callable, batch_size: int, conditioning, unconditional_conditioning=None,
+                   x_T: Optional[torch.Tensor] = None, group=None, chunk: Optional[int] = None):
+    """Run ``sample_fn(local_batch, cond, un_cond, x_T) -> latents`` on this rank's shard (optionally in
+    chunks of ``chunk`` prompts) and all-gather the results in prompt order.
+
+    ``x_T`` (if given) is the FULL-batch noise so that the result is bit-identical to the single-GPU run."""
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    lo, hi = shard_bounds(batch_size, rank, world)
+    outs = []
+    step = (hi - lo) if not chunk else chunk
+    for a in range(lo, hi, max(step, 1)):
+        b = min(hi, a + step)
+        outs.append(sample_fn(b - a, shard_conditioning(conditioning, a, b),
+                              shard_conditioning(unconditional_conditioning, a, b),
+                              None if x_T is None else x_T[a:b]))
+    local = torch.cat(outs) if outs else None
+    if local is None:
+        raise ValueError(f"rank {rank} owns no prompts (batch {batch_size} < world {world})")
+    return all_gather_latents(local, batch_size, group)

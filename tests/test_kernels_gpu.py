@@ -1,0 +1,261 @@
+"""Per-kernel parity through the C-ABI (ctypes) against plain torch fp32 ops on the same GPU.
+
+Tolerances (written per test): fp32 kernels <= 2e-5 rel-L2 (different summation order only);
+bf16 kernels are compared with a torch fp32 evaluation of the SAME bf16-rounded operands, so the
+only error left is fp32 accumulation order + the final bf16 rounding (<= 6e-3 rel-L2, 2^-8 max)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+
+
+def _ops():
+    from prompt_diffusion_b200 import ops
+    return ops
+
+
+def _pm(x):
+    """NCHW -> pixel-major [B*H*W, C]"""
+    B, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous()
+
+
+def _conv_case(dt, engine, B, H, W, C, Cout, ksize, stride=1, upsample=False, C2=0, rowvec=False, res=False,
+               act=0, alpha=1.0, out_dt=None, ldo_extra=0, seed=0):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    out_dt = dt if out_dt is None else out_dt
+    x = torch.randn(B, C, H, W, device=DEV, generator=g)
+    w = torch.randn(Cout, C, ksize, ksize, device=DEV, generator=g) / math.sqrt(C * ksize * ksize)
+    bias = torch.randn(Cout, device=DEV, generator=g)
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if upsample else x
+    xq, wq = x.to(dt).float(), w.to(dt).float()
+    xinq = F.interpolate(xq, scale_factor=2, mode="nearest") if upsample else xq
+    ref = F.conv2d(xinq, wq, None, stride=stride, padding=ksize // 2)
+    Ho, Wo = ref.shape[-2:]
+    ktot = ksize * ksize * C + C2
+    wp = torch.empty(Cout, ktot, dtype=dt, device=DEV)
+    ops.repack_conv_weight(w, wp)
+    x2_pm = None
+    if C2:
+        x2 = torch.randn(B, C2, Ho, Wo, device=DEV, generator=g)
+        w2 = torch.randn(Cout, C2, 1, 1, device=DEV, generator=g) / math.sqrt(C2)
+        ops.repack_conv_weight(w2, wp, k_offset=ksize * ksize * C)
+        ref = ref + F.conv2d(x2.to(dt).float(), w2.to(dt).float())
+        x2_pm = _pm(x2).to(dt)
+    ref = (ref + bias[None, :, None, None]) * alpha
+    rv = None
+    if rowvec:
+        rv = torch.randn(B, Cout, device=DEV, generator=g)
+        ref = ref + rv[:, :, None, None]
+    res_pm = None
+    if res:
+        r = torch.randn(B, Cout, Ho, Wo, device=DEV, generator=g)
+        res_pm = _pm(r).to(out_dt)
+        ref = ref + _pm(r).to(out_dt).float().reshape(B, Ho, Wo, Cout).permute(0, 3, 1, 2)
+    if act:
+        ref = F.silu(ref)
+    M = B * Ho * Wo
+    full = torch.full((M, Cout + ldo_extra), 7.0, dtype=out_dt, device=DEV)
+    out = full[:, ldo_extra:] if ldo_extra else full
+    ops.conv2d(_pm(x).to(dt), wp, out, B, H, W, ksize=ksize, stride=stride, upsample=upsample, bias=bias,
+               rowvec=rv, res=res_pm, x2=x2_pm, act=act, alpha=alpha, engine=engine)
+    torch.cuda.synchronize()
+    if ldo_extra:
+        assert bool((full[:, :ldo_extra] == 7.0).all()), "kernel wrote outside its column slot"
+    return rel_l2(out.float(), _pm(ref))
+
+
+SIMT_CASES = [
+    dict(B=2, H=9, W=7, C=6, Cout=16, ksize=3),                                  # hint conv_in, ragged
+    dict(B=1, H=16, W=16, C=4, Cout=320, ksize=3, res=True),                     # input_blocks.0 + hint
+    dict(B=2, H=12, W=12, C=32, Cout=96, ksize=3, stride=2, act=1),              # hint stride-2 + SiLU
+    dict(B=2, H=8, W=8, C=64, Cout=64, ksize=3, rowvec=True),                    # ResBlock conv1 + emb
+    dict(B=2, H=8, W=8, C=64, Cout=128, ksize=3, C2=32),                         # fused skip segment
+    dict(B=1, H=6, W=5, C=48, Cout=40, ksize=3, upsample=True),                  # Upsample conv
+    dict(B=3, H=5, W=5, C=70, Cout=33, ksize=1, res=True, alpha=0.7),            # zero conv + scale + add
+    dict(B=2, H=8, W=8, C=320, Cout=4, ksize=3),                                 # UNet `out` conv
+    dict(B=1, H=1, W=1, C=320, Cout=1280, ksize=1, act=1),                       # time_embed row
+]
+
+
+@pytest.mark.parametrize("case", SIMT_CASES)
+def test_conv_simt_fp32(case):
+    from prompt_diffusion_b200._lib import PD_ENGINE_SIMT
+    err = _conv_case(torch.float32, PD_ENGINE_SIMT, **case)
+    assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("case", SIMT_CASES[:6])
+def test_conv_simt_bf16(case):
+    from prompt_diffusion_b200._lib import PD_ENGINE_SIMT
+    err = _conv_case(torch.bfloat16, PD_ENGINE_SIMT, **case)
+    assert err < 6e-3, err
+
+
+TC_CASES = [
+    dict(B=1, H=16, W=16, C=64, Cout=64, ksize=3),                               # smallest: 2 M tiles
+    dict(B=2, H=16, W=16, C=128, Cout=96, ksize=1),                              # plain GEMM, M=512
+    dict(B=1, H=1, W=1000, C=64, Cout=160, ksize=1),                             # ragged M (partial tile)
+    dict(B=2, H=32, W=32, C=320, Cout=320, ksize=3, rowvec=True),                # ResBlock conv1
+    dict(B=2, H=32, W=32, C=320, Cout=640, ksize=3, C2=320),                     # conv2 + fused skip
+    dict(B=2, H=16, W=16, C=128, Cout=128, ksize=3, stride=2),                   # Downsample (TMA elem strides)
+    dict(B=3, H=8, W=8, C=1280, Cout=1280, ksize=3, res=True),                   # 8x8 level: box spans 2 images
+    dict(B=2, H=16, W=16, C=640, Cout=640, ksize=1, res=True, alpha=0.5, ldo_extra=64),  # zero conv into a slot
+    dict(B=1, H=1, W=16, C=1280, Cout=1280, ksize=1, act=1, out_dt=torch.float32),       # time_embed, fp32 out
+    dict(B=2, H=24, W=24, C=64, Cout=64, ksize=3),                               # non power-of-two latent (768^2 family)
+    dict(B=2, H=64, W=64, C=64, Cout=2560, ksize=1),                             # wide N (GEGLU proj): many N tiles
+    dict(B=1, H=16, W=16, C=2560, Cout=1280, ksize=3),                           # longest K: 360 k-blocks
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_bf16(case):
+    from prompt_diffusion_b200._lib import PD_ENGINE_TC
+    err = _conv_case(torch.bfloat16, PD_ENGINE_TC, **case)
+    assert err < 6e-3, err
+
+
+def test_conv_tc_rejects_unsupported():
+    from prompt_diffusion_b200._lib import PD_ENGINE_TC
+    with pytest.raises(RuntimeError):
+        _conv_case(torch.bfloat16, PD_ENGINE_TC, B=1, H=8, W=8, C=48, Cout=64, ksize=3)
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float32, 2e-5), (torch.bfloat16, 6e-3)])
+@pytest.mark.parametrize("C,HW,B,act", [(320, 1024, 2, 1), (960, 256, 2, 1), (1280, 64, 3, 0), (2560, 64, 1, 1),
+                                        (640, 300, 2, 0)])
+def test_group_norm(dt, tol, C, HW, B, act):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = (torch.randn(B, HW, C, device=DEV, generator=g) * 2 + 0.5).to(dt)
+    gamma = torch.randn(C, device=DEV, generator=g)
+    beta = torch.randn(C, device=DEV, generator=g)
+    eps = 1e-6 if act == 0 else 1e-5
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, eps).permute(0, 2, 1)
+    if act:
+        ref = F.silu(ref)
+    # input read through a wider pitch (concat slot), output too
+    xin = torch.zeros(B * HW, C + 64, dtype=dt, device=DEV)
+    xin[:, 64:] = x.reshape(B * HW, C)
+    out = torch.empty(B * HW, C, dtype=dt, device=DEV)
+    ops.group_norm(xin[:, 64:], out, gamma, beta, B, HW, eps=eps, act=act)
+    assert rel_l2(out.float(), ref.reshape(B * HW, C)) < tol
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float32, 2e-5), (torch.bfloat16, 6e-3)])
+@pytest.mark.parametrize("C", [320, 640, 1280])
+def test_layer_norm(dt, tol, C):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(2)
+    x = (torch.randn(777, C, device=DEV, generator=g) * 3 - 1).to(dt)
+    gamma = torch.randn(C, device=DEV, generator=g)
+    beta = torch.randn(C, device=DEV, generator=g)
+    out = torch.empty_like(x)
+    ops.layer_norm(x, out, gamma, beta)
+    assert rel_l2(out.float(), F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)) < tol
+
+
+@pytest.mark.parametrize("dt,tol", [(torch.float32, 1e-6), (torch.bfloat16, 6e-3)])
+def test_geglu(dt, tol):
+    ops = _ops()
+    x = torch.randn(513, 2 * 1280, device=DEV).to(dt)
+    out = torch.empty(513, 1280, dtype=dt, device=DEV)
+    ops.geglu(x, out)
+    a, gate = x.float().chunk(2, dim=-1)
+    assert rel_l2(out.float(), a * F.gelu(gate)) < tol
+
+
+def _attn_ref(q, k, v, heads, scale):
+    B, Nq, Cc = q.shape
+    d = Cc // heads
+    sp = lambda t: t.reshape(B, t.shape[1], heads, d).permute(0, 2, 1, 3).float()
+    sim = torch.einsum("bhid,bhjd->bhij", sp(q), sp(k)) * scale
+    o = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), sp(v))
+    return o.permute(0, 2, 1, 3).reshape(B, Nq, Cc)
+
+
+ATTN_CASES = [(2, 8, 256, 256, 40), (1, 8, 1024, 1024, 40), (2, 8, 100, 77, 80), (2, 8, 64, 64, 160),
+              (1, 8, 576, 77, 160), (1, 4, 130, 130, 64)]
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", ATTN_CASES)
+@pytest.mark.parametrize("dt,engine,tol", [(torch.float32, 1, 2e-5), (torch.bfloat16, 1, 6e-3),
+                                           (torch.bfloat16, 2, 1e-2)])
+def test_attention(B, heads, Nq, Nk, d, dt, engine, tol):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(3)
+    Cc = heads * d
+    # q/k/v as column slices of one fused buffer (how the model calls it)
+    if Nq == Nk:
+        qkv = torch.randn(B * Nq, 3 * Cc, device=DEV, generator=g).to(dt)
+        q, k, v = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
+    else:
+        q = torch.randn(B * Nq, Cc, device=DEV, generator=g).to(dt)
+        kv = torch.randn(B * Nk, 2 * Cc, device=DEV, generator=g).to(dt)
+        k, v = kv[:, :Cc], kv[:, Cc:]
+    out = torch.empty(B * Nq, Cc, dtype=dt, device=DEV)
+    ops.attention(q, k, v, out, B, heads, Nq, Nk, d, engine=engine)
+    ref = _attn_ref(q.reshape(B, Nq, Cc), k.reshape(B, Nk, Cc), v.reshape(B, Nk, Cc), heads, d ** -0.5)
+    assert rel_l2(out.float().reshape(B, Nq, Cc), ref) < tol
+
+
+def test_timestep_embedding_matches_oracle(golden):
+    ops = _ops()
+    t = torch.tensor(golden["temb_t"], device=DEV, dtype=torch.int64)
+    out = torch.empty(t.shape[0], 320, device=DEV)
+    ops.timestep_embedding(t, out)
+    ref = torch.tensor(golden["temb"], device=DEV)
+    assert float((out - ref).abs().max()) < 2e-6
+
+
+def test_layout_bridges_and_upsample():
+    ops = _ops()
+    x = torch.randn(3, 6, 10, 14, device=DEV)
+    for dt in (torch.float32, torch.bfloat16):
+        pm = torch.empty(3 * 10 * 14, 6, dtype=dt, device=DEV)
+        ops.nchw_to_nhwc(x, pm)
+        assert torch.equal(pm.float(), _pm(x).to(dt).float())
+        back = ops.nhwc_to_nchw(pm, 3, 6, 10, 14)
+        assert torch.equal(back, x.to(dt).float())
+    acc = _pm(x).clone()
+    ops.nchw_to_nhwc(x, acc, accumulate=True)
+    assert torch.allclose(acc, 2 * _pm(x))
+    y = torch.randn(2, 64, 5, 7, device=DEV).to(torch.bfloat16)
+    up = torch.empty(2 * 10 * 14, 64, dtype=torch.bfloat16, device=DEV)
+    ops.upsample2x(_pm(y.float()).to(torch.bfloat16), up, 2, 5, 7)
+    assert torch.equal(up, _pm(F.interpolate(y.float(), scale_factor=2, mode="nearest")).to(torch.bfloat16))
+
+
+def test_cfg_ddim_step_bit_exact():
+    """Same fp32 op order as cldm/ddim_hacked.py:193,218,229-233 -> bit-identical to torch."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    shape = (4, 4, 32, 32)
+    eu, ec, x, nz = (torch.randn(shape, device=DEV, generator=g) for _ in range(4))
+    for a_t, a_prev, sigma, scale, temp in ((0.5, 0.6, 0.0, 9.0, 1.0), (0.00577550008893013, 0.007281727157533169,
+                                                                      0.3, 7.5, 0.8)):
+        s1m = math.sqrt(1 - a_t)
+        coef = torch.tensor([a_t, a_prev, sigma, s1m, scale, temp], dtype=torch.float32, device=DEV)
+        xp, p0 = torch.empty_like(x), torch.empty_like(x)
+        ops.cfg_ddim_step(eu, ec, x, nz if sigma else None, coef, xp, p0)
+        full = lambda v: torch.full((4, 1, 1, 1), v, device=DEV)
+        e = eu + scale * (ec - eu)
+        r_p0 = (x - full(s1m) * e) / full(a_t).sqrt()
+        r_xp = full(a_prev).sqrt() * r_p0 + (1. - full(a_prev) - full(sigma) ** 2).sqrt() * e + full(sigma) * nz * temp
+        assert torch.equal(p0, r_p0)
+        assert torch.equal(xp, r_xp)

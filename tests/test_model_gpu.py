@@ -1,0 +1,167 @@
+"""End-to-end parity of the CUDA path (through the reference-signature classes and the C-ABI) against
+
+* golden vectors produced by the reference itself (tests/golden/cldm_v15_golden.npz), and
+* the oracle (oracle/cldm_oracle.py) evaluated in fp32 on the same GPU with TF32 off.
+
+Gates (BASELINE.json north_star): per-step eps rel-L2 <= 1e-4 in fp32 mode, <= 1e-2 in bf16 mode;
+final-latent cosine >= 0.999.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+CASES = {
+    "cfg1": (1, 256, 256, None, False),
+    "lat8": (2, 64, 64, None, False),
+    "rect": (1, 192, 128, [0.5 + 0.1 * i for i in range(13)], False),
+    "midonly": (1, 128, 128, None, True),
+}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_grad_enabled(False)
+    yield
+    torch.set_grad_enabled(True)
+
+
+@pytest.fixture(scope="module")
+def models(cfg, state_dict_cpu):
+    from prompt_diffusion_b200 import ControlLDM
+    out = {}
+    for mode in ("fp32", "bf16"):
+        out[mode] = ControlLDM(cfg, mode=mode, device=DEV).load_state_dict(state_dict_cpu)
+    torch.cuda.synchronize()
+    return out
+
+
+def _cfg_inputs(cfg, b, H, W, device=DEV):
+    from prompt_diffusion_b200.synth import make_conds, synthetic_inputs
+    inp = synthetic_inputs(cfg, b, H, W, seed=2)          # CPU generators: same bits as the golden run
+    inp = {k: v.to(device) for k, v in inp.items()}
+    cond, un = make_conds(inp)
+    x_in = torch.cat([inp["x_T"]] * 2)
+    c_in = {k: [torch.cat([un[k][0], cond[k][0]])] for k in cond}
+    return inp, cond, un, x_in, c_in
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_apply_model_vs_reference_golden(models, golden, cfg, mode, name):
+    b, H, W, scales, only_mid = CASES[name]
+    model = models[mode]
+    _, _, _, x_in, c_in = _cfg_inputs(cfg, b, H, W)
+    t = torch.tensor(golden[f"{name}_t"], dtype=torch.long, device=DEV)
+    model.control_scales = [1.0] * 13 if scales is None else list(scales)
+    model.only_mid_control = only_mid
+    try:
+        eps = model.apply_model(x_in, t, c_in)
+        eps2 = model.apply_model(x_in, t, c_in)              # second call exercises the hint / K-V caches
+    finally:
+        model.control_scales = [1.0] * 13
+        model.only_mid_control = False
+    assert eps.shape == x_in.shape and eps.dtype == torch.float32
+    err = rel_l2(eps.cpu(), golden[f"{name}_eps"])
+    print(f"[parity] apply_model {name} {mode}: eps rel-L2 = {err:.3e}")
+    assert err <= TOL[mode], (name, mode, err)
+    assert torch.equal(eps, eps2), "cached second call differs"
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_controlnet_forward_vs_reference_golden(models, golden, cfg, mode):
+    """ControlNet.forward(x, timesteps, example_pair, query, context) -> 13 NCHW tensors (cldm.py:302-325)."""
+    _, _, _, x_in, c_in = _cfg_inputs(cfg, 1, 256, 256)
+    t = torch.tensor(golden["cfg1_t"], dtype=torch.long, device=DEV)
+    outs = models[mode].control_model(x=x_in, timesteps=t, example_pair=c_in["example_pair"][0],
+                                      query=c_in["query"][0], context=c_in["c_crossattn"][0])
+    assert len(outs) == 13
+    want_shapes = [(2, 320, 32, 32)] * 3 + [(2, 320, 16, 16)] + [(2, 640, 16, 16)] * 2 + [(2, 640, 8, 8)] + \
+                  [(2, 1280, 8, 8)] * 2 + [(2, 1280, 4, 4)] * 4
+    assert [tuple(o.shape) for o in outs] == want_shapes
+    tol = TOL[mode]
+    assert rel_l2(outs[0][:, :8].cpu(), golden["cfg1_ctrl0"]) <= tol
+    assert rel_l2(outs[12][:, :8].cpu(), golden["cfg1_ctrl12"]) <= tol
+    summ = golden["cfg1_ctrl_summary"]
+    for i, o in enumerate(outs):
+        assert abs(float(o.double().std()) - summ[i, 1]) <= 5 * tol * summ[i, 1] + 1e-7, i
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_unet_forward_consumes_control(models, golden, cfg, mode):
+    """ControlledUnetModel.forward pops the caller's control list (cldm.py:35,41) and, fed with the
+    ControlNet's scaled outputs, reproduces apply_model."""
+    model = models[mode]
+    _, _, _, x_in, c_in = _cfg_inputs(cfg, 1, 256, 256)
+    t = torch.tensor(golden["cfg1_t"], dtype=torch.long, device=DEV)
+    ctx = c_in["c_crossattn"][0]
+    control = model.control_model(x=x_in, timesteps=t, example_pair=c_in["example_pair"][0],
+                                  query=c_in["query"][0], context=ctx)
+    eps = model.model.diffusion_model(x=x_in, timesteps=t, context=ctx, control=control, only_mid_control=False)
+    assert control == []
+    # bf16: the unfused route rounds the 13 controls once more than the fused one
+    assert rel_l2(eps.cpu(), golden["cfg1_eps"]) <= TOL[mode] * (1.0 if mode == "fp32" else 1.5)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_sampler_config1_vs_reference_golden(models, golden, cfg, mode):
+    """BASELINE config 1: 256^2, batch 1, 20 DDIM steps, CFG 9, eta 0 through DDIMSampler.sample."""
+    from prompt_diffusion_b200 import DDIMSampler
+    inp, cond, un, _, _ = _cfg_inputs(cfg, 1, 256, 256)
+    smp = DDIMSampler(models[mode])
+    calls = []
+    samples, inter = smp.sample(20, 1, (4, 32, 32), cond, verbose=False, eta=0.0, x_T=inp["x_T"],
+                                unconditional_guidance_scale=9.0, unconditional_conditioning=un, log_every_t=5,
+                                callback=calls.append)
+    assert calls == list(range(20))
+    assert len(inter["x_inter"]) == golden["sample_cfg1_x_inter"].shape[0]
+    ref = torch.tensor(golden["sample_cfg1_final"])
+    cos = torch.nn.functional.cosine_similarity(samples.cpu().flatten().double(), ref.flatten().double(), dim=0)
+    err = rel_l2(samples.cpu(), ref)
+    # first step = pure per-step eps parity through the sampler
+    e1 = rel_l2(inter["pred_x0"][1].cpu(), golden["sample_cfg1_pred_x0"][1])
+    print(f"[parity] sampler cfg1 {mode}: cosine = {float(cos):.6f}, final rel-L2 = {err:.3e}, step-1 pred_x0 rel-L2 = {e1:.3e}")
+    assert float(cos) >= 0.999
+    assert err <= (2e-3 if mode == "fp32" else 5e-2)
+    for a, b in zip(inter["x_inter"], golden["sample_cfg1_x_inter"]):
+        assert rel_l2(a.cpu(), b) <= (2e-3 if mode == "fp32" else 5e-2)
+
+
+def test_sampler_eta_noise_path(models, golden, cfg):
+    """eta > 0: noise is drawn from torch's RNG each step (ddim_hacked.py:230); with the same seed on the
+    same device type results are reproducible, and sigma_t > 0 actually perturbs the trajectory."""
+    from prompt_diffusion_b200 import DDIMSampler
+    inp, cond, _, _, _ = _cfg_inputs(cfg, 1, 128, 128)
+    smp = DDIMSampler(models["fp32"])
+    torch.manual_seed(1234)
+    a, _ = smp.sample(4, 1, (4, 16, 16), cond, verbose=False, eta=0.7, x_T=inp["x_T"])
+    torch.manual_seed(1234)
+    b, _ = smp.sample(4, 1, (4, 16, 16), cond, verbose=False, eta=0.7, x_T=inp["x_T"])
+    c, _ = smp.sample(4, 1, (4, 16, 16), cond, verbose=False, eta=0.0, x_T=inp["x_T"])
+    assert torch.equal(a, b)
+    assert rel_l2(a.cpu(), c.cpu()) > 1e-2
+    assert float(smp.ddim_sigmas.abs().max()) == 0.0
+
+
+def test_apply_model_config2_shape_vs_oracle_gpu(models, cfg, state_dict_cpu):
+    """A slice of BASELINE config 2 (512^2 -> 64x64 latent, 4096-token self-attention), batch 1 (B_eff 2):
+    CUDA path vs the oracle run in fp32 on this GPU."""
+    from oracle import cldm_oracle as O
+    sd_gpu = {k: v.to(DEV) for k, v in state_dict_cpu.items()}
+    _, _, _, x_in, c_in = _cfg_inputs(cfg, 1, 512, 512)
+    t = torch.tensor([501, 501], dtype=torch.long, device=DEV)
+    ref = O.apply_model(sd_gpu, cfg, x_in, t, c_in)
+    del sd_gpu
+    for mode in ("fp32", "bf16"):
+        eps = models[mode].apply_model(x_in, t, c_in)
+        err = rel_l2(eps, ref)
+        print(f"[parity] apply_model 512^2 {mode} vs oracle(gpu fp32): eps rel-L2 = {err:.3e}")
+        assert err <= TOL[mode], (mode, err)
