@@ -52,6 +52,12 @@ uint64_t pd_launch_count(void);
 /* 1 when the current device is sm_100 (tcgen05/TMEM present) */
 int pd_device_is_sm100(void);
 
+/* Measurement hook (bench.py roofline leg): per-launch CUDA-event timing of the tcgen05 engine.
+ * pd_prof_enable(1) clears the log and starts recording, pd_prof_read() synchronises and returns the
+ * summed kernel milliseconds, the summed algorithmic FLOPs (2*M*Cout*K per launch) and the launch count. */
+int pd_prof_enable(int on);
+int pd_prof_read(double* total_ms, double* total_flops, uint64_t* launches);
+
 /*
  * Convolution / linear as one implicit GEMM.
  *   replaces  nn.Conv2d 3x3 / 1x1 (conv_nd, util.py:221-231) as used by ResBlock
@@ -130,9 +136,12 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
                     int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
                     int32_t Nk, int32_t d, float scale, int32_t dtype, int32_t engine, void* stream);
 
-/* timestep_embedding (util.py:154-174): t [B] int64 -> [B, dim] = [cos(t f), sin(t f)]. */
-int pd_timestep_embedding(const int64_t* t, void* out, int32_t ldo, int32_t B, int32_t dim,
-                          float max_period, int32_t out_dtype, void* stream);
+/* timestep_embedding (util.py:154-174): t [B] int64 -> [B, dim] = [cos(t f), sin(t f)].
+ * `freqs` (optional, dim/2 device floats) is the frequency table exp(-ln(max_period) j / half) as the
+ * caller's host library rounds it (the reference builds it with torch.exp on the host, util.py:165-167);
+ * NULL = computed in-kernel (may differ from a given host exp() by 1 ulp, i.e. ~5e-5 in cos(981 f)). */
+int pd_timestep_embedding(const int64_t* t, const float* freqs, void* out, int32_t ldo, int32_t B,
+                          int32_t dim, float max_period, int32_t out_dtype, void* stream);
 
 /* elementwise SiLU (nn.SiLU between hint-stack convs is fused via pd_conv_params.act;
  * this one serves emb_layers' leading SiLU, openaimodel.py:217-218). */

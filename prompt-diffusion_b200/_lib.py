@@ -39,6 +39,8 @@ SIGNATURES = {
     "pd_abi_version": (C.c_int, []),
     "pd_launch_count": (C.c_uint64, []),
     "pd_device_is_sm100": (C.c_int, []),
+    "pd_prof_enable": (C.c_int, [C.c_int]),
+    "pd_prof_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "pd_conv2d": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
     "pd_repack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),
     "pd_group_norm_scratch_floats": (C.c_int64, [C.c_int32]),
@@ -55,7 +57,7 @@ SIGNATURES = {
     "pd_attention_ex": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                   C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
-    "pd_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+    "pd_timestep_embedding": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_float, C.c_int32, C.c_void_p]),
     "pd_silu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "pd_nchw_to_nhwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -168,8 +168,8 @@ __global__ void upsample2x_scalar_kernel(const T* __restrict__ x, int ldx, T* __
 
 // ---- timestep embedding -------------------------------------------------------------
 template <typename T>
-__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, T* __restrict__ out, int ldo,
-                                          int B, int dim, float neg_log_period) {
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
+                                          T* __restrict__ out, int ldo, int B, int dim, float neg_log_period) {
   int half = dim / 2;
   int total = B * half;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -178,7 +178,7 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, T* __re
     // Only B*dim/2 elements: evaluate exp/cos/sin in double and round once, so each fp32
     // intermediate is the correctly rounded value the reference's fp32 ops aim for.
     float e = __fdiv_rn(__fmul_rn(neg_log_period, (float)j), (float)half);
-    float freq = (float)exp((double)e);
+    float freq = freqs != nullptr ? freqs[j] : (float)exp((double)e);
     float arg = __fmul_rn((float)t[b], freq);
     Dt<T>::st(out + (int64_t)b * ldo + j, (float)cos((double)arg));
     Dt<T>::st(out + (int64_t)b * ldo + half + j, (float)sin((double)arg));
@@ -343,16 +343,16 @@ int pd_upsample2x(const void* x, int32_t ldx, void* out, int32_t ldo, int32_t B,
   return check_launch("pd_upsample2x");
 }
 
-int pd_timestep_embedding(const int64_t* t, void* out, int32_t ldo, int32_t B, int32_t dim,
+int pd_timestep_embedding(const int64_t* t, const float* freqs, void* out, int32_t ldo, int32_t B, int32_t dim,
                           float max_period, int32_t out_dtype, void* stream) {
   PD_REQUIRE(t && out && B > 0 && dim >= 2 && ldo >= dim, "pd_timestep_embedding: bad args");
   cudaStream_t s = (cudaStream_t)stream;
   int g = grid_for((int64_t)B * (dim / 2), 128);
   float nlp = (float)(-log((double)max_period));  // python: -math.log(max_period) -> fp32 scalar
   if (out_dtype == PD_F32)
-    timestep_embedding_kernel<float><<<g, 128, 0, s>>>(t, (float*)out, ldo, B, dim, nlp);
+    timestep_embedding_kernel<float><<<g, 128, 0, s>>>(t, freqs, (float*)out, ldo, B, dim, nlp);
   else if (out_dtype == PD_BF16)
-    timestep_embedding_kernel<bf16><<<g, 128, 0, s>>>(t, (bf16*)out, ldo, B, dim, nlp);
+    timestep_embedding_kernel<bf16><<<g, 128, 0, s>>>(t, freqs, (bf16*)out, ldo, B, dim, nlp);
   else
     PD_REQUIRE(false, "pd_timestep_embedding: bad dtype %d", out_dtype);
   return check_launch("pd_timestep_embedding");

@@ -18,6 +18,8 @@
 //   with an arbitrary row pitch (writes land directly in channel-concat slots).
 #include <cuda.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace pd {
@@ -258,7 +260,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int n = n0 + cc + g * 8;
-            if (n < a.Cout) {   // Cout % 8 == 0 (host-checked): an 8-column group is all-in or all-out
+            // BN % 16 == 0 and Cout % 8 == 0 (host-checked): an 8-column group is all-in or all-out
+            if (cc + g * 8 < a.BN && n < a.Cout) {
               float f[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
@@ -327,6 +330,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 }
 
 // ---- host side --------------------------------------------------------------------------------------
+// Optional per-launch CUDA-event timing of this engine (bench.py's roofline leg; never on in a
+// captured graph): every launch is bracketed by two events on ITS stream and logged with its
+// algorithmic FLOPs (2*M*Cout*K of the layer, padding excluded).
+struct ProfRec { cudaEvent_t e0, e1; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -480,8 +489,48 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   }
   int64_t tiles = (int64_t)a.m_tiles * a.n_tiles;
   int grid = (int)(tiles < sms ? tiles : sms);
+  ProfRec rec;
+  if (g_prof_on) {
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    rec.flops = 2.0 * (double)p->B * Ho * Wo * (double)p->Cout * (double)(p->ksize * p->ksize * p->C + p->C2);
+    cudaEventRecord(rec.e0, s);
+  }
   conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(map_a0, map_a1, map_w, a);
+  if (g_prof_on) {
+    cudaEventRecord(rec.e1, s);
+    g_prof.push_back(rec);
+  }
   return check_launch("conv_tc");
 }
+
+}  // namespace pd
+
+extern "C" {
+// enable (1) / disable (0) per-launch timing of the tcgen05 engine; enabling clears the log
+int pd_prof_enable(int on) {
+  for (auto& r : pd::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  pd::g_prof.clear();
+  pd::g_prof_on = on != 0;
+  return 0;
+}
+// synchronises the recorded events and returns totals since pd_prof_enable(1)
+int pd_prof_read(double* total_ms, double* total_flops, uint64_t* launches) {
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : pd::g_prof) {
+    cudaError_t e = cudaEventSynchronize(r.e1);
+    float t = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.e0, r.e1);
+    if (e != cudaSuccess) { pd::set_error("pd_prof_read: %s", cudaGetErrorString(e)); return (int)e; }
+    ms += t; fl += r.flops;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = (uint64_t)pd::g_prof.size();
+  return 0;
+}
+}
+
+namespace pd {
 
 }  // namespace pd

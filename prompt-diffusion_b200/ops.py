@@ -133,11 +133,27 @@ def attention(q, k, v, out, B, heads, Nq, Nk, d, scale=None, engine=0):
     return out
 
 
-def timestep_embedding(t: torch.Tensor, out: torch.Tensor, max_period: float = 10000.0):
+_freq_tables = {}
+
+
+def _freqs(dim: int, max_period: float, device) -> torch.Tensor:
+    """Host-built frequency table, the way the reference builds it (util.py:165-167), uploaded once."""
+    import math
+    key = (dim, float(max_period), str(device))
+    f = _freq_tables.get(key)
+    if f is None:
+        half = dim // 2
+        f = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half).to(device)
+        _freq_tables[key] = f
+    return f
+
+
+def timestep_embedding(t: torch.Tensor, out: torch.Tensor, max_period: float = 10000.0, host_freqs: bool = True):
     _cuda(t, out)
     if t.dtype != torch.int64:
         raise TypeError("timesteps must be int64")
-    check(lib.pd_timestep_embedding(t.data_ptr(), out.data_ptr(), _ld(out), t.shape[0], out.shape[1],
+    fr = _freqs(out.shape[1], max_period, out.device) if host_freqs else None
+    check(lib.pd_timestep_embedding(t.data_ptr(), _p(fr), out.data_ptr(), _ld(out), t.shape[0], out.shape[1],
                                     float(max_period), dt_code(out), _stream()), "pd_timestep_embedding")
     return out
 

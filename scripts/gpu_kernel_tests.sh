@@ -12,6 +12,6 @@ run() { # name, timeout, pytest args...
 run simt 600 tests/test_kernels_gpu.py -k "simt or group_norm or layer_norm or geglu or timestep or bridges or cfg_ddim"
 run attn 600 tests/test_kernels_gpu.py -k "attention"
 for i in 0 1 2 3 4 5 6 7 8 9 10 11; do
-  run tc$i 300 tests/test_kernels_gpu.py -k "test_conv_tcgen05_bf16 and case$i-" 
+  run tc$i 300 "tests/test_kernels_gpu.py::test_conv_tcgen05_bf16[case$i]"
 done
 run tcrej 120 tests/test_kernels_gpu.py -k "rejects"

@@ -221,6 +221,8 @@ def test_timestep_embedding_matches_oracle(golden):
     ops.timestep_embedding(t, out)
     ref = torch.tensor(golden["temb"], device=DEV)
     assert float((out - ref).abs().max()) < 2e-6
+    ops.timestep_embedding(t, out, host_freqs=False)      # in-kernel exp(): 1 ulp of freq * t = 981
+    assert float((out - ref).abs().max()) < 1e-4
 
 
 def test_layout_bridges_and_upsample():
