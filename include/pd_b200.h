@@ -57,6 +57,11 @@ int pd_device_is_sm100(void);
  * summed kernel milliseconds, the summed algorithmic FLOPs (2*M*Cout*K per launch) and the launch count. */
 int pd_prof_enable(int on);
 int pd_prof_read(double* total_ms, double* total_flops, uint64_t* launches);
+/* one CSV line per recorded launch (shape, tile choice, milliseconds, TFLOP/s) */
+int pd_prof_dump(const char* path_host);
+/* debugging aid: device buffer of 3*64*2 uint64 that receives CTA 0's per-role (TMA / MMA / epilogue) tile
+ * start/end globaltimer stamps of subsequent tcgen05 launches; NULL switches it off */
+int pd_debug_timeline(void* dev_buf);
 
 /*
  * Convolution / linear as one implicit GEMM.
@@ -107,7 +112,8 @@ int pd_repack_conv_weight(const float* w_oihw, void* w_out, int32_t cout, int32_
 /* GroupNorm(32 groups) + optional SiLU, fp32 statistics.
  *   replaces GroupNorm32 (util.py:217-219) + nn.SiLU in ResBlock.in_layers/out_layers
  *   (openaimodel.py:200-231), UNet `out` (:726-728) and Normalize (attention.py:88-89, eps 1e-6).
- *   `partial` is caller-provided scratch of pd_group_norm_scratch_floats(B) floats. */
+ *   `partial` is caller-provided scratch of pd_group_norm_scratch_floats(B) floats that must be ZERO-filled
+ *   once when allocated (it holds self-resetting arrival counters) and must not be shared by concurrent streams. */
 int64_t pd_group_norm_scratch_floats(int32_t B);
 int pd_group_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const float* gamma,
                   const float* beta, float* partial, int32_t B, int32_t HW, int32_t C,

@@ -41,6 +41,8 @@ SIGNATURES = {
     "pd_device_is_sm100": (C.c_int, []),
     "pd_prof_enable": (C.c_int, [C.c_int]),
     "pd_prof_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "pd_prof_dump": (C.c_int, [C.c_char_p]),
+    "pd_debug_timeline": (C.c_int, [C.c_void_p]),
     "pd_conv2d": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
     "pd_repack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),
     "pd_group_norm_scratch_floats": (C.c_int64, [C.c_int32]),

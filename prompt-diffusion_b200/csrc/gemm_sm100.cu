@@ -26,7 +26,7 @@ namespace pd {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_BUDGET = 227 * 1024 - 2048;
@@ -41,6 +41,8 @@ struct TcArgs {
   int cpt0, nk0, nk1;           // 64-ch blocks per tap, k-blocks of segment 0 / 1
   int bw, bh, bn;               // pixel box of one 128-row M tile
   int tiles_x, tiles_y, tiles_b, m_tiles, n_tiles, BN, stages;
+  unsigned long long* dbg;      // optional timeline buffer [3 roles][64 tiles][2] (globaltimer ns), CTA 0 only
+  int epi_tma;                  // 1: bf16 output staged in smem and written by TMA (residual read by TMA too)
   uint32_t idesc;
 };
 
@@ -93,6 +95,26 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(s_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PD_DBG(role, tileidx, which)                                                        \
+  do {                                                                                      \
+    if (a.dbg != nullptr && blockIdx.x == 0 && (tileidx) < 64)                              \
+      a.dbg[((role) * 64 + (tileidx)) * 2 + (which)] = gtimer();                            \
+  } while (0)
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -135,14 +157,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- the kernel ---------------------------------------------------------------------------------
+// EPI: bit0 residual, bit1 timestep row-vector, bit2 SiLU (bf16 output through smem + TMA store); 8 = fp32 output
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-               const __grid_constant__ CUtensorMap map_w, const TcArgs a) {
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_o64,
+               const __grid_constant__ CUtensorMap map_o32, const __grid_constant__ CUtensorMap map_r64,
+               const __grid_constant__ CUtensorMap map_r32, const TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ __align__(8) uint64_t res_full[4];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -158,7 +185,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tma_prefetch_desc(&map_w);
     if (a.nk1 > 0) tma_prefetch_desc(&map_a1);
     for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI == 8 ? 4 : 8); }
+    for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
+    if (EPI != 8) { tma_prefetch_desc(&map_o64); if (EPI & 1) tma_prefetch_desc(&map_r64); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -181,8 +210,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int tyi = (mt / a.tiles_x) % a.tiles_y;
         const int tbi = mt / (a.tiles_x * a.tiles_y);
         const int x0 = txi * a.bw, y0 = tyi * a.bh, b0 = tbi * a.bn, n0 = nt * a.BN;
+        const int tix = (tile - blockIdx.x) / gridDim.x;
+        PD_DBG(0, tix, 0);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+          if (kb == nkb - 1) PD_DBG(0, tix, 1);
           unsigned char* sa = smem + stage * stage_bytes;
           unsigned char* sb = sa + TC_A_BYTES;
           mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
@@ -211,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
+        PD_DBG(1, it, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase, 300 + stage);
@@ -227,10 +260,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
+        PD_DBG(1, it, 1);
       }
     }
-  } else {
-    // ================= epilogue (warps 2..5) =================
+  } else if (EPI == 8) {
+    // ================= legacy epilogue (fp32 output: the tiny timestep-embedding GEMMs), warps 2..5 =================
+    if (warp < 6) {
     const int qd = warp & 3;               // TMEM lane quadrant this warp may touch
     const int r = qd * 32 + lane;          // accumulator row == tile pixel
     const int rx = r % a.bw;
@@ -248,7 +283,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const bool row_ok = x < a.Wo && y < a.Ho && b < a.B;
       const int64_t m = ((int64_t)b * a.Ho + y) * a.Wo + x;
       const int n0 = nt * a.BN;
-
       mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)acc * 256u;
@@ -319,6 +353,126 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    }
+  } else {
+    // ================= epilogue, warps 2..9: two independent groups of 4 warps =================
+    // Group g owns the 64-column slabs s = g, g+2 of every tile, two 16 KiB staging buffers, one named barrier and
+    // one elected thread that drives its TMA traffic.  Per tile: (a) residual slabs are prefetched by TMA while the
+    // MMAs of the tile are still running, (b) TMEM -> registers, (c) +bias, *alpha, +emb row, +residual, act in
+    // registers/smem (flags are template parameters: no branches in the unrolled code), (d) TMA store.
+    constexpr bool RES = (EPI & 1) != 0, RV = (EPI & 2) != 0, ACT = (EPI & 4) != 0;
+    const int ew = warp - 2, grp = ew >> 2;
+    const int qd = warp & 3;               // TMEM lane quadrant this warp may touch
+    const int r = qd * 32 + lane;          // accumulator row == tile pixel
+    const int rx = r % a.bw;
+    const int ry = (r / a.bw) % a.bh;
+    const int rb = r / (a.bw * a.bh);
+    unsigned char* gstg = smem + a.stages * stage_bytes + grp * 32768;   // 1024-aligned
+    uint64_t* rbar = &res_full[grp * 2];
+    const bool elected = (ew & 3) == 0 && lane == 0;
+    const int bar_id = 1 + grp;
+    const int n64 = a.BN >> 6, nslabs = n64 + ((a.BN & 63) ? 1 : 0);
+    const int ns_mine = (nslabs > grp ? 1 : 0) + (nslabs > grp + 2 ? 1 : 0);
+    const float alpha = a.alpha;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int nt = tile / a.m_tiles, mt = tile - nt * a.m_tiles;
+      const int txi = mt % a.tiles_x;
+      const int tyi = (mt / a.tiles_x) % a.tiles_y;
+      const int tbi = mt / (a.tiles_x * a.tiles_y);
+      const int x0 = txi * a.bw, y0 = tyi * a.bh, b0 = tbi * a.bn;
+      const int x = x0 + rx, y = y0 + ry, b = b0 + rb;
+      const bool row_ok = x < a.Wo && y < a.Ho && b < a.B;
+      const int64_t m = ((int64_t)b * a.Ho + y) * a.Wo + x;
+      const int n0 = nt * a.BN;
+
+      if (elected) {
+        tma_store_wait_read<0>();          // this group's staging buffers are no longer being read
+        if (RES) {
+          for (int i = 0; i < ns_mine; ++i) {
+            const int sl = grp + 2 * i;
+            const int w = sl < n64 ? 64 : 32;
+            mbar_expect_tx(&rbar[i], (uint32_t)(128 * w * 2));
+            tma_load_4d(gstg + i * 16384, w == 64 ? &map_r64 : &map_r32, &rbar[i], n0 + sl * 64, x0, y0, b0);
+          }
+        }
+      }
+      epi_bar_sync(bar_id);
+      mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
+      tc_fence_after();
+      if (ew == 0 && lane == 0) PD_DBG(2, it, 0);
+      const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)acc * 256u;
+      if (ns_mine == 0) {                  // BN <= 64: group 1 has no slab, it only hands the accumulator back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+      const float* rvp = nullptr;
+      if (RV) rvp = a.rowvec + (row_ok ? (m / a.hw_real) : 0) * a.ldrv;
+      for (int i = 0; i < ns_mine; ++i) {
+        const int sl = grp + 2 * i;
+        const int w = sl < n64 ? 64 : 32;
+        const int col0 = sl * 64;
+        unsigned char* stg = gstg + i * 16384;
+        uint32_t v[64];
+        tmem_ld32(t_row + (uint32_t)col0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        if (w == 64) tmem_ld32(t_row + (uint32_t)col0 + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_wait();
+        if (i == ns_mine - 1) {            // accumulator drained by this warp: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (RES) mbar_wait(&rbar[i], (uint32_t)it & 1u, 500 + grp * 2 + i);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (g * 8 < w) {
+            // columns past Cout exist only in a partial last N tile; TMA clips them, the clamp keeps the reads legal
+            const int n = min(n0 + col0 + g * 8, a.Cout - 8);
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+            {
+              const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+              const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
+              f[0] = (f[0] + q0.x) * alpha; f[1] = (f[1] + q0.y) * alpha; f[2] = (f[2] + q0.z) * alpha;
+              f[3] = (f[3] + q0.w) * alpha; f[4] = (f[4] + q1.x) * alpha; f[5] = (f[5] + q1.y) * alpha;
+              f[6] = (f[6] + q1.z) * alpha; f[7] = (f[7] + q1.w) * alpha;
+            }
+            if (RV) {
+              const float4 q0 = __ldg(reinterpret_cast<const float4*>(rvp + n));
+              const float4 q1 = __ldg(reinterpret_cast<const float4*>(rvp + n + 4));
+              f[0] += q0.x; f[1] += q0.y; f[2] += q0.z; f[3] += q0.w;
+              f[4] += q1.x; f[5] += q1.y; f[6] += q1.z; f[7] += q1.w;
+            }
+            // 16-byte chunk g of row r inside the TMA-swizzled slab (SWIZZLE_128B / SWIZZLE_64B rows)
+            const int off = w == 64 ? r * 128 + ((g ^ (r & 7)) << 4) : r * 64 + ((g ^ ((r >> 1) & 3)) << 4);
+            bf16x8* cell = reinterpret_cast<bf16x8*>(stg + off);
+            if (RES) {
+              float rf[8];
+              unpack8(*cell, rf);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += rf[e];
+            }
+            if (ACT) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+            }
+            *cell = pack8(f);
+          }
+        }
+        fence_proxy_async();               // generic-proxy smem writes -> visible to the TMA engine
+        epi_bar_sync(bar_id);
+        if (elected) {
+          tma_store_4d(w == 64 ? &map_o64 : &map_o32, stg, n0 + col0, x0, y0, b0);
+          tma_store_commit();
+        }
+      }
+      if (ew == 0 && lane == 0) PD_DBG(2, it, 1);
+    }
+    if (elected) tma_store_wait_all();     // smem must outlive the bulk stores
   }
 
   tc_fence_before();
@@ -333,8 +487,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 // Optional per-launch CUDA-event timing of this engine (bench.py's roofline leg; never on in a
 // captured graph): every launch is bracketed by two events on ITS stream and logged with its
 // algorithmic FLOPs (2*M*Cout*K of the layer, padding excluded).
-struct ProfRec { cudaEvent_t e0, e1; double flops; };
+struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, ksize, stride, BN, m_tiles, n_tiles, stages, grid; };
 static bool g_prof_on = false;
+static unsigned long long* g_dbg = nullptr;
 static std::vector<ProfRec> g_prof;
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -355,12 +510,13 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, const uint32_t* estrides, const char* what) {
+                      const uint32_t* box, const uint32_t* estrides, const char* what,
+                      CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return PD_ERR_NO_DEVICE; }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                   (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box,
-                  (const cuuint32_t*)estrides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  (const cuuint32_t*)estrides, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("conv_tc: cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)",
@@ -409,6 +565,7 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   a.bias = p->bias; a.rowvec = p->rowvec; a.res = p->res; a.out = p->out;
   a.ldr = p->ldr; a.ldo = p->ldo; a.ldrv = p->ldrv; a.act = p->act; a.out_f32 = p->out_dtype == PD_F32;
   a.alpha = p->alpha;
+  a.dbg = g_dbg;
   a.ksize = p->ksize; a.stride = p->stride; a.C = p->C; a.C2 = p->C2; a.Cout = p->Cout;
   a.cpt0 = p->C / TC_BK;
   a.nk0 = p->ksize * p->ksize * a.cpt0;
@@ -436,17 +593,20 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   // ---- N tile: minimise waves x (BN + fixed per-k-block cost) -------------------------------------
   const int sms = num_sms();
   int best_bn = 64; double best_cost = 1e30;
-  for (int bn = 256; bn >= 32; bn -= 16) {
+  // per k-block a CTA pulls (128 + BN) x 128 B through L2, which (not the MMA) bounds a 1-CTA tile
+  for (int bn = 256; bn >= 32; bn -= 32) {
     int n_tiles = (p->Cout + bn - 1) / bn;
     int64_t tiles = (int64_t)a.m_tiles * n_tiles;
     int64_t waves = (tiles + sms - 1) / sms;
-    double cost = (double)waves * (bn + 40.0);
+    double cost = (double)waves * (bn + 128.0);
     if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; }
   }
   a.BN = best_bn;
   a.n_tiles = (p->Cout + a.BN - 1) / a.BN;
   const int stage_bytes = TC_A_BYTES + a.BN * TC_BK * 2;
-  a.stages = TC_SMEM_BUDGET / stage_bytes;
+  a.epi_tma = p->out_dtype == PD_BF16 ? 1 : 0;
+  const int epi_bytes = a.epi_tma ? 4 * 16384 : 0;
+  a.stages = (TC_SMEM_BUDGET - epi_bytes) / stage_bytes;
   if (a.stages > TC_MAX_STAGES) a.stages = TC_MAX_STAGES;
   if (a.stages < 2) { set_error("conv_tc: not enough shared memory for 2 stages"); return PD_ERR_UNSUPPORTED; }
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -480,12 +640,52 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
     if (rc) return rc;
   }
 
-  const size_t smem = (size_t)a.stages * stage_bytes + 1024;
+  CUtensorMap map_o64 = map_a0, map_o32 = map_a0, map_r64 = map_a0, map_r32 = map_a0;
+  if (a.epi_tma) {
+    uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)gW, (uint64_t)gH, (uint64_t)gB};
+    uint32_t es[4] = {1, 1, 1, 1};
+    for (int which = 0; which < 2; ++which) {
+      const void* base = which == 0 ? p->out : p->res;
+      if (base == nullptr) continue;
+      const uint64_t ld = which == 0 ? (uint64_t)p->ldo : (uint64_t)p->ldr;
+      uint64_t strides[3] = {ld * 2, (uint64_t)gW * ld * 2, (uint64_t)gH * gW * ld * 2};
+      uint32_t box64[4] = {64, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn};
+      uint32_t box32[4] = {32, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn};
+      int rc = encode_map(which == 0 ? &map_o64 : &map_r64, base, 4, dims, strides, box64, es, which == 0 ? "O64" : "R64",
+                          CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+      rc = encode_map(which == 0 ? &map_o32 : &map_r32, base, 4, dims, strides, box32, es, which == 0 ? "O32" : "R32",
+                      CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+  }
+
+  const size_t smem = (size_t)a.stages * stage_bytes + epi_bytes + 1024;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                           const CUtensorMap, const CUtensorMap, const TcArgs);
+  static const KernelFn kernels[9] = {conv_tc_kernel<0>, conv_tc_kernel<1>, conv_tc_kernel<2>, conv_tc_kernel<3>,
+                                      conv_tc_kernel<4>, conv_tc_kernel<5>, conv_tc_kernel<6>, conv_tc_kernel<7>,
+                                      conv_tc_kernel<8>};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-    if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    for (int i = 0; i < 9; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+      if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     attr_set = true;
+  }
+  const int epi = a.epi_tma ? ((p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0)) : 8;
+  static const float* zero_bias = nullptr;   // the TMA epilogue always adds a bias vector
+  if (a.epi_tma && a.bias == nullptr) {
+    if (zero_bias == nullptr) {
+      float* zb = nullptr;
+      if (cudaMalloc(&zb, 16384 * sizeof(float)) != cudaSuccess || cudaMemset(zb, 0, 16384 * sizeof(float)) != cudaSuccess) {
+        set_error("conv_tc: cannot allocate the zero bias"); return PD_ERR_NO_DEVICE;
+      }
+      zero_bias = zb;
+    }
+    if (p->Cout > 16384) { set_error("conv_tc: bias-less launch with Cout > 16384"); return PD_ERR_UNSUPPORTED; }
+    a.bias = zero_bias;
   }
   int64_t tiles = (int64_t)a.m_tiles * a.n_tiles;
   int grid = (int)(tiles < sms ? tiles : sms);
@@ -494,9 +694,12 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
     cudaEventCreate(&rec.e0);
     cudaEventCreate(&rec.e1);
     rec.flops = 2.0 * (double)p->B * Ho * Wo * (double)p->Cout * (double)(p->ksize * p->ksize * p->C + p->C2);
+    rec.M = p->B * Ho * Wo; rec.N = p->Cout; rec.K = p->ksize * p->ksize * p->C + p->C2; rec.ksize = p->ksize;
+    rec.stride = p->stride; rec.BN = a.BN; rec.m_tiles = a.m_tiles; rec.n_tiles = a.n_tiles; rec.stages = a.stages;
+    rec.grid = grid;
     cudaEventRecord(rec.e0, s);
   }
-  conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(map_a0, map_a1, map_w, a);
+  kernels[epi]<<<grid, TC_THREADS, smem, s>>>(map_a0, map_a1, map_w, map_o64, map_o32, map_r64, map_r32, a);
   if (g_prof_on) {
     cudaEventRecord(rec.e1, s);
     g_prof.push_back(rec);
@@ -507,11 +710,28 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
 }  // namespace pd
 
 extern "C" {
+// debugging aid: device buffer of 3*64*2 uint64 receiving CTA 0's per-role tile timeline (NULL = off)
+int pd_debug_timeline(void* dev_buf) { pd::g_dbg = (unsigned long long*)dev_buf; return 0; }
 // enable (1) / disable (0) per-launch timing of the tcgen05 engine; enabling clears the log
 int pd_prof_enable(int on) {
   for (auto& r : pd::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   pd::g_prof.clear();
   pd::g_prof_on = on != 0;
+  return 0;
+}
+// writes one CSV line per recorded launch: M,N,K,ksize,stride,BN,m_tiles,n_tiles,stages,grid,ms,tflops
+int pd_prof_dump(const char* path) {
+  FILE* f = fopen(path, "w");
+  if (!f) { pd::set_error("pd_prof_dump: cannot open %s", path); return PD_ERR_BAD_ARG; }
+  fprintf(f, "M,N,K,ksize,stride,BN,m_tiles,n_tiles,stages,grid,ms,tflops\n");
+  for (auto& r : pd::g_prof) {
+    float t = 0.f;
+    cudaEventSynchronize(r.e1);
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.5f,%.1f\n", r.M, r.N, r.K, r.ksize, r.stride, r.BN, r.m_tiles,
+            r.n_tiles, r.stages, r.grid, t, r.flops / (t * 1e-3) / 1e12);
+  }
+  fclose(f);
   return 0;
 }
 // synchronises the recorded events and returns totals since pd_prof_enable(1)

@@ -102,7 +102,7 @@ def group_norm(x, out, gamma, beta, B, HW, *, groups=32, eps=1e-5, act=PD_ACT_NO
     key = (x.device.index, B)
     scratch = _gn_scratch.get(key)
     if scratch is None:
-        scratch = torch.empty(int(lib.pd_group_norm_scratch_floats(B)), dtype=torch.float32, device=x.device)
+        scratch = torch.zeros(int(lib.pd_group_norm_scratch_floats(B)), dtype=torch.float32, device=x.device)
         _gn_scratch[key] = scratch
     check(lib.pd_group_norm(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), gamma.data_ptr(), beta.data_ptr(),
                             scratch.data_ptr(), B, HW, x.shape[1], groups, float(eps), act, dt_code(x),

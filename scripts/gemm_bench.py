@@ -1,0 +1,56 @@
+"""Micro-benchmark of pd_conv2d (tcgen05 engine) on single layer shapes, CUDA-event timed.
+    python scripts/gemm_bench.py                 # table over the path's dominant shapes
+    python scripts/gemm_bench.py --one M N K ks res   # one shape, few launches (for ncu)
+"""
+import argparse, math, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from prompt_diffusion_b200 import ops
+from prompt_diffusion_b200._lib import PD_ENGINE_TC
+
+dev = "cuda"
+def run(B, H, W, C, N, ks, res, iters=20, warm=3, rowvec=False):
+    M = B * H * W
+    x = torch.randn(M, C, device=dev).to(torch.bfloat16)
+    w = (torch.randn(N, ks * ks * C, device=dev) / math.sqrt(ks * ks * C)).to(torch.bfloat16)
+    bias = torch.randn(N, device=dev)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    r = torch.randn(M, N, device=dev).to(torch.bfloat16) if res else None
+    rv = torch.randn(B, N, device=dev) if rowvec else None
+    # rotate over enough distinct buffers that nothing stays L2-resident between launches
+    for _ in range(warm):
+        ops.conv2d(x, w, out, B, H, W, ksize=ks, bias=bias, res=r, rowvec=rv, engine=PD_ENGINE_TC)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.conv2d(x, w, out, B, H, W, ksize=ks, bias=bias, res=r, rowvec=rv, engine=PD_ENGINE_TC)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / iters * 1e3
+    fl = 2.0 * M * N * ks * ks * C
+    by = (M * C + M * N * (2 if res else 1) + N * ks * ks * C) * 2
+    return us, fl / us / 1e6, by / us / 1e3
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--one", nargs=7, type=int, default=None, help="B H W C N ks res")
+ap.add_argument("--iters", type=int, default=20)
+a = ap.parse_args()
+if a.one:
+    B, H, W, C, N, ks, res = a.one
+    us, tf, gb = run(B, H, W, C, N, ks, bool(res), iters=a.iters, warm=2)
+    print(f"B{B} {H}x{W} C{C}->N{N} k{ks} res={res}: {us:.1f} us  {tf:.0f} TFLOP/s  {gb:.0f} GB/s")
+else:
+    shapes = [  # (B,H,W,C,N,ks,res)
+        (16, 64, 64, 320, 320, 1, 0), (16, 64, 64, 320, 320, 1, 1), (16, 64, 64, 320, 960, 1, 0),
+        (16, 64, 64, 320, 2560, 1, 0), (16, 64, 64, 1280, 320, 1, 1), (16, 64, 64, 320, 320, 3, 0),
+        (16, 64, 64, 320, 320, 3, 1), (16, 64, 64, 640, 640, 3, 0), (16, 32, 32, 640, 640, 1, 1),
+        (16, 32, 32, 640, 5120, 1, 0), (16, 32, 32, 640, 640, 3, 1), (16, 32, 32, 1280, 1280, 3, 0),
+        (16, 16, 16, 1280, 1280, 1, 1), (16, 16, 16, 1280, 10240, 1, 0), (16, 16, 16, 1280, 1280, 3, 1),
+        (16, 16, 16, 2560, 1280, 3, 0), (16, 8, 8, 1280, 1280, 3, 1), (16, 8, 8, 2560, 1280, 3, 0),
+        (16, 8, 8, 1280, 1280, 1, 0),
+    ]
+    print("   B   HxW     C     N ks res |     us   TFLOP/s    GB/s")
+    for s in shapes:
+        us, tf, gb = run(*s, iters=a.iters)
+        print("%4d %3dx%-3d %5d %5d %2d %3d | %7.1f %8.0f %8.0f" % (s[0], s[1], s[2], s[3], s[4], s[5], s[6], us, tf, gb))

@@ -43,3 +43,10 @@ torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print(f"denoise step: {e0.elapsed_time(e1) / a.reps:.3f} ms (GPU events), host issue {host_ms / a.reps:.3f} ms, "
       f"{(_lib.launch_count() - n0) // a.reps} pd_b200 launches/step, pool {model.pool.nbytes() / 2**30:.2f} GiB")
+if os.environ.get("PD_DUMP"):
+    _lib.lib.pd_prof_enable(1)
+    smp.p_sample_ddim(x, cond, ts, index=25, unconditional_guidance_scale=9.0, unconditional_conditioning=un, _c_in=c_in)
+    torch.cuda.synchronize()
+    _lib.lib.pd_prof_dump(os.environ["PD_DUMP"].encode())
+    _lib.lib.pd_prof_enable(0)
+    print("dumped", os.environ["PD_DUMP"])
