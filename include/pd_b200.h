@@ -62,6 +62,8 @@ int pd_prof_dump(const char* path_host);
 /* debugging aid: device buffer of 3*64*2 uint64 that receives CTA 0's per-role (TMA / MMA / epilogue) tile
  * start/end globaltimer stamps of subsequent tcgen05 launches; NULL switches it off */
 int pd_debug_timeline(void* dev_buf);
+/* same for the tcgen05 attention kernel: 6 phases x 32 tiles of uint64 stamps from block (0,0,0) */
+int pd_debug_attention_timeline(void* dev_buf);
 
 /*
  * Convolution / linear as one implicit GEMM.
@@ -137,7 +139,8 @@ int pd_geglu(const void* x, int32_t ldx, void* out, int32_t ldo, int64_t rows, i
 int pd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
                  int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
                  int32_t Nk, int32_t d, float scale, int32_t dtype, void* stream);
-/* same, with an explicit engine: 0 auto, 1 SIMT (fp32 math, any dtype), 2 tensor-core (bf16) */
+/* same, with an explicit engine: 0 auto, 1 SIMT (fp32 math, any dtype), 2 warp-level mma.sync (bf16),
+ * 3 tcgen05/TMEM/TMA (bf16, head dim <= 64) */
 int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
                     int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
                     int32_t Nk, int32_t d, float scale, int32_t dtype, int32_t engine, void* stream);

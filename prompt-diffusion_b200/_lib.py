@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libpd_b200.so")
 PD_F32, PD_BF16 = 0, 1
 PD_ACT_NONE, PD_ACT_SILU = 0, 1
 PD_ENGINE_AUTO, PD_ENGINE_SIMT, PD_ENGINE_TC = 0, 1, 2
-PD_ATTN_AUTO, PD_ATTN_SIMT, PD_ATTN_MMA = 0, 1, 2
+PD_ATTN_AUTO, PD_ATTN_SIMT, PD_ATTN_MMA, PD_ATTN_TC = 0, 1, 2, 3
 
 
 class ConvParams(C.Structure):
@@ -43,6 +43,7 @@ SIGNATURES = {
     "pd_prof_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "pd_prof_dump": (C.c_int, [C.c_char_p]),
     "pd_debug_timeline": (C.c_int, [C.c_void_p]),
+    "pd_debug_attention_timeline": (C.c_int, [C.c_void_p]),
     "pd_conv2d": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
     "pd_repack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),
     "pd_group_norm_scratch_floats": (C.c_int64, [C.c_int32]),

@@ -188,6 +188,12 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
                       ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0 &&
                       ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
                       ((uintptr_t)out % 4) == 0;
+  const bool tc_ok = attention_tc_supported(dtype, d, ldq, ldk, ldv, ldo, q, k, v, out);
+  if (engine == 3 && !tc_ok) {
+    set_error("pd_attention: tcgen05 engine needs sm_100, bf16, d <= 64 (multiple of 8), 16B-aligned tensors and pitches");
+    return PD_ERR_UNSUPPORTED;
+  }
+  if (engine == 3 || (engine == 0 && tc_ok)) return attention_tc(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   if (engine == 2 && !mma_ok) {
     set_error("pd_attention: tensor-core engine needs bf16, d in {32,40,48,64,80,128,160}, 16B-aligned q/k/v");
     return PD_ERR_UNSUPPORTED;

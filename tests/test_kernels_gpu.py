@@ -214,6 +214,33 @@ def test_attention(B, heads, Nq, Nk, d, dt, engine, tol):
     assert rel_l2(out.float().reshape(B, Nq, Cc), ref) < tol
 
 
+TC_ATTN_CASES = [(1, 8, 256, 256, 40), (2, 8, 1024, 1024, 40), (2, 8, 100, 77, 40), (1, 8, 4096, 4096, 40),
+                 (1, 4, 130, 130, 64), (2, 2, 384, 200, 32), (1, 8, 9216 // 4, 9216 // 4, 40)]
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", TC_ATTN_CASES)
+def test_attention_tcgen05(B, heads, Nq, Nk, d):
+    """tcgen05 flash attention (engine 3) vs torch fp32 on the same bf16 operands; tolerance 1e-2 rel-L2
+    (P is rounded to bf16 before the P.V MMA, as in every bf16 flash kernel)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(7)
+    Cc = heads * d
+    if Nq == Nk:
+        qkv = torch.randn(B * Nq, 3 * Cc, device=DEV, generator=g).to(torch.bfloat16)
+        q, k, v = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
+    else:
+        q = torch.randn(B * Nq, Cc, device=DEV, generator=g).to(torch.bfloat16)
+        kv = torch.randn(B * Nk, 2 * Cc, device=DEV, generator=g).to(torch.bfloat16)
+        k, v = kv[:, :Cc], kv[:, Cc:]
+    out = torch.full((B * Nq, Cc + 8), 3.0, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q, k, v, out[:, :Cc], B, heads, Nq, Nk, d, engine=3)
+    torch.cuda.synchronize()
+    assert bool((out[:, Cc:] == 3.0).all()), "wrote past the head columns"
+    ref = _attn_ref(q.reshape(B, Nq, Cc), k.reshape(B, Nk, Cc), v.reshape(B, Nk, Cc), heads, d ** -0.5)
+    err = rel_l2(out[:, :Cc].float().reshape(B, Nq, Cc), ref)
+    assert err < 1e-2, err
+
+
 def test_timestep_embedding_matches_oracle(golden):
     ops = _ops()
     t = torch.tensor(golden["temb_t"], device=DEV, dtype=torch.int64)
