@@ -190,7 +190,7 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
                       ((uintptr_t)out % 4) == 0;
   const bool tc_ok = attention_tc_supported(dtype, d, ldq, ldk, ldv, ldo, q, k, v, out);
   if (engine == 3 && !tc_ok) {
-    set_error("pd_attention: tcgen05 engine needs sm_100, bf16, d <= 64 (multiple of 8), 16B-aligned tensors and pitches");
+    set_error("pd_attention: tcgen05 engine needs sm_100, bf16, d <= 128 (multiple of 8), 16B-aligned tensors and pitches");
     return PD_ERR_UNSUPPORTED;
   }
   if (engine == 3 || (engine == 0 && tc_ok)) return attention_tc(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);

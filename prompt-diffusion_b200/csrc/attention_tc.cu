@@ -1,220 +1,359 @@
-// tcgen05 / TMEM / TMA streaming-softmax attention (bf16) for head dims <= 64 — the d = 40, 4096..9216-token
-// self-attention of the 64x64 / 96x96 latent level and its 77-key cross-attention (CrossAttention.forward,
-// ldm/modules/attention.py:171-193), which dominate the attention time of a denoising step.
+// tcgen05 / TMEM / TMA streaming-softmax attention (bf16) for head dims <= 128 — the d = 40, 4096..9216-token
+// self-attention of the 64x64 / 96x96 latent level, the d = 80 level below it and their 77-key cross-attention
+// (CrossAttention.forward, ldm/modules/attention.py:171-193), which dominate the attention time of a step.
 //
-// One CTA = 128 queries of one (batch, head); two CTAs are resident per SM (112 KiB smem, 256 TMEM columns each),
-// so while one CTA's softmax warps run, the other CTA's MMAs use the tensor pipe.
+// At d = 40 the tensor pipe needs ~380 cycles per 128x128 score tile but the exponentials need >= 1024 cycles of
+// MUFU, so the kernel is organised around keeping the softmax threads busy, not the MMA:
 //
-//   warp 0   : TMA producer — Q once, then K/V tiles of 128 keys into a 2-stage ring.  The tensor maps view
-//              q/k/v as (d, heads, tokens, batch); the 64-wide box over a 40-wide head makes TMA zero-fill
-//              channels 40..63, so no padding pass and no padded copies exist.
-//   warp 1   : MMA issuer — S[128x128] = Q K^T (both K-major, SWIZZLE_128B) into TMEM columns [0,128);
-//              O[128xNP] += P V with P from shared memory (K-major) and the V tile used in place as the
-//              MN-major B operand; O lives in TMEM columns [128, 128+NP).
-//   warps 2-5: softmax — ONE THREAD PER QUERY ROW (TMEM lane == row): row max / sum need no shuffles.
-//              Pass 1 reads S for the max, pass 2 re-reads S, exponentiates (exp2, log2e folded into the scale),
-//              writes P (bf16, swizzled) to smem; O is rescaled in TMEM only when some row max moved.
-//              Epilogue: O / l -> bf16 -> swizzled smem -> TMA store (clips columns >= d and rows >= Nq).
+//   one CTA per SM = 256 queries of one (batch, head) = two 128-query groups (A, B) sharing every K/V tile
+//   (halves the L2 -> smem traffic), 320 threads:
+//   warp 8    : TMA producer — Q (both groups) once, then K and V tiles of 128 keys into two independent rings.
+//               The tensor maps view q/k/v as (d, heads, tokens, batch); a 64-wide box over a 40-wide head makes
+//               TMA zero-fill channels 40..63, so no padding pass and no padded copies exist.
+//   warp 9    : MMA issuer — S_g[128x128] = Q_g K^T (smem x smem) into TMEM; O_g[128xd] += P_g V with the A
+//               operand P_g read FROM TMEM (bf16, written by the softmax threads over the first 64 columns of
+//               S_g) and the V tile used in place as the MN-major B operand.  Issue order per key tile:
+//               PV_a(j), QK_a(j+1), PV_b(j), QK_b(j+1) — the tensor pipe executes in order, so S_g(j+1) can
+//               never overtake the read of P_g(j), and group B's exponentials cover group A's MMA latency.
+//   warps 0-3 : softmax of group A, warps 4-7: group B — ONE THREAD PER QUERY ROW (TMEM lane == row): the row
+//               max / sum need no shuffles.  S is read from TMEM exactly once (128 registers), the max uses
+//               3-input FMNMX, scale-and-subtract is a packed FFMA2, the row sum a packed FADD2, P goes back to
+//               TMEM with tcgen05.st.  O is rescaled lazily: only when a row max grew by more than 2^8 (the
+//               stale reference keeps p <= 256, exact after the final division by l).
+//   epilogue  : O / l -> bf16 -> swizzled smem (the dead Q tile) -> TMA store (clips columns >= d, rows >= Nq).
+//
 #include "tc_ptx.cuh"
 
 namespace pd {
 
-constexpr int FA_BQ = 128, FA_BK = 128, FA_THREADS = 192;
+constexpr int FA_BQ = 128, FA_GROUPS = 2, FA_BK = 128, FA_THREADS = 320, FA_MAX_STAGES = 3;
 constexpr int FA_TILE_BYTES = 128 * 128;   // one [128 rows][64 bf16] SWIZZLE_128B tile
-constexpr int FA_ALIGN_SLACK = 512;
-constexpr int FA_SMEM_BYTES = 7 * FA_TILE_BYTES + 128 + FA_ALIGN_SLACK;
-__device__ unsigned long long* g_fa_dbg = nullptr;   // optional phase timeline (block 0 only)
+constexpr int FA_ALIGN_SLACK = 1024;
+constexpr float FA_RESCALE_THRESHOLD = 8.0f;   // log2 units
+#ifndef FA_ORDERED
+#define FA_ORDERED 0
+#endif
+static unsigned long long* g_fa_dbg_host = nullptr;   // optional phase timeline (block 0 only), passed by value
 
 #define FA_DBG(slot, tile)                                                                       \
   do {                                                                                           \
-    if (g_fa_dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 32) \
-      g_fa_dbg[(slot) * 32 + (tile)] = gtimer();                                                 \
+    if (a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 32) \
+      a.dbg[(slot) * 32 + (tile)] = gtimer();                                                    \
   } while (0)
 
 struct FaArgs {
   int Nq, Nk, d;
-  int kpad;            // d rounded up to 16 (K extent of Q K^T)
-  int npad;            // d rounded up to 16 (N extent of P V)
+  int nd;              // 64-channel chunks per head (1 or 2)
+  int stages;          // depth of the K ring and of the V ring
   float scale_log2;
   uint32_t idesc_s_full, idesc_s_last, idesc_pv;
   int n_last_pad;      // S columns computed for the last K/V tile (multiple of 16)
   int n_last_valid;    // keys actually present in the last tile
   int ntiles;
+  unsigned long long* dbg;   // phase-timeline buffer or nullptr (a kernel argument: no global load on the hot path)
 };
 
-__global__ void __launch_bounds__(FA_THREADS, 2)
+// KP16 = ceil(d / 16): K extent of Q K^T and N extent of P V in units of 16 (compile time so that the single
+// MMA-issuing thread runs a branch-free, fully unrolled instruction stream — it shares an SM sub-partition with
+// two softmax warps and every issue slot it wastes delays the tensor pipe).
+//
+// TMEM (512 columns), d <= 64:  S_a [0,128) | S_b [128,256) | P_a [256,320) | P_b [320,384) | O_a [384,448) | O_b [448,512)
+//   P has its own columns, so Q K^T of tile j+1 is issued as soon as the softmax threads have pulled S(j) into
+//   registers (s_free) and the softmax threads never wait for the tensor pipe.
+// 64 < d <= 128 (ALIAS):        S_a [0,128) | S_b [128,256) | O_a [256,384) | O_b [384,512), P_g over S_g[:, 0:64)
+//   P aliases S; in-order execution of the tensor pipe (PV_g(j) issued before QK_g(j+1)) protects it.
+template <int KP16>
+__global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                     const FaArgs a) {
-  // No static shared memory: two CTAs must fit in one SM (2 x (7 x 16 KiB tiles + barriers + slack + 1 KiB
-  // reserved) <= 228 KiB), so the barriers live behind the tiles in the dynamic allocation.
+  constexpr bool ALIAS = KP16 > 4;
+  constexpr int ND = ALIAS ? 2 : 1;
+  constexpr int KPAD = KP16 * 16;
+  constexpr uint32_t COL_S = 0, COL_P = ALIAS ? 0 : 256, COL_O = ALIAS ? 256 : 384;
+  constexpr uint32_t GSTRIDE_P = ALIAS ? 128 : 64, GSTRIDE_O = ALIAS ? 128 : 64;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  if (threadIdx.x == 0 && (smem - smem_raw) > FA_ALIGN_SLACK) {
-    printf("attention_tc: dynamic smem base misaligned by %d bytes\n", (int)(smem - smem_raw));
-    __trap();
-  }
-  unsigned char* q_s = smem;                              // 16 KiB  (reused as the O staging tile at the end)
-  unsigned char* kv_s = smem + FA_TILE_BYTES;             // 2 stages x (K 16 KiB + V 16 KiB)
-  unsigned char* p_s = smem + 5 * FA_TILE_BYTES;          // 2 x 16 KiB: keys 0..63 | keys 64..127
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * FA_TILE_BYTES);
-  uint64_t& q_full = bars[0]; uint64_t& s_full = bars[1]; uint64_t& p_full = bars[2]; uint64_t& o_final = bars[3];
-  uint64_t* kv_full = bars + 4; uint64_t* kv_empty = bars + 6;
-  uint32_t& tmem_base_slot = *reinterpret_cast<uint32_t*>(bars + 8);
+  const int stages = a.stages;
+  unsigned char* q_s = smem;                                              // [group][chunk] tiles
+  unsigned char* k_s = q_s + FA_GROUPS * ND * FA_TILE_BYTES;              // [stage][chunk]
+  unsigned char* v_s = k_s + stages * ND * FA_TILE_BYTES;                 // [stage][chunk]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + stages * ND * FA_TILE_BYTES);
+  uint64_t& q_full = bars[0];
+  uint64_t* s_full = bars + 1;        // [2]  MMA -> softmax: S_g(j) complete
+  uint64_t* p_full = bars + 3;        // [2]  softmax -> MMA: P_g(j) in TMEM, O_g rescaled
+  uint64_t* o_final = bars + 5;       // [2]
+  uint64_t* k_full = bars + 7;        // [3]
+  uint64_t* k_empty = bars + 10;      // [3]
+  uint64_t* v_full = bars + 13;       // [3]
+  uint64_t* v_empty = bars + 16;      // [3]
+  uint64_t* s_free = bars + 19;       // [2]  softmax -> MMA: S_g(j) is in registers (!ALIAS only)
+  uint64_t* p_free = bars + 21;       // [2]  MMA -> softmax: P_g(j) V(j) retired (!ALIAS only)
+  uint32_t& tmem_base_slot = *reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * FA_BQ, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * (FA_GROUPS * FA_BQ), h = blockIdx.y, b = blockIdx.z;
+  // Roles: warps 0-3 softmax A, 4-7 softmax B, 8 TMA, 9 MMA (the sub-partition arbiter favours high warp ids)
+  constexpr int W_TMA = 8, W_MMA = 9;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_o);
-    mbar_init(&q_full, 1); mbar_init(&s_full, 1); mbar_init(&p_full, 4); mbar_init(&o_final, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(&q_full, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 4); mbar_init(&o_final[g], 1);
+      mbar_init(&s_free[g], 4); mbar_init(&p_free[g], 1);
+    }
+    for (int i = 0; i < FA_MAX_STAGES; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_slot)), "r"(256));
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128u;
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     if (lane == 0) {
-      mbar_expect_tx(&q_full, FA_TILE_BYTES);
-      tma_load_4d(q_s, &map_q, &q_full, 0, h, q0, b);
+      mbar_expect_tx(&q_full, FA_GROUPS * ND * FA_TILE_BYTES);
+      for (int g = 0; g < FA_GROUPS; ++g)
+        for (int c = 0; c < ND; ++c)
+          tma_load_4d(q_s + (g * ND + c) * FA_TILE_BYTES, &map_q, &q_full, c * 64, h, q0 + g * FA_BQ, b);
+      int st = 0; uint32_t ph = 0;
       for (int j = 0; j < a.ntiles; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((uint32_t)(j >> 1) & 1u) ^ 1u, 100 + st);
-        unsigned char* ks = kv_s + st * 2 * FA_TILE_BYTES;
-        mbar_expect_tx(&kv_full[st], 2 * FA_TILE_BYTES);
-        tma_load_4d(ks, &map_k, &kv_full[st], 0, h, j * FA_BK, b);
-        tma_load_4d(ks + FA_TILE_BYTES, &map_v, &kv_full[st], 0, h, j * FA_BK, b);
+        mbar_wait(&k_empty[st], ph ^ 1u, 100 + st);
+        mbar_expect_tx(&k_full[st], ND * FA_TILE_BYTES);
+        for (int c = 0; c < ND; ++c)
+          tma_load_4d(k_s + (st * ND + c) * FA_TILE_BYTES, &map_k, &k_full[st], c * 64, h, j * FA_BK, b);
+        mbar_wait(&v_empty[st], ph ^ 1u, 110 + st);
+        mbar_expect_tx(&v_full[st], ND * FA_TILE_BYTES);
+        for (int c = 0; c < ND; ++c)
+          tma_load_4d(v_s + (st * ND + c) * FA_TILE_BYTES, &map_v, &v_full[st], c * 64, h, j * FA_BK, b);
+        if (++st == stages) { st = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     if (lane == 0) {
-      mbar_wait(&q_full, 0, 200);
-      const uint32_t q_addr = s_u32(q_s), p_addr = s_u32(p_s);
-      for (int j = 0; j < a.ntiles; ++j) {
-        const int st = j & 1;
-        const bool last = j == a.ntiles - 1;
-        const uint32_t k_addr = s_u32(kv_s + st * 2 * FA_TILE_BYTES);
-        const uint32_t v_addr = k_addr + FA_TILE_BYTES;
-        mbar_wait(&kv_full[st], (uint32_t)(j >> 1) & 1u, 300 + st);
-        tc_fence_after();
-        FA_DBG(0, j);
-        // S = Q K^T  (K extent = kpad; channels d..63 of both tiles are TMA zero fill)
-        const uint64_t qd = make_smem_desc(q_addr), kd = make_smem_desc(k_addr);
-        for (int k = 0; k < a.kpad / 16; ++k)
-          umma_bf16(tmem_s, qd + (uint64_t)(2 * k), kd + (uint64_t)(2 * k), last ? a.idesc_s_last : a.idesc_s_full,
-                    k != 0 ? 1u : 0u);
-        umma_commit(&s_full);           // also implies: the previous tile's P V has retired
-        // O += P V once the softmax warps have published P (and rescaled O)
-        mbar_wait(&p_full, (uint32_t)j & 1u, 400);
-        tc_fence_after();
-        FA_DBG(1, j);
-        const int ksteps = last ? (a.n_last_valid + 15) / 16 : FA_BK / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t pd_ = make_smem_desc(p_addr + (uint32_t)(k >> 2) * FA_TILE_BYTES + (uint32_t)(k & 3) * 32u);
-          const uint64_t vd = make_smem_desc_mn(v_addr + (uint32_t)k * 2048u, FA_TILE_BYTES, 1024);
-          umma_bf16(tmem_o, pd_, vd, a.idesc_pv, (j | k) != 0 ? 1u : 0u);
+      // descriptors: only the 14-bit start-address field changes between tiles, so every MMA operand is
+      // base + a compile-time or per-stage constant in the low word
+      const uint64_t qdesc0 = make_smem_desc(s_u32(q_s));
+      const uint64_t kdesc0 = make_smem_desc(s_u32(k_s));
+      const uint64_t vdesc0 = make_smem_desc_mn(s_u32(v_s), FA_TILE_BYTES, 1024);
+      constexpr uint64_t TILE16 = FA_TILE_BYTES >> 4;
+      const uint32_t tm_s = tmem_base + COL_S, tm_p = tmem_base + COL_P, tm_o = tmem_base + COL_O;
+      // S_g = Q_g K^T : K extent KPAD (channels d..KPAD-1 of both operands are TMA zero fill)
+      auto issue_qk = [&](int g, int st_k, uint32_t idesc) {
+        const uint64_t qd = qdesc0 + (uint64_t)(g * ND) * TILE16, kd = kdesc0 + (uint64_t)(st_k * ND) * TILE16;
+#pragma unroll
+        for (int k = 0; k < KP16; ++k) {
+          const uint64_t off = (uint64_t)(k >> 2) * TILE16 + (uint64_t)(k & 3) * 2u;
+          umma_bf16(tm_s + (uint32_t)(g * 128), qd + off, kd + off, idesc, k != 0 ? 1u : 0u);
         }
-        umma_commit(&kv_empty[st]);     // K/V stage may be refilled once these MMAs retire
-        if (last) umma_commit(&o_final);
+        umma_commit(&s_full[g]);
+      };
+      // O_g += P_g V : A = P_g from TMEM (8 columns per 16-key step), B = V tile in place, MN-major
+      auto issue_pv = [&](int g, int st_v, bool first, bool last) {
+        const uint64_t vd = vdesc0 + (uint64_t)(st_v * ND) * TILE16;
+        const uint32_t pa = tm_p + (uint32_t)g * GSTRIDE_P, oa = tm_o + (uint32_t)g * GSTRIDE_O;
+        if (!last) {
+#pragma unroll
+          for (int k = 0; k < FA_BK / 16; ++k)
+            umma_bf16_ts(oa, pa + (uint32_t)(8 * k), vd + (uint64_t)(k * 128), a.idesc_pv, (k != 0 || !first) ? 1u : 0u);
+        } else {
+          const int ksteps = (a.n_last_valid + 15) / 16;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_ts(oa, pa + (uint32_t)(8 * k), vd + (uint64_t)(k * 128), a.idesc_pv, (k != 0 || !first) ? 1u : 0u);
+        }
+      };
+      mbar_wait(&q_full, 0, 200);
+      mbar_wait(&k_full[0], 0, 300);
+      tc_fence_after();
+      FA_DBG(0, 0);
+      const uint32_t id0 = a.ntiles == 1 ? a.idesc_s_last : a.idesc_s_full;
+      issue_qk(0, 0, id0);
+      issue_qk(1, 0, id0);
+      umma_commit(&k_empty[0]);
+      int st = 0; uint32_t ph = 0;          // ring position of tile j
+      for (int j = 0; j < a.ntiles; ++j) {
+        int stn = st + 1; uint32_t phn = ph;
+        if (stn == stages) { stn = 0; phn ^= 1u; }
+        const bool more = j + 1 < a.ntiles, last = !more;
+        const uint32_t idn = (j + 2 == a.ntiles) ? a.idesc_s_last : a.idesc_s_full;
+        if constexpr (!ALIAS) {
+          if (more) {
+            mbar_wait(&k_full[stn], phn, 300 + stn);
+            for (int g = 0; g < FA_GROUPS; ++g) {
+              mbar_wait(&s_free[g], (uint32_t)j & 1u, 450 + g);
+              tc_fence_after();
+              issue_qk(g, stn, idn);
+              if (g == 0) FA_DBG(0, j + 1);
+            }
+            umma_commit(&k_empty[stn]);
+          }
+          mbar_wait(&v_full[st], ph, 310 + st);
+          for (int g = 0; g < FA_GROUPS; ++g) {
+            mbar_wait(&p_full[g], (uint32_t)j & 1u, 400 + g);
+            tc_fence_after();
+            if (g == 0) FA_DBG(1, j);
+            issue_pv(g, st, j == 0, last);
+            umma_commit(last ? &o_final[g] : &p_free[g]);
+          }
+          umma_commit(&v_empty[st]);
+        } else {
+          mbar_wait(&v_full[st], ph, 310 + st);
+          if (more) mbar_wait(&k_full[stn], phn, 300 + stn);
+          for (int g = 0; g < FA_GROUPS; ++g) {
+            mbar_wait(&p_full[g], (uint32_t)j & 1u, 400 + g);
+            tc_fence_after();
+            if (g == 0) FA_DBG(1, j);
+            issue_pv(g, st, j == 0, last);
+            if (g == 1) umma_commit(&v_empty[st]);
+            if (more) {
+              issue_qk(g, stn, idn);
+              if (g == 1) umma_commit(&k_empty[stn]);
+              if (g == 0) FA_DBG(0, j + 1);
+            } else {
+              umma_commit(&o_final[g]);
+            }
+          }
+        }
+        st = stn; ph = phn;
       }
     }
   } else {
     // ---------------- softmax / correction / epilogue: thread == query row ----------------
-    const int qd4 = warp & 3;
+    const int g = warp >> 2;                       // 0: warps 0-3, 1: warps 4-7
+    const int qd4 = warp & 3;                      // TMEM lane quadrant this warp may touch
     const int r = qd4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd4 * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t tmem_s = tmem_base + COL_S + (uint32_t)(g * 128) + lane_off;
+    const uint32_t tmem_p = tmem_base + COL_P + (uint32_t)g * GSTRIDE_P + lane_off;
+    const uint32_t tmem_o = tmem_base + COL_O + (uint32_t)g * GSTRIDE_O + lane_off;
+    const bool dbg = (warp & 3) == 0 && lane == 0;
+    const int dslot = 2 + 4 * g;
+    const float sc = a.scale_log2;
+    float m_ref = -INFINITY, l_run = 0.f;
     for (int j = 0; j < a.ntiles; ++j) {
       const bool last = j == a.ntiles - 1;
-      const int ncols = last ? a.n_last_pad : FA_BK;
-      const int nvalid = last ? a.n_last_valid : FA_BK;
-      mbar_wait(&s_full, (uint32_t)j & 1u, 500);
+      mbar_wait(&s_full[g], (uint32_t)j & 1u, 500 + g);
       tc_fence_after();
-      if (warp == 2 && lane == 0) FA_DBG(2, j);
-      // pass 1: row max
-      float mx = -INFINITY;
-      for (int c = 0; c < ncols; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_s + lane_off + (uint32_t)c, v);
-        tmem_ld_wait();
+      if (dbg) FA_DBG(dslot, j);
+      uint32_t s[128];
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (c + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+      for (int c = 0; c < 4; ++c) tmem_ld32p(tmem_s + (uint32_t)(c * 32), s + c * 32);
+      tmem_ld_wait();
+      if constexpr (!ALIAS) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[g]);    // S_g may be overwritten by Q K^T of the next tile
       }
-      if (warp == 2 && lane == 0) FA_DBG(3, j);
-      const float m_new = fmaxf(m_run, mx * a.scale_log2);
-      const float corr = exp2f(m_run - m_new);      // first tile: exp2(-inf) = 0
-      // pass 2: p = exp2(s*scale - m), row sum, P -> smem (bf16, SWIZZLE_128B K-major)
-      float lsum = 0.f;
-      for (int c = 0; c < ncols; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_s + lane_off + (uint32_t)c, v);
-        tmem_ld_wait();
+      if (last && a.n_last_valid < FA_BK) {
+        const int nv = a.n_last_valid;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float p[8];
+        for (int e = 0; e < 128; ++e)
+          if (e >= nv) s[e] = 0xff800000u;         // -inf: keys past Nk (stale / zero-filled columns)
+      }
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col = c + g * 8 + e;
-            const float pv = exp2f(fmaf(__uint_as_float(v[g * 8 + e]), a.scale_log2, -m_new));
-            p[e] = col < nvalid ? pv : 0.f;
-            lsum += p[e];
+      for (int e = 2; e < 126; e += 4) {
+        mx0 = fmax3(mx0, __uint_as_float(s[e]), __uint_as_float(s[e + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[e + 2]), __uint_as_float(s[e + 3]));
+      }
+      const float mx = fmax3(mx0, mx1, fmaxf(__uint_as_float(s[126]), __uint_as_float(s[127]))) * sc;
+      if (dbg) FA_DBG(dslot + 1, j);
+      // lazy reference update: keep the stale reference unless the row max grew by more than 2^THRESHOLD
+      float corr = 1.0f;
+      if (mx > m_ref + FA_RESCALE_THRESHOLD) {
+        corr = ex2_approx(m_ref - mx);             // first tile: exp2(-inf) = 0
+        m_ref = mx;
+        l_run *= corr;
+      }
+      if (j > 0) {
+        if constexpr (!ALIAS) {                    // P_g(j-1) V(j-1) retired: P_g is free, O_g is complete
+          mbar_wait(&p_free[g], (uint32_t)(j - 1) & 1u, 550 + g);
+          tc_fence_after();
+        }
+        // (ALIAS: s_full(j) was committed after P V(j-1) in issue order, so O_g is complete here too)
+        if (__any_sync(0xffffffffu, corr != 1.0f)) {
+#pragma unroll
+          for (int c = 0; c < KPAD; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(tmem_o + (uint32_t)c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * corr);
+            tmem_st16(tmem_o + (uint32_t)c, o);
           }
-          const int kc = (c >> 3) + g;              // 16-byte chunk index along the key axis (0..15)
-          unsigned char* dst = p_s + (kc >> 3) * FA_TILE_BYTES + r * 128 + (((kc & 7) ^ (r & 7)) << 4);
-          *reinterpret_cast<bf16x8*>(dst) = pack8(p);
         }
       }
-      if (warp == 2 && lane == 0) FA_DBG(4, j);
-      l_run = l_run * corr + lsum;
-      m_run = m_new;
-      // rescale O (already complete for tiles < j: s_full of this tile was committed after their P V)
-      if (j > 0 && __any_sync(0xffffffffu, corr != 1.0f)) {
-        for (int c = 0; c < a.npad; c += 16) {
-          uint32_t o[16];
-          tmem_ld16(tmem_o + lane_off + (uint32_t)c, o);
-          tmem_ld_wait();
+      const float nm = -m_ref;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      // The two groups take turns on the MUFU-bound exponential section (named barriers 3/4 carry the token):
+      // while one group exponentiates at the full SFU rate, the other loads S, takes its max and synchronises,
+      // instead of both stalling on the same pipe and then both idling it.
+#if FA_ORDERED
+      if (g == 0) { if (j > 0) asm volatile("bar.sync 3, 256;" ::: "memory"); }
+      else asm volatile("bar.sync 4, 256;" ::: "memory");
+#endif
+      // scale-and-subtract (packed FFMA2), exp2 (MUFU), row sum (packed FADD2), bf16 pack, P -> TMEM
 #pragma unroll
-          for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * corr);
-          tmem_st16(tmem_o + lane_off + (uint32_t)c, o);
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const int i = c * 32 + e;
+          float x0, x1, x2, x3;
+          ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sc, sc, nm, nm);
+          ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sc, sc, nm, nm);
+          x0 = ex2_approx(x0); x1 = ex2_approx(x1); x2 = ex2_approx(x2); x3 = ex2_approx(x3);
+          fadd2(l0, l1, l0, l1, x0, x1);
+          fadd2(l2, l3, l2, l3, x2, x3);
+          pk[e >> 1] = pack_bf16x2(x0, x1);
+          pk[(e >> 1) + 1] = pack_bf16x2(x2, x3);
         }
-        tmem_st_wait();
+        tmem_st16p(tmem_p + (uint32_t)(c * 16), pk);   // P_g: 64 columns of bf16 pairs
+#if FA_ORDERED
+        if (c == 2) {                                  // hand the SFU over a little early: the tail overlaps
+          if (g == 0) asm volatile("bar.arrive 4, 256;" ::: "memory");
+          else if (!last) asm volatile("bar.arrive 3, 256;" ::: "memory");
+        }
+#endif
       }
-      fence_proxy_async();            // P (generic-proxy smem writes) -> visible to the tensor core's async proxy
+      tmem_st_wait();
+      l_run += (l0 + l1) + (l2 + l3);
+      if (dbg) FA_DBG(dslot + 2, j);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full);
-      if (warp == 2 && lane == 0) FA_DBG(5, j);
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (dbg) FA_DBG(dslot + 3, j);
     }
     // ---------------- epilogue ----------------
-    mbar_wait(&o_final, 0, 600);
+    mbar_wait(&o_final[g], 0, 600 + g);
     tc_fence_after();
     const float inv = 1.0f / l_run;
-    for (int c = 0; c < a.npad; c += 16) {
+    unsigned char* stage_o = q_s + (g * ND) * FA_TILE_BYTES;       // Q_g is dead: every Q K^T has retired
+#pragma unroll
+    for (int c = 0; c < KPAD; c += 16) {
       uint32_t o[16];
-      tmem_ld16(tmem_o + lane_off + (uint32_t)c, o);
+      tmem_ld16(tmem_o + (uint32_t)c, o);
       tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
+      for (int gg = 0; gg < 2; ++gg) {
         float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g * 8 + e]) * inv;
-        const int kc = (c >> 3) + g;
-        *reinterpret_cast<bf16x8*>(q_s + r * 128 + ((kc ^ (r & 7)) << 4)) = pack8(f);   // Q tile is dead by now
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[gg * 8 + e]) * inv;
+        const int kc = (c >> 3) + gg;               // 16-byte chunk along the channel axis
+        *reinterpret_cast<bf16x8*>(stage_o + (kc >> 3) * FA_TILE_BYTES + r * 128 + (((kc & 7) ^ (r & 7)) << 4)) = pack8(f);
       }
     }
     fence_proxy_async();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (warp == 2 && lane == 0) {
-      tma_store_4d(&map_o, q_s, 0, h, q0, b);
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+    if (qd4 == 0 && lane == 0 && q0 + g * FA_BQ < a.Nq) {
+      for (int c = 0; c < ND; ++c) tma_store_4d(&map_o, stage_o + c * FA_TILE_BYTES, c * 64, h, q0 + g * FA_BQ, b);
       tma_store_commit();
       tma_store_wait_all();
     }
@@ -222,9 +361,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -232,7 +371,7 @@ bool attention_tc_supported(int dtype, int d, int ldq, int ldk, int ldv, int ldo
                             const void* v, const void* out) {
   static int sm100 = -1;
   if (sm100 < 0) sm100 = pd_device_is_sm100();
-  return sm100 && dtype == PD_BF16 && d % 8 == 0 && d >= 16 && d <= 64 && ldq % 8 == 0 && ldk % 8 == 0 &&
+  return sm100 && dtype == PD_BF16 && d % 8 == 0 && d >= 16 && d <= 128 && ldq % 8 == 0 && ldk % 8 == 0 &&
          ldv % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 &&
          ((uintptr_t)v % 16) == 0 && ((uintptr_t)out % 16) == 0;
 }
@@ -241,17 +380,19 @@ int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, 
                  int heads, int Nq, int Nk, int d, float scale, cudaStream_t s) {
   FaArgs a;
   a.Nq = Nq; a.Nk = Nk; a.d = d;
-  a.kpad = (d + 15) / 16 * 16;
-  a.npad = (d + 15) / 16 * 16;
+  a.nd = (d + 63) / 64;
+  a.stages = a.nd == 1 ? 3 : 2;
+  const int kpad = (d + 15) / 16 * 16;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.ntiles = (Nk + FA_BK - 1) / FA_BK;
   a.n_last_valid = Nk - (a.ntiles - 1) * FA_BK;
   a.n_last_pad = (a.n_last_valid + 15) / 16 * 16;
+  a.dbg = g_fa_dbg_host;
   // kind::f16 instruction descriptor: fp32 accumulate, bf16 A/B, M = 128 (see gemm_sm100.cu)
   const uint32_t base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
   a.idesc_s_full = base | ((uint32_t)(FA_BK >> 3) << 17);
   a.idesc_s_last = base | ((uint32_t)(a.n_last_pad >> 3) << 17);
-  a.idesc_pv = base | (1u << 16) | ((uint32_t)(a.npad >> 3) << 17);   // B (= V tile) is MN-major
+  a.idesc_pv = base | (1u << 16) | ((uint32_t)(kpad >> 3) << 17);   // B (= V tile) is MN-major
 
   CUtensorMap mq, mk, mv, mo;
   const uint32_t box[4] = {64, 1, 128, 1};
@@ -264,23 +405,31 @@ int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, 
     int rc = encode_map(t[i].m, t[i].p, 4, dims, strides, box, es, t[i].nm);
     if (rc) return rc;
   }
-  const size_t smem = FA_SMEM_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_set = true;
+  const size_t smem = (size_t)(FA_GROUPS * a.nd + 2 * a.stages * a.nd) * FA_TILE_BYTES + 256 + FA_ALIGN_SLACK;
+  dim3 grid((Nq + FA_GROUPS * FA_BQ - 1) / (FA_GROUPS * FA_BQ), heads, B);
+#define FA_LAUNCH(KP)                                                                                              \
+  case KP: {                                                                                                       \
+    static bool attr_set = false;                                                                                  \
+    if (!attr_set) {                                                                                               \
+      cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                           (int)smem);                                                             \
+      if (e != cudaSuccess) { set_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; } \
+      attr_set = true;                                                                                             \
+    }                                                                                                              \
+    attention_tc_kernel<KP><<<grid, FA_THREADS, smem, s>>>(mq, mk, mv, mo, a);                                     \
+  } break;
+  switch (kpad / 16) {
+    FA_LAUNCH(1) FA_LAUNCH(2) FA_LAUNCH(3) FA_LAUNCH(4) FA_LAUNCH(5) FA_LAUNCH(6) FA_LAUNCH(7) FA_LAUNCH(8)
+    default: set_error("attention_tc: unsupported head dim %d", d); return PD_ERR_UNSUPPORTED;
   }
-  dim3 grid((Nq + FA_BQ - 1) / FA_BQ, heads, B);
-  attention_tc_kernel<<<grid, FA_THREADS, smem, s>>>(mq, mk, mv, mo, a);
+#undef FA_LAUNCH
   return check_launch("attention_tc");
 }
 
 }  // namespace pd
 
-// debugging aid: device buffer of 6*32 uint64 receiving block (0,0,0)'s per-tile phase stamps; NULL = off
+// debugging aid: device buffer of 10*32 uint64 receiving block (0,0,0)'s per-tile phase stamps; NULL = off
 extern "C" int pd_debug_attention_timeline(void* dev_buf) {
-  unsigned long long* p = (unsigned long long*)dev_buf;
-  cudaError_t e = cudaMemcpyToSymbol(pd::g_fa_dbg, &p, sizeof(p));
-  return e == cudaSuccess ? 0 : (int)e;
+  pd::g_fa_dbg_host = (unsigned long long*)dev_buf;
+  return 0;
 }

@@ -20,7 +20,7 @@ def run(B, heads, Nq, Nk, d, engine, iters=10):
 print("   B  h    Nq    Nk    d eng |      us  TFLOP/s")
 for (B, h, Nq, Nk, d) in [(16, 8, 4096, 4096, 40), (16, 8, 4096, 77, 40), (16, 8, 1024, 1024, 80), (16, 8, 1024, 77, 80), (32, 8, 9216, 9216, 40)]:
     for eng in (2, 3):
-        if eng == 3 and d > 64: continue
+        if eng == 3 and d > 128: continue
         if Nq > 8000 and eng == 2: continue
         try:
             us, tf = run(B, h, Nq, Nk, d, eng, iters=5 if Nq > 8000 else 10)

@@ -1,17 +1,18 @@
+"""Per-tile phase timeline of CTA (0,0,0) of the tcgen05 attention kernel (globaltimer stamps, us)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from prompt_diffusion_b200 import ops, _lib
-B, h, N, d = 16, 8, 4096, 40
+B, h, N, d = 16, 8, 4096, int(sys.argv[1]) if len(sys.argv) > 1 else 40
 C = h * d; dev = "cuda"
 qkv = torch.randn(B * N, 3 * C, device=dev).to(torch.bfloat16)
 out = torch.empty(B * N, C, device=dev, dtype=torch.bfloat16)
 for _ in range(2): ops.attention(qkv[:, :C], qkv[:, C:2*C], qkv[:, 2*C:], out, B, h, N, N, d, engine=3)
-dbg = torch.zeros(6 * 32, dtype=torch.int64, device=dev)
+dbg = torch.zeros(10 * 32, dtype=torch.int64, device=dev)
 _lib.lib.pd_debug_attention_timeline(dbg.data_ptr())
 ops.attention(qkv[:, :C], qkv[:, C:2*C], qkv[:, 2*C:], out, B, h, N, N, d, engine=3)
 torch.cuda.synchronize(); _lib.lib.pd_debug_attention_timeline(None)
-t = dbg.cpu().reshape(6, 32); t0 = int(t[t > 0].min())
-print("tile | MMA:kv_ready  p_ready | SM: s_ready  max_done  p_written  arrived   (us)")
-for j in range(12):
-    print("%4d | %8.2f %8.2f | %8.2f %8.2f %8.2f %8.2f" % tuple([j] + [(int(t[k, j]) - t0) / 1e3 for k in range(6)]))
+t = dbg.cpu().reshape(10, 32); t0 = int(t[t > 0].min())
+print("tile | MMA: qk_a_issued p_a_seen | A: s_ready max_done p_written arrived | B: s_ready max_done p_written arrived  (us)")
+for j in range(14):
+    print("%4d | %8.2f %8.2f | %8.2f %8.2f %8.2f %8.2f | %8.2f %8.2f %8.2f %8.2f" % tuple([j] + [(int(t[k, j]) - t0) / 1e3 for k in range(10)]))

@@ -215,7 +215,9 @@ def test_attention(B, heads, Nq, Nk, d, dt, engine, tol):
 
 
 TC_ATTN_CASES = [(1, 8, 256, 256, 40), (2, 8, 1024, 1024, 40), (2, 8, 100, 77, 40), (1, 8, 4096, 4096, 40),
-                 (1, 4, 130, 130, 64), (2, 2, 384, 200, 32), (1, 8, 9216 // 4, 9216 // 4, 40)]
+                 (1, 4, 130, 130, 64), (2, 2, 384, 200, 32), (1, 8, 9216 // 4, 9216 // 4, 40),
+                 (2, 8, 1024, 1024, 80), (2, 8, 1024, 77, 80), (1, 4, 300, 513, 128), (1, 2, 640, 1, 40),
+                 (1, 3, 128, 128, 16), (1, 8, 576, 576, 80)]
 
 
 @pytest.mark.parametrize("B,heads,Nq,Nk,d", TC_ATTN_CASES)
