@@ -100,5 +100,17 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")
 
 
+_graph_launches = 0
+
+
+def note_graph_replay(n_kernels: int) -> None:
+    """A replayed CUDA graph re-issues ``n_kernels`` of this library's kernels without passing through the
+    C-ABI entry points; keep the launch counter honest."""
+    global _graph_launches
+    _graph_launches += int(n_kernels)
+
+
 def launch_count() -> int:
-    return int(lib.pd_launch_count())
+    """Kernels of libpd_b200 launched so far: direct launches (counted inside the library) + kernels re-issued
+    by CUDA-graph replays of the denoising step."""
+    return int(lib.pd_launch_count()) + _graph_launches

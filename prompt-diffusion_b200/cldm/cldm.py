@@ -411,6 +411,7 @@ class ControlLDM:
         self.pool = pool
         self.only_mid_control = only_mid_control
         self.control_scales = [1.0] * 13
+        self.supports_step_graph = True     # apply_model is capture-safe once its buffers and caches are warm
         self.parameterization = cfg.parameterization
         self.channels = cfg.in_channels
         self._register_schedule()
@@ -457,6 +458,16 @@ class ControlLDM:
         eps_pm = self._denoise_pm(x_pm, t_dev, ctx_list, list(cond["example_pair"]), cond["query"][0], B, H, W)
         eps = ops.nhwc_to_nchw(eps_pm, B, self.cfg.out_channels, H, W)
         return eps if x_noisy.dtype == torch.float32 else eps.to(x_noisy.dtype)
+
+    @torch.no_grad()
+    def prepare_conditioning(self, cond) -> None:
+        """Fill the step-invariant caches (both nets' context K/V projections, the two hint encoders) for
+        ``cond``; a no-op when they already hold this conditioning.  A captured step graph reads those cache
+        buffers, so the sampler calls this before every replay."""
+        ctx_list = list(cond["c_crossattn"])
+        self.model.diffusion_model.context_kv(ctx_list)
+        self.control_model.context_kv(ctx_list)
+        self.control_model.guided_hint(list(cond["example_pair"]), cond["query"][0])
 
     def _denoise_pm(self, x_pm, t_dev, ctx_list, pair_list, query, B, H, W):
         """UNet encoder -> ControlNet (zero-conv epilogues add scale*control onto the stored skips, in

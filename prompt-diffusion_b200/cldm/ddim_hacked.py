@@ -13,11 +13,77 @@ Differences in mechanism, not in results:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from ..schedule import make_ddim_sampling_parameters, make_ddim_timesteps
+
+
+_STEP_GRAPHS = os.environ.get("PD_B200_STEP_GRAPH", "1") != "0"
+
+
+def step_graphs_enabled() -> bool:
+    return _STEP_GRAPHS
+
+
+def set_step_graphs(on: bool) -> bool:
+    """Switch CUDA-graph replay of the denoising step on/off (off: every kernel is launched eagerly, which
+    per-launch profiling needs).  Returns the previous setting."""
+    global _STEP_GRAPHS
+    prev, _STEP_GRAPHS = _STEP_GRAPHS, bool(on)
+    return prev
+
+
+def _cond_key(conds):
+    """Shapes only: the captured step reads the model's hint / context-K/V cache buffers (static addresses),
+    which ``prepare_conditioning`` refreshes eagerly whenever the conditioning tensors change."""
+    return tuple((k, tuple(t_.shape)) for k in sorted(conds) for t_ in conds[k])
+
+
+def _graph_key(model, x, t, conds, guided, with_noise):
+    return (id(model), tuple(x.shape), str(x.device), bool(guided), bool(with_noise), _cond_key(conds),
+            tuple(float(v) for v in model.control_scales), bool(model.only_mid_control),
+            model.control_model.w is not None and id(model.control_model.w), id(model.model.diffusion_model.w))
+
+
+class _StepGraph:
+    """One denoising step (apply_model at [uncond, cond] + fused CFG/DDIM update) captured into a CUDA graph
+    with static input/output buffers.  Step-invariant caches (hint encoders, context K/V) are filled by the
+    eager warm-up run, so the captured graph holds only per-step work."""
+
+    def __init__(self, sampler, x, t, c, c_in, guided, coef, noise):
+        self.model = sampler.model
+        self.x, self.t = x.clone(), t.clone()
+        self.coef = coef.clone()
+        self.noise = noise.clone() if noise is not None else None
+        self.x_prev, self.pred_x0 = torch.empty_like(x), torch.empty_like(x)
+        run = lambda: sampler._eager_step(self.x, self.t, c, c_in, guided, self.coef, self.noise, self.x_prev,
+                                          self.pred_x0)
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):
+            run()                                  # allocates every pool buffer, fills the caches
+            run()
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.lib.pd_launch_count()
+        with torch.cuda.graph(self.graph):
+            run()
+        self.n_kernels = int(_lib.lib.pd_launch_count() - n0)     # library kernels inside the captured step
+
+    def replay(self, x, t, coef, noise, conds):
+        self.model.prepare_conditioning(conds)     # no-op unless the conditioning tensors changed
+        self.x.copy_(x)
+        self.t.copy_(t)
+        self.coef.copy_(coef)
+        if self.noise is not None:
+            self.noise.copy_(noise)
+        self.graph.replay()
+        _lib.note_graph_replay(self.n_kernels)
+        return self.x_prev.clone(), self.pred_x0.clone()
 
 
 def _noise_like(shape, device, repeat=False):
@@ -34,6 +100,7 @@ class DDIMSampler(object):
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
         self._coef_cache = None
+        self._graphs = None
 
     def register_buffer(self, name, attr):
         # the reference moves tensors to "cuda" here (:17-21); buffers follow the model's device instead
@@ -208,13 +275,6 @@ class DDIMSampler(object):
 
         # CFG branch is taken whenever an unconditional conditioning is given — even at scale 1 (:188)
         guided = unconditional_conditioning is not None
-        if guided:
-            x_in, t_in = torch.cat([x] * 2), torch.cat([t] * 2)
-            c_in = _c_in if _c_in is not None else self._concat_conds(c, unconditional_conditioning)
-            out = model.apply_model(x_in, t_in, c_in)
-            e_u, e_c = out[:b], out[b:]          # == .chunk(2): contiguous halves of a fresh tensor
-        else:
-            e_u, e_c = None, model.apply_model(x, t, c)
 
         if dynamic_threshold is not None:
             raise NotImplementedError()
@@ -222,14 +282,23 @@ class DDIMSampler(object):
         plain = (model.parameterization == "eps" and score_corrector is None and not quantize_denoised
                  and noise_dropout == 0.)
         coef, host_row = self._coef_row(index, use_original_steps, unconditional_guidance_scale, temperature)
-        # the reference draws the noise every step, also when sigma_t == 0 (:230): keep the RNG stream
-        noise = _noise_like(x.shape, device, repeat_noise)
         if plain:
-            x_prev = torch.empty_like(x)
-            pred_x0 = torch.empty_like(x)
-            ops.cfg_ddim_step(e_u, e_c.contiguous(), x, noise if host_row[2] != 0.0 else None, coef,
-                              x_prev, pred_x0)
-            return x_prev, pred_x0
+            c_in = None
+            if guided:
+                c_in = _c_in if _c_in is not None else self._concat_conds(c, unconditional_conditioning)
+            # the reference draws the noise every step, also when sigma_t == 0 (:230): keep the RNG stream
+            noise = _noise_like(x.shape, device, repeat_noise)
+            noise = noise if host_row[2] != 0.0 else None
+            return self._plain_step(x, t, c, c_in, guided, coef, noise)
+
+        if guided:
+            x_in, t_in = torch.cat([x] * 2), torch.cat([t] * 2)
+            c_in = _c_in if _c_in is not None else self._concat_conds(c, unconditional_conditioning)
+            out = model.apply_model(x_in, t_in, c_in)
+            e_u, e_c = out[:b], out[b:]          # == .chunk(2): contiguous halves of a fresh tensor
+        else:
+            e_u, e_c = None, model.apply_model(x, t, c)
+        noise = _noise_like(x.shape, device, repeat_noise)
 
         # ---- rarely used branches: the reference's unfused arithmetic (:193-233) ---------------------------
         model_output = e_c if e_u is None else e_u + unconditional_guidance_scale * (e_c - e_u)
@@ -253,6 +322,33 @@ class DDIMSampler(object):
         if noise_dropout > 0.:
             noise = torch.nn.functional.dropout(noise, p=noise_dropout)
         x_prev = a_prev.sqrt() * pred_x0 + dir_xt + noise
+        return x_prev, pred_x0
+
+    # ---- one denoising step on the fused path: apply_model + CFG combine + DDIM update --------------------
+    def _eager_step(self, x, t, c, c_in, guided, coef, noise, x_prev, pred_x0):
+        b = x.shape[0]
+        if guided:
+            out = self.model.apply_model(torch.cat([x] * 2), torch.cat([t] * 2), c_in)
+            e_u, e_c = out[:b], out[b:]
+        else:
+            e_u, e_c = None, self.model.apply_model(x, t, c)
+        ops.cfg_ddim_step(e_u, e_c.contiguous(), x, noise, coef, x_prev, pred_x0)
+
+    def _plain_step(self, x, t, c, c_in, guided, coef, noise):
+        """Runs the step either eagerly or — for this package's ControlLDM — as ONE replayed CUDA graph
+        (~600 kernel launches per step otherwise cost more host time than a fast GPU step takes)."""
+        if step_graphs_enabled() and getattr(self.model, "supports_step_graph", False) and x.is_cuda:
+            conds = c_in if guided else c
+            key = _graph_key(self.model, x, t, conds, guided, noise is not None)
+            g = self._graphs.get(key) if self._graphs is not None else None
+            if g is None:
+                if self._graphs is None or len(self._graphs) >= 4:
+                    self._graphs = {}
+                g = _StepGraph(self, x, t, c, c_in, guided, coef, noise)
+                self._graphs[key] = g
+            return g.replay(x, t, coef, noise, conds)
+        x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
+        self._eager_step(x, t, c, c_in, guided, coef, noise, x_prev, pred_x0)
         return x_prev, pred_x0
 
     @torch.no_grad()

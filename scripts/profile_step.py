@@ -14,8 +14,11 @@ ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--mode", default="bf16")
+ap.add_argument("--graph", type=int, default=0, help="1: time the CUDA-graph replay of the step instead of eager launches")
 a = ap.parse_args()
 torch.set_grad_enabled(False)
+from prompt_diffusion_b200.cldm.ddim_hacked import set_step_graphs
+set_step_graphs(bool(a.graph))
 dev = "cuda:0"
 sd = synthetic_state_dict(cfg, 0, device=dev)
 model = ControlLDM(cfg, mode=a.mode, device=dev).load_state_dict(sd)
@@ -27,7 +30,7 @@ smp.make_schedule(50, ddim_eta=0.0, verbose=False)
 c_in = smp._concat_conds(cond, un)
 x = inp["x_T"]
 ts = torch.full((a.batch,), 501, device=dev, dtype=torch.long)
-for _ in range(2):
+for _ in range(3):
     smp.p_sample_ddim(x, cond, ts, index=25, unconditional_guidance_scale=9.0, unconditional_conditioning=un, _c_in=c_in)
 torch.cuda.synchronize()
 n0 = _lib.launch_count()
@@ -44,6 +47,7 @@ torch.cuda.profiler.stop()
 print(f"denoise step: {e0.elapsed_time(e1) / a.reps:.3f} ms (GPU events), host issue {host_ms / a.reps:.3f} ms, "
       f"{(_lib.launch_count() - n0) // a.reps} pd_b200 launches/step, pool {model.pool.nbytes() / 2**30:.2f} GiB")
 if os.environ.get("PD_DUMP"):
+    set_step_graphs(False)
     _lib.lib.pd_prof_enable(1)
     smp.p_sample_ddim(x, cond, ts, index=25, unconditional_guidance_scale=9.0, unconditional_conditioning=un, _c_in=c_in)
     torch.cuda.synchronize()
