@@ -62,6 +62,10 @@ int pd_prof_dump(const char* path_host);
 /* debugging aid: device buffer of 3*64*2 uint64 that receives CTA 0's per-role (TMA / MMA / epilogue) tile
  * start/end globaltimer stamps of subsequent tcgen05 launches; NULL switches it off */
 int pd_debug_timeline(void* dev_buf);
+/* tile-shape override of the tcgen05 conv engine: 0 auto, 1 single-CTA 128-row tiles, 2 CTA-pair 256-row tiles */
+int pd_debug_force_cta_group(int32_t cg);
+/* timing experiments on the conv engine (results are WRONG when non-zero): 1 = issue no MMAs, 2 = issue no TMA loads */
+int pd_debug_gemm_mode(int32_t mode);
 /* same for the tcgen05 attention kernel: 6 phases x 32 tiles of uint64 stamps from block (0,0,0) */
 int pd_debug_attention_timeline(void* dev_buf);
 

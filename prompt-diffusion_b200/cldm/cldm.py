@@ -93,6 +93,15 @@ class _Net:
     def buf(self, name, rows, cols, dtype=None, zero=False):
         return self.pool.get(name, rows, cols, self.dt if dtype is None else dtype, zero)
 
+    def latent_buffer(self, name, rows, cx):
+        """Pixel-major copy of the latent as conv_in reads it: in bf16 mode the 4 channels sit in a 64-wide,
+        zero-padded row so that conv_in runs on the tcgen05 engine (only the first ``cx`` columns are ever written)."""
+        self._need_weights()
+        pc = self.w.input_blocks[0][0]
+        if cx != pc.cin:
+            raise ValueError(f"latent has {cx} channels, the model expects {pc.cin}")
+        return self.buf(name, rows, pc.cin_pad, zero=True)
+
     def conv(self, pc: PConv, x, out, B, H, W, **kw):
         return ops.conv2d(x, pc.w, out, B, H, W, ksize=pc.ksize, stride=pc.stride, bias=pc.bias, **kw)
 
@@ -301,7 +310,7 @@ class ControlNet(_Net):
     def forward(self, x, timesteps, example_pair, query, context, **kwargs) -> List[torch.Tensor]:
         B, Cx, H, W = x.shape
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
-        x_pm = self.buf("ctrl.x", B * H * W, Cx)
+        x_pm = self.latent_buffer("ctrl.x", B * H * W, Cx)
         ops.nchw_to_nhwc(x, x_pm)
         outs: List[torch.Tensor] = []
 
@@ -373,14 +382,14 @@ class ControlledUnetModel(_Net):
         M = B * st.H * st.W
         g = self.buf("t_gn", M, self.cfg.model_channels)
         ops.group_norm(o, g, w.out_norm.gamma, w.out_norm.beta, B, st.H * st.W, eps=1e-5, act=PD_ACT_SILU)
-        eps_pm = self.buf("unet.eps", M, self.cfg.out_channels, torch.float32)
-        self.conv(w.out_conv, g, eps_pm, B, st.H, st.W)
-        return eps_pm
+        eps_full = self.buf("unet.eps", M, w.out_conv.cout_pad, torch.float32)
+        self.conv(w.out_conv, g, eps_full, B, st.H, st.W)
+        return eps_full[:, :self.cfg.out_channels]
 
     def forward(self, x, timesteps=None, context=None, control=None, only_mid_control=False, **kwargs):
         B, Cx, H, W = x.shape
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
-        x_pm = self.buf("unet.x", B * H * W, Cx)
+        x_pm = self.latent_buffer("unet.x", B * H * W, Cx)
         ops.nchw_to_nhwc(x, x_pm)
         st = self.encode(x_pm, _to_dev_i64(timesteps, self.device), [context], B, H, W)
         if control is not None:
@@ -452,7 +461,7 @@ class ControlLDM:
         ctx_list = list(cond["c_crossattn"])
         B, Cx, H, W = x_noisy.shape
         x = x_noisy.to(device=self.device, dtype=torch.float32).contiguous()
-        x_pm = unet.buf("ldm.x", B * H * W, Cx)
+        x_pm = unet.latent_buffer("ldm.x", B * H * W, Cx)
         ops.nchw_to_nhwc(x, x_pm)
         t_dev = _to_dev_i64(t, self.device)
         eps_pm = self._denoise_pm(x_pm, t_dev, ctx_list, list(cond["example_pair"]), cond["query"][0], B, H, W)

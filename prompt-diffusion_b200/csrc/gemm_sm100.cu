@@ -16,6 +16,9 @@
 // * Epilogue: tcgen05.ld -> alpha*(acc+bias) + timestep row-vector + residual (ControlNet
 //   zero-conv add / skip / guided hint) -> optional SiLU -> bf16 (or fp32) 16-byte stores
 //   with an arbitrary row pitch (writes land directly in channel-concat slots).
+#include <cstdlib>
+#include <map>
+#include <tuple>
 #include <vector>
 
 #include "tc_ptx.cuh"
@@ -38,8 +41,9 @@ struct TcArgs {
   int ksize, stride, C, C2;
   int cpt0, nk0, nk1;           // 64-ch blocks per tap, k-blocks of segment 0 / 1
   int bw, bh, bn;               // pixel box of one 128-row M tile
-  int tiles_x, tiles_y, tiles_b, m_tiles, n_tiles, BN, stages;
+  int tiles_x, tiles_y, tiles_b, m_tiles, n_tiles, BN, stages;   // BN = N extent of the (CG x 128) x BN tile
   unsigned long long* dbg;      // optional timeline buffer [3 roles][64 tiles][2] (globaltimer ns), CTA 0 only
+  int dbg_mode;                 // timing experiments only (wrong results): 1 = no MMAs issued, 2 = no TMA loads issued
   int epi_tma;                  // 1: bf16 output staged in smem and written by TMA (residual read by TMA too)
   uint32_t idesc;
 };
@@ -52,7 +56,10 @@ struct TcArgs {
 
 // ---- the kernel ---------------------------------------------------------------------------------
 // EPI: bit0 residual, bit1 timestep row-vector, bit2 SiLU (bf16 output through smem + TMA store); 8 = fp32 output
-template <int EPI>
+// CG: 1 = one CTA per 128-row tile; 2 = CTA pair (cluster of 2, tcgen05 cta_group::2) per 256-row tile: each CTA
+// stages its own 128 A rows and HALF of the B tile, which halves the L2 -> smem weight traffic per FLOP (the
+// 1-CTA kernel is bound by exactly that traffic: 128 x (128 + BN) bytes per 128 x BN x 64 MACs).
+template <int EPI, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_o64,
@@ -69,75 +76,102 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // SWIZZLE_128B atoms need 1024-byte aligned stage bases
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int b_bytes = a.BN * TC_BK * 2;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int b_rows = a.BN / CG;            // rows of the B tile this CTA stages
+  const int b_bytes = b_rows * TC_BK * 2;
   const int stage_bytes = TC_A_BYTES + b_bytes;
   const int nkb = a.nk0 + a.nk1;
-  const int num_tiles = a.m_tiles * a.n_tiles;
+  const int pm_tiles = (a.m_tiles + CG - 1) / CG;      // M tiles of CG x 128 rows
+  const int num_tiles = pm_tiles * a.n_tiles;
+  const int worker = blockIdx.x / CG, nworkers = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_w);
     if (a.nk1 > 0) tma_prefetch_desc(&map_a1);
     for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI == 8 ? 4 : 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CG * (EPI == 8 ? 4 : 8)); }
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
     if (EPI != 8) { tma_prefetch_desc(&map_o64); if (EPI & 1) tma_prefetch_desc(&map_r64); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&tmem_base_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's barriers must be initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer (both CTAs of a pair); warp-uniform loop, one elected lane issues =================
+    {
       int stage = 0; uint32_t phase = 0;
       const int pad = a.ksize >> 1;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile / a.m_tiles, mt = tile - nt * a.m_tiles;
+      for (int tile = worker; tile < num_tiles; tile += nworkers) {
+        const int nt = tile / pm_tiles, mt = (tile - nt * pm_tiles) * CG + (int)cta_rank;
         const int txi = mt % a.tiles_x;
         const int tyi = (mt / a.tiles_x) % a.tiles_y;
-        const int tbi = mt / (a.tiles_x * a.tiles_y);
-        const int x0 = txi * a.bw, y0 = tyi * a.bh, b0 = tbi * a.bn, n0 = nt * a.BN;
-        const int tix = (tile - blockIdx.x) / gridDim.x;
-        PD_DBG(0, tix, 0);
+        const int tbi = mt / (a.tiles_x * a.tiles_y);   // >= tiles_b for the phantom half of an odd last pair: TMA zero-fills
+        const int x0 = txi * a.bw, y0 = tyi * a.bh, b0 = tbi * a.bn, n0 = nt * a.BN + (int)cta_rank * b_rows;
+        const int tix = (tile - worker) / nworkers;
+        if (lane == 0) PD_DBG(0, tix, 0);
+        // (tap, channel block) walk of segment 0 kept in counters: no integer divisions on the issue path
+        int cb = 0, dx = 0, dy = 0, wk0 = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-          if (kb == nkb - 1) PD_DBG(0, tix, 1);
+          if (kb == nkb - 1 && lane == 0) PD_DBG(0, tix, 1);
           unsigned char* sa = smem + stage * stage_bytes;
           unsigned char* sb = sa + TC_A_BYTES;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          if (a.dbg_mode == 2) {
+            if (cta_rank == 0 && elect_one()) mbar_arrive(&full_bar[stage]);
+            __syncwarp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          int ac0, ax, ay, wk;
+          const CUtensorMap* am;
           if (kb < a.nk0) {
-            const int tap = kb / a.cpt0;
-            const int c0 = (kb - tap * a.cpt0) * TC_BK;
-            const int dy = tap / a.ksize, dx = tap - dy * a.ksize;
-            tma_load_4d(sa, &map_a0, &full_bar[stage], c0, x0 * a.stride + dx - pad, y0 * a.stride + dy - pad, b0);
-            tma_load_2d(sb, &map_w, &full_bar[stage], tap * a.C + c0, n0);
+            am = &map_a0; ac0 = cb * TC_BK; ax = x0 * a.stride + dx - pad; ay = y0 * a.stride + dy - pad; wk = wk0;
+            wk0 += TC_BK;                                  // weights are tap-major, channel-minor: K advances linearly
+            if (++cb == a.cpt0) { cb = 0; if (++dx == a.ksize) { dx = 0; ++dy; } }
           } else {
             const int c0 = (kb - a.nk0) * TC_BK;
-            tma_load_4d(sa, &map_a1, &full_bar[stage], c0, x0, y0, b0);
-            tma_load_2d(sb, &map_w, &full_bar[stage], a.ksize * a.ksize * a.C + c0, n0);
+            am = &map_a1; ac0 = c0; ax = x0; ay = y0; wk = a.ksize * a.ksize * a.C + c0;
           }
+          if (elect_one()) {
+            // the even CTA's barrier collects the bytes of both CTAs' loads
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(CG * stage_bytes));
+            if (CG == 2) {
+              tma_load_4d_2sm(sa, am, &full_bar[stage], ac0, ax, ay, b0);
+              tma_load_2d_2sm(sb, &map_w, &full_bar[stage], wk, n0);
+            } else {
+              tma_load_4d(sa, am, &full_bar[stage], ac0, ax, ay, b0);
+              tma_load_2d(sb, &map_w, &full_bar[stage], wk, n0);
+            }
+          }
+          __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (even CTA of a pair); warp-uniform loop, one elected lane issues =================
+    if (cta_rank == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
-        PD_DBG(1, it, 0);
+        if (lane == 0) PD_DBG(1, it, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase, 300 + stage);
@@ -145,16 +179,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint32_t sa = s_u32(smem + stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa);
           const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TC_BK / 16; ++k) {
+              if (a.dbg_mode == 1) break;
+              // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 field
+              if (CG == 2) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
+            if (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+            // accumulator complete -> epilogue (of both CTAs)
+            if (kb == nkb - 1) { if (CG == 2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]); }
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
-        PD_DBG(1, it, 1);
+        if (lane == 0) PD_DBG(1, it, 1);
       }
     }
   } else if (EPI == 8) {
@@ -166,10 +207,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int ry = (r / a.bw) % a.bh;
     const int rb = r / (a.bw * a.bh);
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int nt = tile / a.m_tiles, mt = tile - nt * a.m_tiles;
+      const int nt = tile / pm_tiles, mt = (tile - nt * pm_tiles) * CG + (int)cta_rank;
       const int txi = mt % a.tiles_x;
       const int tyi = (mt / a.tiles_x) % a.tiles_y;
       const int tbi = mt / (a.tiles_x * a.tiles_y);
@@ -245,7 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
     }
     }
   } else {
@@ -269,10 +310,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int ns_mine = (nslabs > grp ? 1 : 0) + (nslabs > grp + 2 ? 1 : 0);
     const float alpha = a.alpha;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int nt = tile / a.m_tiles, mt = tile - nt * a.m_tiles;
+      const int nt = tile / pm_tiles, mt = (tile - nt * pm_tiles) * CG + (int)cta_rank;
       const int txi = mt % a.tiles_x;
       const int tyi = (mt / a.tiles_x) % a.tiles_y;
       const int tbi = mt / (a.tiles_x * a.tiles_y);
@@ -301,7 +342,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       if (ns_mine == 0) {                  // BN <= 64: group 1 has no slab, it only hands the accumulator back
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
       }
       const float* rvp = nullptr;
       if (RV) rvp = a.rowvec + (row_ok ? (m / a.hw_real) : 0) * a.ldrv;
@@ -317,7 +358,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (i == ns_mine - 1) {            // accumulator drained by this warp: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
         }
         if (RES) mbar_wait(&rbar[i], (uint32_t)it & 1u, 500 + grp * 2 + i);
 #pragma unroll
@@ -370,10 +411,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // no CTA of a pair may exit while the other still signals it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -381,8 +423,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 // Optional per-launch CUDA-event timing of this engine (bench.py's roofline leg; never on in a
 // captured graph): every launch is bracketed by two events on ITS stream and logged with its
 // algorithmic FLOPs (2*M*Cout*K of the layer, padding excluded).
-struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, ksize, stride, BN, m_tiles, n_tiles, stages, grid; };
+struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, ksize, stride, BN, m_tiles, n_tiles, stages, grid, cg; };
 static bool g_prof_on = false;
+static int g_dbg_mode = 0;
+static int g_force_cg = 0;   // 0 auto, 1 single-CTA tiles only, 2 CTA pairs whenever the epilogue allows (tests / A-B timing)
 static unsigned long long* g_dbg = nullptr;
 static std::vector<ProfRec> g_prof;
 EncodeTiledFn get_encode_fn() {
@@ -446,7 +490,7 @@ bool conv2d_tc_supported(const pd_conv_params* p, const char** why) {
   return true;
 }
 
-int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
+static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg) {
   TcArgs a;
   const int pad = p->ksize / 2;
   const int Ho = (p->H + 2 * pad - p->ksize) / p->stride + 1;
@@ -455,6 +499,7 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   a.ldr = p->ldr; a.ldo = p->ldo; a.ldrv = p->ldrv; a.act = p->act; a.out_f32 = p->out_dtype == PD_F32;
   a.alpha = p->alpha;
   a.dbg = g_dbg;
+  a.dbg_mode = g_dbg_mode;
   a.ksize = p->ksize; a.stride = p->stride; a.C = p->C; a.C2 = p->C2; a.Cout = p->Cout;
   a.cpt0 = p->C / TC_BK;
   a.nk0 = p->ksize * p->ksize * a.cpt0;
@@ -479,26 +524,34 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   a.tiles_b = (gB + a.bn - 1) / a.bn;
   a.m_tiles = a.tiles_x * a.tiles_y * a.tiles_b;
 
-  // ---- N tile: minimise waves x (BN + fixed per-k-block cost) -------------------------------------
+  // ---- tile shape: CTA pair or single CTA, N extent ----------------------------------------------------
+  // Per 64-deep k-block a CTA issues 4 MMAs (2*BN tensor cycles) and pulls 128 x (128 + BN/CG) bytes through L2;
+  // at ~39 B/clk/SM of L2 bandwidth (measured: 10.9 TB/s over 148 SMs) the second term dominates, which is why
+  // the pair (half the B traffic per CTA) wins whenever there are enough tiles to fill the machine.
   const int sms = num_sms();
-  int best_bn = 64; double best_cost = 1e30;
-  // per k-block a CTA pulls (128 + BN) x 128 B through L2, which (not the MMA) bounds a 1-CTA tile
-  for (int bn = 256; bn >= 32; bn -= 32) {
-    int n_tiles = (p->Cout + bn - 1) / bn;
-    int64_t tiles = (int64_t)a.m_tiles * n_tiles;
-    int64_t waves = (tiles + sms - 1) / sms;
-    double cost = (double)waves * (bn + 128.0);
-    if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; }
+  a.epi_tma = p->out_dtype == PD_BF16 ? 1 : 0;
+  int best_bn = 64, best_cg = 1; double best_cost = 1e30;
+  const int cg_max = (a.epi_tma && force_cg != 1) ? 2 : 1;
+  for (int cg = cg_max; cg >= (force_cg == 2 && cg_max == 2 ? 2 : 1); --cg) {
+    for (int bn = 256; bn >= 32; bn -= 32) {
+      int n_tiles = (p->Cout + bn - 1) / bn;
+      int64_t tiles = (int64_t)((a.m_tiles + cg - 1) / cg) * n_tiles;
+      int64_t workers = sms / cg;
+      int64_t waves = (tiles + workers - 1) / workers;
+      double per_kb = fmax(2.0 * bn, 3.3 * (128.0 + (double)bn / cg));
+      double cost = (double)waves * per_kb;
+      if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; best_cg = cg; }
+    }
   }
+  const int CGv = best_cg;
   a.BN = best_bn;
   a.n_tiles = (p->Cout + a.BN - 1) / a.BN;
-  const int stage_bytes = TC_A_BYTES + a.BN * TC_BK * 2;
-  a.epi_tma = p->out_dtype == PD_BF16 ? 1 : 0;
+  const int stage_bytes = TC_A_BYTES + (a.BN / CGv) * TC_BK * 2;
   const int epi_bytes = a.epi_tma ? 4 * 16384 : 0;
   a.stages = (TC_SMEM_BUDGET - epi_bytes) / stage_bytes;
   if (a.stages > TC_MAX_STAGES) a.stages = TC_MAX_STAGES;
   if (a.stages < 2) { set_error("conv_tc: not enough shared memory for 2 stages"); return PD_ERR_UNSUPPORTED; }
-  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)((TC_BM * CGv) >> 4) << 24);
 
   // ---- tensor maps ------------------------------------------------------------------------------
   CUtensorMap map_a0, map_a1, map_w;
@@ -523,7 +576,7 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   {
     uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p->Cout};
     uint64_t strides[1] = {(uint64_t)Ktot * 2};
-    uint32_t box[2] = {TC_BK, (uint32_t)a.BN};
+    uint32_t box[2] = {TC_BK, (uint32_t)(a.BN / CGv)};
     uint32_t es[2] = {1, 1};
     int rc = encode_map(&map_w, p->w, 2, dims, strides, box, es, "W");
     if (rc) return rc;
@@ -552,15 +605,19 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   const size_t smem = (size_t)a.stages * stage_bytes + epi_bytes + 1024;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                            const CUtensorMap, const CUtensorMap, const TcArgs);
-  static const KernelFn kernels[9] = {conv_tc_kernel<0>, conv_tc_kernel<1>, conv_tc_kernel<2>, conv_tc_kernel<3>,
-                                      conv_tc_kernel<4>, conv_tc_kernel<5>, conv_tc_kernel<6>, conv_tc_kernel<7>,
-                                      conv_tc_kernel<8>};
+  static const KernelFn kernels[2][9] = {
+      {conv_tc_kernel<0, 1>, conv_tc_kernel<1, 1>, conv_tc_kernel<2, 1>, conv_tc_kernel<3, 1>, conv_tc_kernel<4, 1>,
+       conv_tc_kernel<5, 1>, conv_tc_kernel<6, 1>, conv_tc_kernel<7, 1>, conv_tc_kernel<8, 1>},
+      {conv_tc_kernel<0, 2>, conv_tc_kernel<1, 2>, conv_tc_kernel<2, 2>, conv_tc_kernel<3, 2>, conv_tc_kernel<4, 2>,
+       conv_tc_kernel<5, 2>, conv_tc_kernel<6, 2>, conv_tc_kernel<7, 2>, nullptr}};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 9; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-      if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    }
+    for (int c = 0; c < 2; ++c)
+      for (int i = 0; i < 9; ++i) {
+        if (kernels[c][i] == nullptr) continue;
+        cudaError_t e = cudaFuncSetAttribute(kernels[c][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+        if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+      }
     attr_set = true;
   }
   const int epi = a.epi_tma ? ((p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0)) : 8;
@@ -576,8 +633,9 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
     if (p->Cout > 16384) { set_error("conv_tc: bias-less launch with Cout > 16384"); return PD_ERR_UNSUPPORTED; }
     a.bias = zero_bias;
   }
-  int64_t tiles = (int64_t)a.m_tiles * a.n_tiles;
-  int grid = (int)(tiles < sms ? tiles : sms);
+  int64_t tiles = (int64_t)((a.m_tiles + CGv - 1) / CGv) * a.n_tiles;
+  const int64_t workers = sms / CGv;
+  int grid = (int)(tiles < workers ? tiles : workers) * CGv;
   ProfRec rec;
   if (g_prof_on) {
     cudaEventCreate(&rec.e0);
@@ -585,10 +643,19 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
     rec.flops = 2.0 * (double)p->B * Ho * Wo * (double)p->Cout * (double)(p->ksize * p->ksize * p->C + p->C2);
     rec.M = p->B * Ho * Wo; rec.N = p->Cout; rec.K = p->ksize * p->ksize * p->C + p->C2; rec.ksize = p->ksize;
     rec.stride = p->stride; rec.BN = a.BN; rec.m_tiles = a.m_tiles; rec.n_tiles = a.n_tiles; rec.stages = a.stages;
-    rec.grid = grid;
+    rec.grid = grid; rec.cg = CGv;
     cudaEventRecord(rec.e0, s);
   }
-  kernels[epi]<<<grid, TC_THREADS, smem, s>>>(map_a0, map_a1, map_w, map_o64, map_o32, map_r64, map_r32, a);
+  {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = smem; lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)CGv; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, kernels[CGv - 1][epi], map_a0, map_a1, map_w, map_o64, map_o32, map_r64, map_r32, a);
+    if (e != cudaSuccess) { set_error("conv_tc: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+  }
   if (g_prof_on) {
     cudaEventRecord(rec.e1, s);
     g_prof.push_back(rec);
@@ -596,11 +663,68 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   return check_launch("conv_tc");
 }
 
+// Tile-shape autotuning.  Single-CTA vs CTA-pair tiles trade L2 / shared-memory operand traffic against per-tile
+// synchronisation cost, and which wins depends on (M, N, K) in ways a closed-form model gets wrong for the short-K
+// layers; both variants produce bit-identical results (same K order per output element), so the first idempotent
+// call of each layer shape simply times both (CUDA events on the caller's stream; that one call is synchronous) and
+// the choice is cached.  Calls that accumulate in place, calls during stream capture and profiled calls never tune.
+struct TuneKey {
+  int M, N, K, ksize, stride, c2, epi;
+  bool operator<(const TuneKey& o) const {
+    return std::tie(M, N, K, ksize, stride, c2, epi) < std::tie(o.M, o.N, o.K, o.ksize, o.stride, o.c2, o.epi);
+  }
+};
+static std::map<TuneKey, int> g_tune;
+static int g_autotune = -1;
+
+int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
+  if (g_autotune < 0) {
+    const char* e = getenv("PD_B200_AUTOTUNE");
+    g_autotune = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (g_force_cg != 0 || !g_autotune || p->out_dtype != PD_BF16 || g_dbg_mode != 0) return conv2d_tc_impl(p, s, g_force_cg);
+  const int pad = p->ksize / 2;
+  const int Ho = (p->H + 2 * pad - p->ksize) / p->stride + 1, Wo = (p->W + 2 * pad - p->ksize) / p->stride + 1;
+  const TuneKey key{p->B * Ho * Wo, p->Cout, p->ksize * p->ksize * p->C + p->C2, p->ksize, p->stride, p->C2 > 0 ? 1 : 0,
+                    (p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0)};
+  auto it = g_tune.find(key);
+  if (it != g_tune.end()) return conv2d_tc_impl(p, s, it->second);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+  const bool in_place = p->res == p->out || p->x == p->out || (p->x2 != nullptr && p->x2 == p->out);
+  if (cap != cudaStreamCaptureStatusNone || in_place || g_prof_on) return conv2d_tc_impl(p, s, 0);
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaGetLastError(); return conv2d_tc_impl(p, s, 0); }
+  float best_ms = 1e30f; int best = 1;
+  for (int cg = 1; cg <= 2; ++cg) {
+    int rc = conv2d_tc_impl(p, s, cg);                     // warm (tensor maps, L2)
+    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < 3 && rc == 0; ++i) rc = conv2d_tc_impl(p, s, cg);
+    cudaEventRecord(e1, s);
+    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    float ms = 0.f;
+    if (cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) {
+      cudaError_t e = cudaGetLastError();
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      set_error("conv_tc autotune: %s", cudaGetErrorString(e));
+      return (int)(e != cudaSuccess ? e : cudaErrorUnknown);
+    }
+    if (ms < best_ms) { best_ms = ms; best = cg; }
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  g_tune[key] = best;
+  return 0;                                                  // the output already holds the result
+}
+
 }  // namespace pd
 
 extern "C" {
 // debugging aid: device buffer of 3*64*2 uint64 receiving CTA 0's per-role tile timeline (NULL = off)
 int pd_debug_timeline(void* dev_buf) { pd::g_dbg = (unsigned long long*)dev_buf; return 0; }
+// tile-shape override of the tcgen05 engine: 0 auto, 1 single-CTA tiles, 2 CTA-pair (cta_group::2) tiles
+int pd_debug_gemm_mode(int mode) { pd::g_dbg_mode = mode; return 0; }
+int pd_debug_force_cta_group(int cg) { pd::g_force_cg = (cg == 1 || cg == 2) ? cg : 0; return 0; }
 // enable (1) / disable (0) per-launch timing of the tcgen05 engine; enabling clears the log
 int pd_prof_enable(int on) {
   for (auto& r : pd::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -612,13 +736,13 @@ int pd_prof_enable(int on) {
 int pd_prof_dump(const char* path) {
   FILE* f = fopen(path, "w");
   if (!f) { pd::set_error("pd_prof_dump: cannot open %s", path); return PD_ERR_BAD_ARG; }
-  fprintf(f, "M,N,K,ksize,stride,BN,m_tiles,n_tiles,stages,grid,ms,tflops\n");
+  fprintf(f, "M,N,K,ksize,stride,BN,m_tiles,n_tiles,stages,grid,cg,ms,tflops\n");
   for (auto& r : pd::g_prof) {
     float t = 0.f;
     cudaEventSynchronize(r.e1);
     cudaEventElapsedTime(&t, r.e0, r.e1);
-    fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.5f,%.1f\n", r.M, r.N, r.K, r.ksize, r.stride, r.BN, r.m_tiles,
-            r.n_tiles, r.stages, r.grid, t, r.flops / (t * 1e-3) / 1e12);
+    fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.5f,%.1f\n", r.M, r.N, r.K, r.ksize, r.stride, r.BN, r.m_tiles,
+            r.n_tiles, r.stages, r.grid, r.cg, t, r.flops / (t * 1e-3) / 1e12);
   }
   fclose(f);
   return 0;

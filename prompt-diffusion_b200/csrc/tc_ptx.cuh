@@ -42,6 +42,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     }
   }
 }
+// One lane of a CONVERGED warp (elect.sync).  Role loops run warp-uniformly and guard only the single-thread
+// instructions (TMA, tcgen05.mma / commit) with this: ptxas then emits a plain predicated UTMALDG / UTCHMMA, whereas
+// the same instructions inside an `if (lane == 0)` region are wrapped in an ELECT ... BRA.U.ANY retry loop each —
+// several hundred cycles per k-block on the issuing thread, enough to starve the tensor pipe.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -222,6 +235,53 @@ __device__ __forceinline__ uint32_t pack_bf16x2_b32_v(uint32_t lo, uint32_t hi) 
   uint32_t r;
   asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
   return r;
+}
+
+
+// ---- CTA-pair (cta_group::2) variants ---------------------------------------------------------------------
+// Two CTAs of a cluster (same TPC) execute ONE tcgen05.mma of M = 256: each CTA supplies its 128 rows of A and
+// half of the B tile from its own shared memory and receives its 128 accumulator rows in its own TMEM.  Only the
+// even CTA issues MMAs; TMA loads of both CTAs report their bytes to the even CTA's mbarrier.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> even CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once all prior MMAs of this thread retire) on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(s_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at this offset in the cluster's CTA `rank` (remote shared memory)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(s_u32(bar)), "r"(rank) : "memory");
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

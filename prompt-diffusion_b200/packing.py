@@ -27,10 +27,11 @@ def pad_channels(c: int, dt: torch.dtype) -> int:
 
 
 class PConv:
-    __slots__ = ("w", "bias", "cin", "cin_pad", "cout", "ksize", "stride", "c2", "role")
+    __slots__ = ("w", "bias", "cin", "cin_pad", "cout", "cout_pad", "ksize", "stride", "c2", "role")
 
     def __init__(self, w, bias, cin, cin_pad, cout, ksize, stride, c2=0, role="conv"):
         self.w, self.bias, self.cin, self.cin_pad, self.cout = w, bias, cin, cin_pad, cout
+        self.cout_pad = cout
         self.ksize, self.stride, self.c2, self.role = ksize, stride, c2, role
 
 
@@ -67,25 +68,37 @@ class Packer:
     def norm(self, key: str) -> PNorm:
         return PNorm(self.vec(key + ".weight"), self.vec(key + ".bias"))
 
-    def conv(self, key: str, stride: int = 1, skip_key: Optional[str] = None, pad: bool = True) -> PConv:
+    def conv(self, key: str, stride: int = 1, skip_key: Optional[str] = None, pad: bool = True,
+             tc_small: bool = False) -> PConv:
+        """``tc_small`` (bf16 mode only): also pad a tiny channel count so that the layer runs on the tcgen05
+        engine — input channels up to 64 (conv_in: 4 -> 64, zero columns in the activation buffer) and output
+        channels up to 8 (out conv: 4 -> 8, zero weight rows; the caller slices the result)."""
         w = self.t(key + ".weight")
         if w.dim() == 2:
             w = w[:, :, None, None]
         cout, cin, kh, kw = w.shape
         cin_pad = pad_channels(cin, self.dt) if pad else cin
+        cout_pad = cout
+        if tc_small and self.dt == torch.bfloat16:
+            cin_pad = (cin + 63) // 64 * 64
+            cout_pad = (cout + 7) // 8 * 8
         ktot = kh * kw * cin_pad
         c2 = 0
         if skip_key is not None:
             ws = self.t(skip_key + ".weight")
             c2 = ws.shape[1]
             ktot += c2
-        out = torch.empty((cout, ktot), dtype=self.dt, device=self.device)
-        ops.repack_conv_weight(w, out, cin_pad=cin_pad, k_offset=0)
+        out = (torch.zeros if cout_pad != cout else torch.empty)((cout_pad, ktot), dtype=self.dt, device=self.device)
+        ops.repack_conv_weight(w, out[:cout], cin_pad=cin_pad, k_offset=0)
         bias = self.vec(key + ".bias") if (self.prefix + key + ".bias") in self.sd else None
         if skip_key is not None:
             ops.repack_conv_weight(ws, out, k_offset=kh * kw * cin_pad)
             bias = (bias + self.vec(skip_key + ".bias")).contiguous()
-        return PConv(out, bias, cin, cin_pad, cout, kh, stride, c2)
+        if cout_pad != cout and bias is not None:
+            bias = torch.cat([bias, torch.zeros(cout_pad - cout, dtype=bias.dtype, device=bias.device)]).contiguous()
+        pc = PConv(out, bias, cin, cin_pad, cout, kh, stride, c2)
+        pc.cout_pad = cout_pad
+        return pc
 
     def stacked_linear(self, keys: List[str], with_bias: bool) -> PConv:
         ws = [self.t(k + ".weight") for k in keys]
@@ -135,7 +148,7 @@ class Packer:
         if isinstance(layer, ST):
             return self.st(layer)
         if isinstance(layer, Conv):
-            return self.conv(layer.key, stride=layer.stride)
+            return self.conv(layer.key, stride=layer.stride, tc_small=True)       # input_blocks.0.0 (4 -> 320)
         if isinstance(layer, Down):
             pc = self.conv(layer.key + ".op", stride=2)
             pc.role = "down"
@@ -171,7 +184,7 @@ class PackedNet:
         self.emb_total = off
         if decoder:
             self.out_norm = pk.norm("out.0")
-            self.out_conv = pk.conv("out.2")
+            self.out_conv = pk.conv("out.2", tc_small=True)                         # 320 -> 4
         else:
             self.zero_convs = [pk.conv(f"zero_convs.{i}.0") for i in range(len(topo.input_blocks))]
             self.middle_out = pk.conv("middle_block_out.0")

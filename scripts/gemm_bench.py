@@ -35,8 +35,23 @@ def run(B, H, W, C, N, ks, res, iters=20, warm=3, rowvec=False):
 ap = argparse.ArgumentParser()
 ap.add_argument("--one", nargs=7, type=int, default=None, help="B H W C N ks res")
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--modes", action="store_true", help="timing experiment: full kernel vs no-MMA vs no-TMA, per tile shape")
 a = ap.parse_args()
-if a.one:
+if a.modes:
+    from prompt_diffusion_b200 import _lib
+    print("   B   HxW     C     N ks res cg |  full us | noMMA us | noTMA us")
+    for s_ in [(16, 64, 64, 320, 320, 3, 0), (16, 64, 64, 320, 320, 1, 0), (16, 32, 32, 1280, 1280, 3, 0), (16, 64, 64, 320, 2560, 1, 0),
+               (16, 16, 16, 1280, 1280, 3, 1), (16, 8, 8, 1280, 1280, 3, 1)]:
+        for cg in (1, 2):
+            _lib.lib.pd_debug_force_cta_group(cg)
+            row = []
+            for mode in (0, 1, 2):
+                _lib.lib.pd_debug_gemm_mode(mode)
+                row.append(run(*s_, iters=a.iters)[0])
+            _lib.lib.pd_debug_gemm_mode(0)
+            print("%4d %3dx%-3d %5d %5d %2d %3d %2d | %8.1f | %8.1f | %8.1f" % (*s_, cg, *row))
+    _lib.lib.pd_debug_force_cta_group(0)
+elif a.one:
     B, H, W, C, N, ks, res = a.one
     us, tf, gb = run(B, H, W, C, N, ks, bool(res), iters=a.iters, warm=2)
     print(f"B{B} {H}x{W} C{C}->N{N} k{ks} res={res}: {us:.1f} us  {tf:.0f} TFLOP/s  {gb:.0f} GB/s")
@@ -50,7 +65,13 @@ else:
         (16, 16, 16, 2560, 1280, 3, 0), (16, 8, 8, 1280, 1280, 3, 1), (16, 8, 8, 2560, 1280, 3, 0),
         (16, 8, 8, 1280, 1280, 1, 0),
     ]
-    print("   B   HxW     C     N ks res |     us   TFLOP/s    GB/s")
+    from prompt_diffusion_b200 import _lib
+    print("   B   HxW     C     N ks res |  auto us  TFLOP/s |  cg1 us  TFLOP/s |  cg2 us  TFLOP/s")
     for s in shapes:
-        us, tf, gb = run(*s, iters=a.iters)
-        print("%4d %3dx%-3d %5d %5d %2d %3d | %7.1f %8.0f %8.0f" % (s[0], s[1], s[2], s[3], s[4], s[5], s[6], us, tf, gb))
+        row = []
+        for cg in (0, 1, 2):
+            _lib.lib.pd_debug_force_cta_group(cg)
+            us, tf, gb = run(*s, iters=a.iters)
+            row += [us, tf]
+        _lib.lib.pd_debug_force_cta_group(0)
+        print("%4d %3dx%-3d %5d %5d %2d %3d | %8.1f %8.0f | %7.1f %8.0f | %7.1f %8.0f" % (s[0], s[1], s[2], s[3], s[4], s[5], s[6], *row))

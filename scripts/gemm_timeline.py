@@ -4,6 +4,7 @@ import torch
 from prompt_diffusion_b200 import ops, _lib
 from prompt_diffusion_b200._lib import PD_ENGINE_TC
 B,H,W,C,N,ks,res = [int(v) for v in sys.argv[1:8]]
+if len(sys.argv) > 8: _lib.lib.pd_debug_force_cta_group(int(sys.argv[8]))
 dev="cuda"; M=B*H*W
 x=torch.randn(M,C,device=dev).to(torch.bfloat16); w=(torch.randn(N,ks*ks*C,device=dev)/math.sqrt(ks*ks*C)).to(torch.bfloat16)
 bias=torch.randn(N,device=dev); out=torch.empty(M,N,device=dev,dtype=torch.bfloat16)

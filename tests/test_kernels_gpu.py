@@ -130,6 +130,20 @@ def test_conv_tcgen05_bf16(case):
     assert err < 6e-3, err
 
 
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_bf16_forced_tile(case, cg):
+    """Same cases with the tile shape pinned: single-CTA 128-row tiles (cg=1) and CTA-pair 256-row tiles
+    (tcgen05 cta_group::2, cg=2; odd M-tile counts exercise the phantom half of the last pair)."""
+    from prompt_diffusion_b200 import _lib
+    _lib.lib.pd_debug_force_cta_group(cg)
+    try:
+        err = _conv_case(torch.bfloat16, _lib.PD_ENGINE_TC, **case)
+    finally:
+        _lib.lib.pd_debug_force_cta_group(0)
+    assert err < 6e-3, err
+
+
 def test_conv_tc_rejects_unsupported():
     from prompt_diffusion_b200._lib import PD_ENGINE_TC
     with pytest.raises(RuntimeError):
