@@ -66,6 +66,8 @@ int pd_debug_timeline(void* dev_buf);
 int pd_debug_force_cta_group(int32_t cg);
 /* timing experiments on the conv engine (results are WRONG when non-zero): 1 = issue no MMAs, 2 = issue no TMA loads */
 int pd_debug_gemm_mode(int32_t mode);
+/* 1 (default): GroupNorm is one cooperative launch; 0: statistics kernel + apply kernel */
+int pd_debug_group_norm_fused(int32_t on);
 /* same for the tcgen05 attention kernel: 6 phases x 32 tiles of uint64 stamps from block (0,0,0) */
 int pd_debug_attention_timeline(void* dev_buf);
 

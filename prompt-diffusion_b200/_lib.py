@@ -45,6 +45,7 @@ SIGNATURES = {
     "pd_debug_timeline": (C.c_int, [C.c_void_p]),
     "pd_debug_force_cta_group": (C.c_int, [C.c_int32]),
     "pd_debug_gemm_mode": (C.c_int, [C.c_int32]),
+    "pd_debug_group_norm_fused": (C.c_int, [C.c_int32]),
     "pd_debug_attention_timeline": (C.c_int, [C.c_void_p]),
     "pd_conv2d": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
     "pd_repack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),

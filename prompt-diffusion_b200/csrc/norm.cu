@@ -21,6 +21,7 @@ namespace pd {
 constexpr int GN_CHUNKS_MAX = 64;
 constexpr int GN_GROUPS_MAX = 32;
 constexpr int GN_THREADS = 512;
+static bool g_gn_fused = true;    // pd_debug_group_norm_fused(0) falls back to the two-kernel form (A/B timing, tests)
 
 __host__ __device__ inline int gn_num_chunks(int HW) {
   int c = (HW + 63) / 64;  // ~64 pixels per chunk, capped
@@ -222,6 +223,160 @@ gn_apply_kernel(const T* __restrict__ x, int ldx, TO* __restrict__ out, int ldo,
   }
 }
 
+// ---- single-launch GroupNorm -------------------------------------------------------------------------------
+// Same thread grid and arithmetic as gn_stats + gn_apply, but ONE cooperative launch: every CTA reduces its row
+// chunk, publishes one (sum, sumsq) partial per group, meets the other CTAs of ITS image at a sense-reversing
+// barrier in global memory (all CTAs are co-resident: cudaLaunchCooperativeKernel), folds the image's partials in
+// a fixed order (deterministic) and normalises the chunk it has just read (L2-hot).  Halves the launches of the 88
+// GroupNorms per step and removes the serial "last CTA folds" tail of the two-kernel form.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_fused_kernel(const T* __restrict__ x, int ldx, TO* __restrict__ out, int ldo, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float* __restrict__ partial, int HW, int C, int groups, int chunks,
+                float eps, int act, unsigned int* __restrict__ sync_words) {
+  constexpr int V = VecIO<T>::V;
+  extern __shared__ float sm[];  // [TY][2*C] per-row-lane, per-channel sum | sumsq
+  __shared__ float s_g[2 * GN_GROUPS_MAX];
+  __shared__ unsigned int s_gen;
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  unsigned int* count = sync_words + 2 * b;
+  unsigned int* flag = sync_words + 2 * b + 1;
+  if (threadIdx.x == 0) s_gen = *reinterpret_cast<volatile unsigned int*>(flag);   // read BEFORE arriving
+  const int rows_per = (HW + chunks - 1) / chunks;
+  const int r0 = chunk * rows_per;
+  const int r1 = min(HW, r0 + rows_per);
+  const GnGrid g = gn_grid(C, V);
+  const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
+  const T* base = x + (int64_t)b * HW * ldx;
+  if (ty < g.ty_n) {
+    for (int ps = 0; ps < g.passes; ++ps) {
+      const int j = tx + ps * g.tx_n;
+      if (j >= g.vpr) break;
+      float s[V], q[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) s[k] = q[k] = 0.f;
+      const T* col = base + (int64_t)j * V;
+      int r = r0 + ty;
+      for (; r + 3 * g.ty_n < r1; r += 4 * g.ty_n) {       // four rows in flight
+        float f0[V], f1[V], f2[V], f3[V];
+        VecIO<T>::ld(col + (int64_t)r * ldx, f0);
+        VecIO<T>::ld(col + (int64_t)(r + g.ty_n) * ldx, f1);
+        VecIO<T>::ld(col + (int64_t)(r + 2 * g.ty_n) * ldx, f2);
+        VecIO<T>::ld(col + (int64_t)(r + 3 * g.ty_n) * ldx, f3);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          s[k] += (f0[k] + f1[k]) + (f2[k] + f3[k]);
+          q[k] += (f0[k] * f0[k] + f1[k] * f1[k]) + (f2[k] * f2[k] + f3[k] * f3[k]);
+        }
+      }
+      for (; r < r1; r += g.ty_n) {
+        float f0[V];
+        VecIO<T>::ld(col + (int64_t)r * ldx, f0);
+#pragma unroll
+        for (int k = 0; k < V; ++k) { s[k] += f0[k]; q[k] += f0[k] * f0[k]; }
+      }
+      float* mine = sm + (size_t)ty * 2 * C;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        mine[j * V + k] = s[k];
+        mine[C + j * V + k] = q[k];
+      }
+    }
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int gi = warp; gi < groups; gi += GN_THREADS / 32) {
+    float a = 0.f, bq = 0.f;
+    for (int c = lane; c < cpg; c += 32)
+      for (int t = 0; t < g.ty_n; ++t) {          // fixed order
+        a += sm[(size_t)t * 2 * C + gi * cpg + c];
+        bq += sm[(size_t)t * 2 * C + C + gi * cpg + c];
+      }
+    a = warp_sum(a); bq = warp_sum(bq);
+    if (lane == 0) {
+      float* dst = partial + (((int64_t)b * GN_CHUNKS_MAX + chunk) * GN_GROUPS_MAX + gi) * 2;
+      dst[0] = a; dst[1] = bq;
+    }
+  }
+  // ---- barrier among the `chunks` CTAs of image b ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int gen = s_gen;
+    const unsigned int prev = atomicAdd(count, 1u);
+    if (prev == (unsigned int)chunks - 1u) {
+      *count = 0u;                                 // self-resetting: ready for the next launch
+      __threadfence();
+      atomicExch(flag, gen + 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*reinterpret_cast<volatile unsigned int*>(flag) == gen) {
+        __nanosleep(40);
+        if (clock64() - t0 > 4000000000LL) { printf("pd_b200 gn_fused: barrier timeout image %d chunk %d\n", b, chunk); __trap(); }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    double su = 0.0, sq = 0.0;
+    for (int ch = 0; ch < chunks; ++ch) {          // fixed order, in double
+      const volatile float* pp = partial + (((int64_t)b * GN_CHUNKS_MAX + ch) * GN_GROUPS_MAX + threadIdx.x) * 2;
+      su += (double)pp[0]; sq += (double)pp[1];
+    }
+    const double n = (double)HW * (double)cpg;
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_g[2 * threadIdx.x] = (float)mean;
+    s_g[2 * threadIdx.x + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  if (ty >= g.ty_n) return;
+  for (int ps = 0; ps < g.passes; ++ps) {
+    const int j = tx + ps * g.tx_n;
+    if (j >= g.vpr) break;
+    const int c0 = j * V;
+    float mean[V], a[V], bt[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int gi = (c0 + k) / cpg;
+      mean[k] = s_g[2 * gi];
+      a[k] = s_g[2 * gi + 1] * gamma[c0 + k];
+      bt[k] = beta[c0 + k];
+    }
+    const T* xc = base + c0;
+    TO* oc = out + (int64_t)b * HW * ldo + c0;
+    for (int r = r0 + ty; r < r1; r += 2 * g.ty_n) {
+      const bool two = r + g.ty_n < r1;
+      float f0[V], f1[V];
+      VecIO<T>::ld(xc + (int64_t)r * ldx, f0);
+      if (two) VecIO<T>::ld(xc + (int64_t)(r + g.ty_n) * ldx, f1);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float y0 = (f0[k] - mean[k]) * a[k] + bt[k];
+        float y1 = two ? (f1[k] - mean[k]) * a[k] + bt[k] : 0.f;
+        if (act == PD_ACT_SILU) {
+          y0 = sizeof(TO) == 4 ? silu_acc(y0) : silu_f(y0);
+          y1 = sizeof(TO) == 4 ? silu_acc(y1) : silu_f(y1);
+        }
+        f0[k] = y0; f1[k] = y1;
+      }
+      if constexpr (sizeof(T) == sizeof(TO)) {
+        VecIO<TO>::st(oc + (int64_t)r * ldo, f0);
+        if (two) VecIO<TO>::st(oc + (int64_t)(r + g.ty_n) * ldo, f1);
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          Dt<TO>::st(oc + (int64_t)r * ldo + k, f0[k]);
+          if (two) Dt<TO>::st(oc + (int64_t)(r + g.ty_n) * ldo + k, f1[k]);
+        }
+      }
+    }
+  }
+}
+
 // ---- LayerNorm -------------------------------------------------------------------------
 // One warp per row; NV = vectors per lane (compile-time), so the row sits in registers and the
 // loads of a row are all issued before the first use.  C in {320, 640, 1280} -> NV in {2, 3, 5} (bf16).
@@ -291,16 +446,103 @@ layer_norm_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ldo
   }
 }
 
+// Grouped-lane variant: LPR lanes share one row and each lane holds NV vectors of it (C = LPR * NV * V), so a warp
+// normalises 32 / LPR rows at once with every lane busy (C = 320 in bf16 is 40 vectors: the one-warp-per-row
+// kernel above leaves 24 of 64 lane slots idle and has one 640-byte row in flight per warp).  gamma / beta live in
+// shared memory, which keeps the register count low enough for 4+ CTAs per SM — the latency of an HBM-bound
+// kernel is covered by bytes in flight, not by issue slots.
+template <typename T, int LPR, int NV>
+__global__ void __launch_bounds__(256)
+layer_norm_grouped_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ldo,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows, int C,
+                          float eps) {
+  constexpr int V = VecIO<T>::V;
+  constexpr int RPW = 32 / LPR;                       // rows per warp per iteration
+  extern __shared__ float s_gb[];                     // gamma[C] | beta[C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_gb[i] = gamma[i]; s_gb[C + i] = beta[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, li = lane % LPR;
+  const float invC = 1.0f / (float)C;
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5) * RPW;
+  for (int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * RPW; row0 < rows; row0 += stride) {
+    const int64_t row = row0 + sub;
+    const bool ok = row < rows;
+    const T* xr = x + (ok ? row : 0) * ldx;
+    float f[NV][V];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) VecIO<T>::ld(xr + (li + i * LPR) * V, f[i]);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int k = 0; k < V; ++k) sum += f[i][k];
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * invC;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int k = 0; k < V; ++k) { const float d = f[i][k] - mean; var += d * d; }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var * invC + eps);
+    if (ok) {
+      T* orow = out + row * ldo;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c0 = (li + i * LPR) * V;
+        float y[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) y[k] = (f[i][k] - mean) * rstd * s_gb[c0 + k] + s_gb[C + c0 + k];
+        VecIO<T>::st(orow + c0, y);
+      }
+    }
+  }
+}
+
 template <typename T, typename TO>
 static int gn_launch(const void* x, int ldx, void* out, int ldo, const float* gamma, const float* beta,
                      float* partial, int B, int HW, int C, int groups, float eps, int act, cudaStream_t s) {
-  const int chunks = gn_num_chunks(HW);
+  int chunks = gn_num_chunks(HW);
   constexpr int Vv = VecIO<T>::V;
   const GnGrid gg = gn_grid(C, Vv);
   const size_t st_smem = (size_t)gg.ty_n * 2 * C * sizeof(float);   // <= 2*V*512*4 = 32 KiB
   // scratch layout: [B][64 chunks][32 groups][2] partials | [B][32][2] mean,rstd | [B] arrival counters (zeroed once)
+  //                 | [B][2] barrier words of the fused kernel (zeroed once)
   float* stats = partial + (int64_t)B * GN_CHUNKS_MAX * GN_GROUPS_MAX * 2;
   unsigned int* counters = reinterpret_cast<unsigned int*>(stats + (int64_t)B * GN_GROUPS_MAX * 2);
+  unsigned int* sync_words = counters + B;
+  {
+    // single cooperative launch when all CTAs can be co-resident (they meet at a barrier)
+    static int per_sm = -1;
+    if (per_sm < 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gn_fused_kernel<T, TO>, GN_THREADS, 40 * 1024) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+      }
+      per_sm = n > 2 ? 2 : n;
+    }
+    const int capacity = per_sm * num_sms();
+    int fchunks = B > 0 ? capacity / B : 0;
+    // as many CTAs per image as can be co-resident, down to ~one pass of the thread grid over a chunk: the small
+    // late-stage tensors (8x8, 16x16) are latency-bound and want parallelism, not long per-thread row walks
+    int want = (HW + gg.ty_n - 1) / gg.ty_n;
+    if (want > GN_CHUNKS_MAX) want = GN_CHUNKS_MAX;
+    if (want < 1) want = 1;
+    if (fchunks > want) fchunks = want;
+    if (fchunks >= 1 && g_gn_fused) {
+      const T* xp = (const T*)x; TO* op = (TO*)out;
+      void* args[] = {(void*)&xp, (void*)&ldx, (void*)&op, (void*)&ldo, (void*)&gamma, (void*)&beta, (void*)&partial,
+                      (void*)&HW, (void*)&C, (void*)&groups, (void*)&fchunks, (void*)&eps, (void*)&act, (void*)&sync_words};
+      cudaError_t e = cudaLaunchCooperativeKernel((const void*)gn_fused_kernel<T, TO>, dim3(fchunks, B), dim3(GN_THREADS),
+                                                  args, st_smem, s);
+      if (e != cudaSuccess) { set_error("pd_group_norm: cooperative launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+      return check_launch("gn_fused");
+    }
+  }
   gn_stats_kernel<T><<<dim3(chunks, B), GN_THREADS, st_smem, s>>>((const T*)x, ldx, partial, HW, C, groups, chunks, eps,
                                                                 stats, counters);
   int rc = check_launch("gn_stats");
@@ -319,7 +561,23 @@ template <typename T>
 static int ln_launch(const void* x, int ldx, void* out, int ldo, const float* gamma, const float* beta,
                      int64_t rows, int C, float eps, cudaStream_t s) {
   constexpr int V = VecIO<T>::V;
-  const int nv = (C / V + 31) / 32;
+  const int nvec = C / V;
+  {
+    // grouped-lane kernel for the widths of the path (5 or 10 vectors per lane)
+    const size_t smem = (size_t)2 * C * sizeof(float);
+#define PD_LNG(L, N)                                                                                              \
+  if (nvec == (L) * (N)) {                                                                                        \
+    int64_t blocks = (rows + 8 * (32 / (L)) - 1) / (8 * (32 / (L)));                                              \
+    const int64_t cap = (int64_t)num_sms() * 8;                                                                   \
+    if (blocks > cap) blocks = cap;                                                                               \
+    layer_norm_grouped_kernel<T, L, N><<<(int)blocks, 256, smem, s>>>((const T*)x, ldx, (T*)out, ldo, gamma, beta, \
+                                                                      rows, C, eps);                              \
+    return check_launch("pd_layer_norm");                                                                         \
+  }
+    PD_LNG(8, 5) PD_LNG(16, 5) PD_LNG(32, 5) PD_LNG(32, 10)
+#undef PD_LNG
+  }
+  const int nv = (nvec + 31) / 32;
   int64_t blocks = (rows + 7) / 8;
   int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
@@ -342,8 +600,10 @@ using namespace pd;
 extern "C" {
 
 int64_t pd_group_norm_scratch_floats(int32_t B) {
-  return (int64_t)B * GN_CHUNKS_MAX * GN_GROUPS_MAX * 2 + (int64_t)B * GN_GROUPS_MAX * 2 + B;
+  return (int64_t)B * GN_CHUNKS_MAX * GN_GROUPS_MAX * 2 + (int64_t)B * GN_GROUPS_MAX * 2 + B + 2 * (int64_t)B;
 }
+
+int pd_debug_group_norm_fused(int32_t on) { g_gn_fused = on != 0; return 0; }
 
 int pd_group_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const float* gamma, const float* beta,
                   float* partial, int32_t B, int32_t HW, int32_t C, int32_t groups, float eps, int32_t act,

@@ -16,7 +16,7 @@ if len(sys.argv) > 2:
     rows=list(csv.DictReader(open(sys.argv[2])))
     agg=collections.OrderedDict()
     for r in rows:
-        k=(int(r['M']),int(r['N']),int(r['K']),int(r['ksize']),int(r['stride']),int(r['BN']),int(r['m_tiles']),int(r['n_tiles']),int(r['stages']),int(r['grid']))
+        k=(int(r['M']),int(r['N']),int(r['K']),int(r['ksize']),int(r['stride']),int(r['BN']),int(r['m_tiles']),int(r['n_tiles']),int(r['stages']),int(r['grid'])*10+int(r.get('cg',1)))
         a=agg.setdefault(k,[0,0.0]); a[0]+=1; a[1]+=float(r['ms'])
     print("conv_tc total (event-timed, warm): %.2f ms"%sum(a[1] for a in agg.values()))
     print("     M     N      K ks s  BN  mt  nt st grid |  n   ms_tot  ms_each  TF/s  | ideal_us  memMB")
