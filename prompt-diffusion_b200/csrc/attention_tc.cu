@@ -116,6 +116,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  griddep_wait();                        // the set-up above overlapped the previous kernel's tail (PDL)
 
   if (warp == W_TMA) {
     if (lane == 0) {
@@ -332,6 +333,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       if (dbg) FA_DBG(dslot + 3, j);
     }
     // ---------------- epilogue ----------------
+    if (warp == 0 && lane == 0) griddep_launch();
     mbar_wait(&o_final[g], 0, 600 + g);
     tc_fence_after();
     const float inv = 1.0f / l_run;
@@ -416,7 +418,8 @@ int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, 
       if (e != cudaSuccess) { set_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; } \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    attention_tc_kernel<KP><<<grid, FA_THREADS, smem, s>>>(mq, mk, mv, mo, a);                                     \
+    cudaError_t le = launch_pdl(attention_tc_kernel<KP>, grid, dim3(FA_THREADS), smem, s, 1, mq, mk, mv, mo, a);   \
+    if (le != cudaSuccess) { set_error("attention_tc: launch failed: %s", cudaGetErrorString(le)); return (int)le; } \
   } break;
   switch (kpad / 16) {
     FA_LAUNCH(1) FA_LAUNCH(2) FA_LAUNCH(3) FA_LAUNCH(4) FA_LAUNCH(5) FA_LAUNCH(6) FA_LAUNCH(7) FA_LAUNCH(8)

@@ -98,4 +98,42 @@ bool attention_tc_supported(int dtype, int d, int ldq, int ldk, int ldv, int ldo
 int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
                  int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// Hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may be
+// scheduled (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while the previous
+// kernel drains, instead of paying a full launch gap ~500 times per denoising step.  Every such kernel calls
+// griddep_wait() before it reads or writes memory another kernel of the stream may touch (it returns once all
+// prerequisite grids have completed and flushed), and griddep_launch() when a CTA is about to finish.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef PD_PDL_TRIGGER
+#define PD_PDL_TRIGGER 0
+#endif
+__device__ __forceinline__ void griddep_launch() {
+#if PD_PDL_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+bool pdl_enabled();     // PD_B200_PDL=0 switches the launch attribute off (the device instructions become no-ops)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              unsigned cluster_x, Args... args) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = s;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  lc.attrs = at; lc.numAttrs = n;
+  return cudaLaunchKernelEx(&lc, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace pd

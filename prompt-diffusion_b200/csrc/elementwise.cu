@@ -8,6 +8,8 @@
 
 #include <atomic>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pd {
@@ -20,6 +22,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PD_B200_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 int check_launch(const char* what) {
@@ -111,6 +121,7 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 __global__ void __launch_bounds__(640)
 geglu_bf16_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int ldo, int64_t rows, int F,
                   int rows_per_cta) {
+  griddep_wait();
   const int vpr = F / 8;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int nr = (int)min((int64_t)rows_per_cta, rows - r0);
@@ -332,7 +343,9 @@ int pd_geglu(const void* x, int32_t ldx, void* out, int32_t ldo, int64_t rows, i
     const int rpc = rows >= (int64_t)num_sms() * 64 ? 8 : 4;      // keep >= ~8 CTAs per SM on the small-M layers
     const int64_t blocks = (rows + rpc - 1) / rpc;
     PD_REQUIRE(blocks <= 0x7fffffff, "pd_geglu: too many rows");
-    geglu_bf16_kernel<<<(unsigned)blocks, threads, 0, s>>>((const bf16*)x, ldx, (bf16*)out, ldo, rows, F, rpc);
+    cudaError_t le = launch_pdl(geglu_bf16_kernel, dim3((unsigned)blocks), dim3(threads), 0, s, 1, (const bf16*)x, ldx,
+                                (bf16*)out, ldo, rows, F, rpc);
+    if (le != cudaSuccess) { set_error("pd_geglu: launch failed: %s", cudaGetErrorString(le)); return (int)le; }
   } else if (dtype == PD_F32) {
     geglu_f32_kernel<<<grid_for(rows * F, 256), 256, 0, s>>>((const float*)x, ldx, (float*)out, ldo, rows, F);
   } else {

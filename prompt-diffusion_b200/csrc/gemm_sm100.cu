@@ -108,6 +108,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's barriers must be initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  griddep_wait();                        // everything above overlapped the previous kernel's tail (PDL)
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs of a pair); warp-uniform loop, one elected lane issues =================
@@ -121,6 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int tbi = mt / (a.tiles_x * a.tiles_y);   // >= tiles_b for the phantom half of an odd last pair: TMA zero-fills
         const int x0 = txi * a.bw, y0 = tyi * a.bh, b0 = tbi * a.bn, n0 = nt * a.BN + (int)cta_rank * b_rows;
         const int tix = (tile - worker) / nworkers;
+        if (tile + nworkers >= num_tiles && lane == 0) griddep_launch();   // last tile of this CTA: let the next kernel in
         if (lane == 0) PD_DBG(0, tix, 0);
         // (tap, channel block) walk of segment 0 kept in counters: no integer divisions on the issue path
         int cb = 0, dx = 0, dy = 0, wk0 = 0;
@@ -647,13 +649,8 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
     cudaEventRecord(rec.e0, s);
   }
   {
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = smem; lc.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)CGv; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    lc.attrs = at; lc.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&lc, kernels[CGv - 1][epi], map_a0, map_a1, map_w, map_o64, map_o32, map_r64, map_r32, a);
+    cudaError_t e = launch_pdl(kernels[CGv - 1][epi], dim3((unsigned)grid), dim3(TC_THREADS), smem, s, (unsigned)CGv, map_a0,
+                               map_a1, map_w, map_o64, map_o32, map_r64, map_r32, a);
     if (e != cudaSuccess) { set_error("conv_tc: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
   }
   if (g_prof_on) {

@@ -459,8 +459,9 @@ layer_norm_grouped_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out,
   constexpr int V = VecIO<T>::V;
   constexpr int RPW = 32 / LPR;                       // rows per warp per iteration
   extern __shared__ float s_gb[];                     // gamma[C] | beta[C]
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_gb[i] = gamma[i]; s_gb[C + i] = beta[i]; }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_gb[i] = gamma[i]; s_gb[C + i] = beta[i]; }   // weights: static
   __syncthreads();
+  griddep_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, li = lane % LPR;
   const float invC = 1.0f / (float)C;
@@ -570,8 +571,9 @@ static int ln_launch(const void* x, int ldx, void* out, int ldo, const float* ga
     int64_t blocks = (rows + 8 * (32 / (L)) - 1) / (8 * (32 / (L)));                                              \
     const int64_t cap = (int64_t)num_sms() * 8;                                                                   \
     if (blocks > cap) blocks = cap;                                                                               \
-    layer_norm_grouped_kernel<T, L, N><<<(int)blocks, 256, smem, s>>>((const T*)x, ldx, (T*)out, ldo, gamma, beta, \
-                                                                      rows, C, eps);                              \
+    cudaError_t le = launch_pdl(layer_norm_grouped_kernel<T, L, N>, dim3((unsigned)blocks), dim3(256), smem, s, 1, \
+                                (const T*)x, ldx, (T*)out, ldo, gamma, beta, rows, C, eps);                       \
+    if (le != cudaSuccess) { set_error("pd_layer_norm: launch failed: %s", cudaGetErrorString(le)); return (int)le; } \
     return check_launch("pd_layer_norm");                                                                         \
   }
     PD_LNG(8, 5) PD_LNG(16, 5) PD_LNG(32, 5) PD_LNG(32, 10)

@@ -21,10 +21,15 @@ def run(B, H, W, C, N, ks, res, iters=20, warm=3, rowvec=False):
     for _ in range(warm):
         ops.conv2d(x, w, out, B, H, W, ksize=ks, bias=bias, res=r, rowvec=rv, engine=PD_ENGINE_TC)
     torch.cuda.synchronize()
+    # GPU time per launch: the launches are captured into one CUDA graph (no host launch overhead in the number)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            ops.conv2d(x, w, out, B, H, W, ksize=ks, bias=bias, res=r, rowvec=rv, engine=PD_ENGINE_TC)
+    g.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        ops.conv2d(x, w, out, B, H, W, ksize=ks, bias=bias, res=r, rowvec=rv, engine=PD_ENGINE_TC)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / iters * 1e3
@@ -35,9 +40,17 @@ def run(B, H, W, C, N, ks, res, iters=20, warm=3, rowvec=False):
 ap = argparse.ArgumentParser()
 ap.add_argument("--one", nargs=7, type=int, default=None, help="B H W C N ks res")
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--small", action="store_true", help="fixed-overhead study: tiny and short-K GEMMs")
 ap.add_argument("--modes", action="store_true", help="timing experiment: full kernel vs no-MMA vs no-TMA, per tile shape")
 a = ap.parse_args()
-if a.modes:
+if a.small:
+    print("   B   HxW     C     N ks res |     us")
+    for s_ in [(1, 1, 128, 64, 64, 1, 0), (1, 1, 128 * 148, 64, 64, 1, 0), (1, 1, 128 * 148, 320, 128, 1, 0), (1, 1, 128 * 148, 320, 256, 1, 0),
+               (1, 1, 128 * 148 * 2, 320, 256, 1, 0), (1, 1, 128 * 148 * 4, 320, 256, 1, 0), (1, 1, 128 * 148 * 4, 320, 256, 1, 1),
+               (1, 1, 128 * 148, 1280, 256, 1, 0), (1, 1, 128 * 148, 2560, 256, 1, 0), (1, 1, 128 * 148, 5120, 256, 1, 0)]:
+        us, tf, gb = run(*s_, iters=a.iters)
+        print("%4d %3dx%-6d %5d %5d %2d %3d | %7.1f" % (*s_, us))
+elif a.modes:
     from prompt_diffusion_b200 import _lib
     print("   B   HxW     C     N ks res cg |  full us | noMMA us | noTMA us")
     for s_ in [(16, 64, 64, 320, 320, 3, 0), (16, 64, 64, 320, 320, 1, 0), (16, 32, 32, 1280, 1280, 3, 0), (16, 64, 64, 320, 2560, 1, 0),
