@@ -35,6 +35,10 @@ extern "C" {
 
 #define PD_ACT_NONE 0
 #define PD_ACT_SILU 1
+/* FeedForward's GEGLU (attention.py:54-56) fused into the linear that feeds it (tcgen05 engine, bf16 only):
+ * w has Cout = 2F rows interleaved in blocks of 32 (32 value rows, then their 32 gate rows), bias likewise;
+ * out has F = Cout/2 columns: out[:, j] = (x W_v^T + b_v)[:, j] * gelu_erf((x W_g^T + b_g)[:, j]) */
+#define PD_ACT_GEGLU 2
 
 #define PD_ERR_BAD_ARG (-1)
 #define PD_ERR_UNSUPPORTED (-2)

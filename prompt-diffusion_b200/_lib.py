@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpd_b200.so")
 
 PD_F32, PD_BF16 = 0, 1
-PD_ACT_NONE, PD_ACT_SILU = 0, 1
+PD_ACT_NONE, PD_ACT_SILU, PD_ACT_GEGLU = 0, 1, 2
 PD_ENGINE_AUTO, PD_ENGINE_SIMT, PD_ENGINE_TC = 0, 1, 2
 PD_ATTN_AUTO, PD_ATTN_SIMT, PD_ATTN_MMA, PD_ATTN_TC = 0, 1, 2, 3
 

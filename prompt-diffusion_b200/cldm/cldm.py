@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from .._lib import PD_ACT_NONE, PD_ACT_SILU
+from .._lib import PD_ACT_GEGLU, PD_ACT_NONE, PD_ACT_SILU
 from ..config import CLDM_V15, CLDMConfig
 from ..packing import PConv, PRes, PST, PackedNet, pad_channels
 from ..synth import CTRL_PREFIX, UNET_PREFIX
@@ -184,10 +184,13 @@ class _Net:
         ops.linear(att, s.out2.w, a, bias=s.out2.bias, res=b)
         # feed-forward (GEGLU)
         ops.layer_norm(a, ln, s.ln3.gamma, s.ln3.beta)
-        ff = self.buf("t_ff", M, 8 * Cc)
-        ops.linear(ln, s.ff1.w, ff, bias=s.ff1.bias)
         gg = self.buf("t_gg", M, 4 * Cc)
-        ops.geglu(ff, gg)
+        if s.ff1_geglu is not None:        # bf16: x * gelu(gate) in the GEMM epilogue, the [M, 8C] tensor never exists
+            ops.linear(ln, s.ff1_geglu.w, gg, bias=s.ff1_geglu.bias, act=PD_ACT_GEGLU)
+        else:
+            ff = self.buf("t_ff", M, 8 * Cc)
+            ops.linear(ln, s.ff1.w, ff, bias=s.ff1.bias)
+            ops.geglu(ff, gg)
         ops.linear(gg, s.ff2.w, b, bias=s.ff2.bias, res=a)
         self.conv(s.proj_out, b, out, 1, 1, M, res=x)
         return out

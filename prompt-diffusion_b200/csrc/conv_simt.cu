@@ -244,15 +244,24 @@ int pd_conv2d(const pd_conv_params* p, void* stream) {
   PD_REQUIRE(p->stride == 1 || p->stride == 2, "pd_conv2d: stride must be 1 or 2 (got %d)", p->stride);
   PD_REQUIRE(!(p->upsample && p->stride != 1), "pd_conv2d: upsample with stride 2 is not a path op");
   PD_REQUIRE(p->C2 >= 0 && (p->C2 == 0 || p->x2 != nullptr), "pd_conv2d: C2 > 0 needs x2");
-  PD_REQUIRE(p->ldx >= p->C && p->ldo >= p->Cout && (p->C2 == 0 || p->ldx2 >= p->C2) &&
+  PD_REQUIRE(p->act == PD_ACT_NONE || p->act == PD_ACT_SILU || p->act == PD_ACT_GEGLU, "pd_conv2d: bad act %d", p->act);
+  PD_REQUIRE(p->ldx >= p->C && p->ldo >= (p->act == PD_ACT_GEGLU ? p->Cout / 2 : p->Cout) && (p->C2 == 0 || p->ldx2 >= p->C2) &&
                  (p->res == nullptr || p->ldr >= p->Cout) && (p->rowvec == nullptr || p->ldrv >= p->Cout),
              "pd_conv2d: pitch smaller than channel count");
   PD_REQUIRE(p->dtype == PD_F32 || p->dtype == PD_BF16, "pd_conv2d: bad dtype %d", p->dtype);
   PD_REQUIRE(p->out_dtype == PD_F32 || p->out_dtype == PD_BF16, "pd_conv2d: bad out_dtype %d", p->out_dtype);
   cudaStream_t s = (cudaStream_t)stream;
+  if (p->act == PD_ACT_GEGLU && p->engine == PD_ENGINE_SIMT) {
+    set_error("pd_conv2d: the GEGLU epilogue exists on the tcgen05 engine only (use pd_conv2d + pd_geglu)");
+    return PD_ERR_UNSUPPORTED;
+  }
   if (p->engine == PD_ENGINE_SIMT) return conv2d_simt(p, s);
   const char* why = "";
   bool tc_ok = conv2d_tc_supported(p, &why);
+  if (p->act == PD_ACT_GEGLU && !tc_ok) {
+    set_error("pd_conv2d: GEGLU epilogue: tcgen05 engine cannot run this shape: %s", why);
+    return PD_ERR_UNSUPPORTED;
+  }
   if (p->engine == PD_ENGINE_TC) {
     if (!tc_ok) {
       set_error("pd_conv2d: tcgen05 engine cannot run this shape: %s", why);

@@ -100,21 +100,6 @@ __global__ void cast2d_kernel(const TI* __restrict__ x, int ldx, TO* __restrict_
 }
 
 // ---- GEGLU ----------------------------------------------------------------------
-// erf by Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7 before the approximate exp / reciprocal): two SFU ops and
-// seven FMAs instead of erff()'s ~25 instructions — the bf16 GEGLU pass is otherwise ALU-bound, not HBM-bound.
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float az = fabsf(z);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = p * t * __expf(-az * az);          // 1 - erf(|z|)
-  const float erf_abs = 1.0f - e;
-  return 0.5f * x * (1.0f + copysignf(erf_abs, z));
-}
-
 // One CTA owns rows_per_cta (4 or 8) consecutive rows; thread t owns the 16-byte column vectors t, t + blockDim, ... of every
 // one of them, so the loop carries no index arithmetic (no divisions) and the loads of four rows (8 x 16 B per
 // thread) are in flight before the first GELU is evaluated.

@@ -55,7 +55,10 @@ struct TcArgs {
   } while (0)
 
 // ---- the kernel ---------------------------------------------------------------------------------
-// EPI: bit0 residual, bit1 timestep row-vector, bit2 SiLU (bf16 output through smem + TMA store); 8 = fp32 output
+// EPI: bit0 residual, bit1 timestep row-vector, bit2 SiLU (bf16 output through smem + TMA store); 8 = fp32 output;
+// 9 = GEGLU (FeedForward's first linear, attention.py:54-56): weight rows interleaved in blocks of 32 (value | gate),
+//     every 64-column accumulator slab becomes 32 output columns value * gelu(gate) — the [M, 8C] intermediate and the
+//     separate GEGLU pass over it never exist
 // CG: 1 = one CTA per 128-row tile; 2 = CTA pair (cluster of 2, tcgen05 cta_group::2) per 256-row tile: each CTA
 // stages its own 128 A rows and HALF of the B tile, which halves the L2 -> smem weight traffic per FLOP (the
 // 1-CTA kernel is bound by exactly that traffic: 128 x (128 + BN) bytes per 128 x BN x 64 MACs).
@@ -297,7 +300,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // one elected thread that drives its TMA traffic.  Per tile: (a) residual slabs are prefetched by TMA while the
     // MMAs of the tile are still running, (b) TMEM -> registers, (c) +bias, *alpha, +emb row, +residual, act in
     // registers/smem (flags are template parameters: no branches in the unrolled code), (d) TMA store.
-    constexpr bool RES = (EPI & 1) != 0, RV = (EPI & 2) != 0, ACT = (EPI & 4) != 0;
+    constexpr bool GEGLU = EPI == 9;
+    constexpr bool RES = !GEGLU && (EPI & 1) != 0, RV = !GEGLU && (EPI & 2) != 0, ACT = !GEGLU && (EPI & 4) != 0;
     const int ew = warp - 2, grp = ew >> 2;
     const int qd = warp & 3;               // TMEM lane quadrant this warp may touch
     const int r = qd * 32 + lane;          // accumulator row == tile pixel
@@ -363,6 +367,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
         }
         if (RES) mbar_wait(&rbar[i], (uint32_t)it & 1u, 500 + grp * 2 + i);
+        if constexpr (GEGLU) {
+          // slab columns [0,32) = values, [32,64) = their gates (load-time row interleave); BN % 64 == 0 (host-checked)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = min(n0 + col0, a.Cout - 64) + g * 8;   // slabs past Cout exist only in a partial last N tile (TMA clips)
+            const float4 x0v = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+            const float4 x1v = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
+            const float4 g0v = __ldg(reinterpret_cast<const float4*>(a.bias + n + 32));
+            const float4 g1v = __ldg(reinterpret_cast<const float4*>(a.bias + n + 36));
+            const float bx[8] = {x0v.x, x0v.y, x0v.z, x0v.w, x1v.x, x1v.y, x1v.z, x1v.w};
+            const float bg[8] = {g0v.x, g0v.y, g0v.z, g0v.w, g1v.x, g1v.y, g1v.z, g1v.w};
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              f[e] = (__uint_as_float(v[g * 8 + e]) + bx[e]) * gelu_erf_fast(__uint_as_float(v[32 + g * 8 + e]) + bg[e]);
+            const int off = r * 64 + ((g ^ ((r >> 1) & 3)) << 4);     // SWIZZLE_64B rows of the 32-column output box
+            *reinterpret_cast<bf16x8*>(stg + off) = pack8(f);
+          }
+        } else {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           if (g * 8 < w) {
@@ -400,10 +423,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             *cell = pack8(f);
           }
         }
+        }
         fence_proxy_async();               // generic-proxy smem writes -> visible to the TMA engine
         epi_bar_sync(bar_id);
         if (elected) {
-          tma_store_4d(w == 64 ? &map_o64 : &map_o32, stg, n0 + col0, x0, y0, b0);
+          if constexpr (GEGLU) tma_store_4d(&map_o32, stg, (n0 + col0) >> 1, x0, y0, b0);
+          else tma_store_4d(w == 64 ? &map_o64 : &map_o32, stg, n0 + col0, x0, y0, b0);
           tma_store_commit();
         }
       }
@@ -486,6 +511,9 @@ bool conv2d_tc_supported(const pd_conv_params* p, const char** why) {
   if (p->res && ((uintptr_t)p->res % 16 != 0 || (p->ldr * oe) % 16 != 0)) PD_NO("residual must be 16-byte aligned");
   if (p->bias && (uintptr_t)p->bias % 16 != 0) PD_NO("bias must be 16-byte aligned");
   if (p->rowvec && ((uintptr_t)p->rowvec % 16 != 0 || p->ldrv % 4 != 0)) PD_NO("rowvec must be 16-byte aligned");
+  if (p->act == PD_ACT_GEGLU && (p->out_dtype != PD_BF16 || p->Cout % 64 != 0 || p->res != nullptr || p->rowvec != nullptr ||
+                                 p->alpha != 1.0f))
+    PD_NO("GEGLU epilogue needs bf16 output, Cout % 64 == 0, no residual / row vector / alpha");
   if (p->stride == 2 && p->ksize != 3) PD_NO("stride 2 only with 3x3");
   if (p->stride == 2 && (p->H % 2 != 0 || p->W % 2 != 0)) PD_NO("stride 2 needs even H, W");
 #undef PD_NO
@@ -536,6 +564,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
   const int cg_max = (a.epi_tma && force_cg != 1) ? 2 : 1;
   for (int cg = cg_max; cg >= (force_cg == 2 && cg_max == 2 ? 2 : 1); --cg) {
     for (int bn = 256; bn >= 32; bn -= 32) {
+      if (p->act == PD_ACT_GEGLU && bn % 64 != 0) continue;
       int n_tiles = (p->Cout + bn - 1) / bn;
       int64_t tiles = (int64_t)((a.m_tiles + cg - 1) / cg) * n_tiles;
       int64_t workers = sms / cg;
@@ -586,7 +615,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
 
   CUtensorMap map_o64 = map_a0, map_o32 = map_a0, map_r64 = map_a0, map_r32 = map_a0;
   if (a.epi_tma) {
-    uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)gW, (uint64_t)gH, (uint64_t)gB};
+    uint64_t dims[4] = {(uint64_t)(p->act == PD_ACT_GEGLU ? p->Cout / 2 : p->Cout), (uint64_t)gW, (uint64_t)gH, (uint64_t)gB};
     uint32_t es[4] = {1, 1, 1, 1};
     for (int which = 0; which < 2; ++which) {
       const void* base = which == 0 ? p->out : p->res;
@@ -607,22 +636,23 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
   const size_t smem = (size_t)a.stages * stage_bytes + epi_bytes + 1024;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                            const CUtensorMap, const CUtensorMap, const TcArgs);
-  static const KernelFn kernels[2][9] = {
+  static const KernelFn kernels[2][10] = {
       {conv_tc_kernel<0, 1>, conv_tc_kernel<1, 1>, conv_tc_kernel<2, 1>, conv_tc_kernel<3, 1>, conv_tc_kernel<4, 1>,
-       conv_tc_kernel<5, 1>, conv_tc_kernel<6, 1>, conv_tc_kernel<7, 1>, conv_tc_kernel<8, 1>},
+       conv_tc_kernel<5, 1>, conv_tc_kernel<6, 1>, conv_tc_kernel<7, 1>, conv_tc_kernel<8, 1>, conv_tc_kernel<9, 1>},
       {conv_tc_kernel<0, 2>, conv_tc_kernel<1, 2>, conv_tc_kernel<2, 2>, conv_tc_kernel<3, 2>, conv_tc_kernel<4, 2>,
-       conv_tc_kernel<5, 2>, conv_tc_kernel<6, 2>, conv_tc_kernel<7, 2>, nullptr}};
+       conv_tc_kernel<5, 2>, conv_tc_kernel<6, 2>, conv_tc_kernel<7, 2>, nullptr, conv_tc_kernel<9, 2>}};
   static bool attr_set = false;
   if (!attr_set) {
     for (int c = 0; c < 2; ++c)
-      for (int i = 0; i < 9; ++i) {
+      for (int i = 0; i < 10; ++i) {
         if (kernels[c][i] == nullptr) continue;
         cudaError_t e = cudaFuncSetAttribute(kernels[c][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
       }
     attr_set = true;
   }
-  const int epi = a.epi_tma ? ((p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0)) : 8;
+  const int epi = !a.epi_tma ? 8 : p->act == PD_ACT_GEGLU ? 9
+                  : ((p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0));
   static const float* zero_bias = nullptr;   // the TMA epilogue always adds a bias vector
   if (a.epi_tma && a.bias == nullptr) {
     if (zero_bias == nullptr) {
@@ -683,7 +713,8 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   const int pad = p->ksize / 2;
   const int Ho = (p->H + 2 * pad - p->ksize) / p->stride + 1, Wo = (p->W + 2 * pad - p->ksize) / p->stride + 1;
   const TuneKey key{p->B * Ho * Wo, p->Cout, p->ksize * p->ksize * p->C + p->C2, p->ksize, p->stride, p->C2 > 0 ? 1 : 0,
-                    (p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0)};
+                    (p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0) |
+                        (p->act == PD_ACT_GEGLU ? 8 : 0)};
   auto it = g_tune.find(key);
   if (it != g_tune.end()) return conv2d_tc_impl(p, s, it->second);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;

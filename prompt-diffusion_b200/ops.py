@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (PD_ACT_NONE, PD_ACT_SILU, PD_BF16, PD_ENGINE_AUTO, PD_ENGINE_SIMT, PD_ENGINE_TC,
+from ._lib import (PD_ACT_GEGLU, PD_ACT_NONE, PD_ACT_SILU, PD_BF16, PD_ENGINE_AUTO, PD_ENGINE_SIMT, PD_ENGINE_TC,
                    PD_F32, ConvParams, check, lib)
 
 _DT = {torch.float32: PD_F32, torch.bfloat16: PD_BF16}
@@ -50,13 +50,15 @@ def _cuda(*ts):
 
 def conv2d(x, w, out, B, H, W, *, ksize=1, stride=1, upsample=False, bias=None, rowvec=None, res=None,
            x2=None, act=PD_ACT_NONE, alpha=1.0, engine=PD_ENGINE_AUTO):
-    """out[B*Ho*Wo, Cout] = act(alpha*(conv(x) [+ x2 @ Wskip] + bias) + rowvec[b] + res)."""
+    """out[B*Ho*Wo, Cout] = act(alpha*(conv(x) [+ x2 @ Wskip] + bias) + rowvec[b] + res).
+    ``act=PD_ACT_GEGLU``: w / bias hold 2F rows (see ``geglu_interleave``), out has F columns."""
     _cuda(x, w, out, bias, rowvec, res, x2)
     p = ConvParams()
     p.x, p.x2, p.w, p.bias, p.rowvec, p.res, p.out = _p(x), _p(x2), _p(w), _p(bias), _p(rowvec), _p(res), _p(out)
     p.B, p.H, p.W, p.C = B, H, W, x.shape[1]
     p.C2 = 0 if x2 is None else x2.shape[1]
-    p.Cout = out.shape[1]
+    # GEGLU epilogue: the GEMM has 2F columns (value | gate, interleaved in blocks of 32), the output F
+    p.Cout = out.shape[1] * (2 if act == PD_ACT_GEGLU else 1)
     p.ksize, p.stride, p.upsample = ksize, stride, int(bool(upsample))
     p.ldx = _ld(x)
     p.ldx2 = 0 if x2 is None else _ld(x2)
@@ -75,6 +77,18 @@ def conv2d(x, w, out, B, H, W, *, ksize=1, stride=1, upsample=False, bias=None, 
         raise ValueError(f"x has {x.shape[0]} pixels, expected {B * H * W}")
     check(lib.pd_conv2d(C.byref(p), _stream()), "pd_conv2d")
     return out
+
+
+def geglu_interleave(w: torch.Tensor) -> torch.Tensor:
+    """Reorder the rows of FeedForward's ``net.0.proj`` weight / bias ([2F, ...]: F value rows then F gate rows,
+    attention.py:49-56) into blocks of 32 value rows followed by their 32 gate rows — the layout
+    ``conv2d(..., act=PD_ACT_GEGLU)`` expects."""
+    F = w.shape[0] // 2
+    if w.shape[0] != 2 * F or F % 32 != 0:
+        raise ValueError("GEGLU interleave needs 2F rows with F a multiple of 32")
+    idx = torch.arange(F, device=w.device).reshape(F // 32, 32)
+    perm = torch.cat([idx, idx + F], dim=1).reshape(-1)
+    return w.index_select(0, perm).contiguous()
 
 
 def linear(x, w, out, **kw):

@@ -207,6 +207,27 @@ def test_layer_norm(dt, tol, C):
     assert rel_l2(out.float(), F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)) < tol
 
 
+@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (640, 1280)])
+def test_linear_geglu_epilogue_matches_linear_then_geglu(M, C):
+    """FeedForward's first linear with GEGLU fused into the tcgen05 epilogue (interleaved weight rows) vs torch fp32
+    on the same bf16 operands: x @ W^T + b -> chunk(2) -> value * gelu(gate) (attention.py:54-56)."""
+    from prompt_diffusion_b200._lib import PD_ACT_GEGLU, PD_ENGINE_TC
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(11)
+    F4 = 4 * C
+    x = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(2 * F4, C, device=DEV, generator=g) / C ** 0.5).to(torch.bfloat16)
+    b = torch.randn(2 * F4, device=DEV, generator=g)
+    out = torch.full((M, F4 + 8), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.linear(x, ops.geglu_interleave(w), out[:, :F4], bias=ops.geglu_interleave(b), act=PD_ACT_GEGLU, engine=PD_ENGINE_TC)
+    torch.cuda.synchronize()
+    assert bool((out[:, F4:] == 7.0).all()), "wrote past the output columns"
+    y = x.float() @ w.float().t() + b
+    val, gate = y.chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    assert rel_l2(out[:, :F4].float(), ref) < 6e-3
+
+
 @pytest.mark.parametrize("dt,tol", [(torch.float32, 1e-6), (torch.bfloat16, 6e-3)])
 def test_geglu(dt, tol):
     ops = _ops()
