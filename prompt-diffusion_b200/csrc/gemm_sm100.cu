@@ -329,9 +329,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int64_t m = ((int64_t)b * a.Ho + y) * a.Wo + x;
       const int n0 = nt * a.BN;
 
-      if (elected) {
-        tma_store_wait_read<0>();          // this group's staging buffers are no longer being read
-        if (RES) {
+      if (RES) {
+        // the residual slabs are prefetched INTO the staging buffers: both must have been drained by their stores
+        if (elected) {
+          tma_store_wait_read<0>();
           for (int i = 0; i < ns_mine; ++i) {
             const int sl = grp + 2 * i;
             const int w = sl < n64 ? 64 : 32;
@@ -339,8 +340,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             tma_load_4d(gstg + i * 16384, w == 64 ? &map_r64 : &map_r32, &rbar[i], n0 + sl * 64, x0, y0, b0);
           }
         }
+        epi_bar_sync(bar_id);
       }
-      epi_bar_sync(bar_id);
       mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
       tc_fence_after();
       if (ew == 0 && lane == 0) PD_DBG(2, it, 0);
@@ -366,7 +367,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           __syncwarp();
           if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
         }
-        if (RES) mbar_wait(&rbar[i], (uint32_t)it & 1u, 500 + grp * 2 + i);
+        if (RES) {
+          mbar_wait(&rbar[i], (uint32_t)it & 1u, 500 + grp * 2 + i);
+        } else {
+          // with two slabs per tile, buffer i was last read by the store issued two slabs ago: the most recent store
+          // (other buffer) may still be in flight, so its latency overlaps this slab instead of stalling every tile
+          if (elected) { if (ns_mine == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          epi_bar_sync(bar_id);
+        }
         if constexpr (GEGLU) {
           // slab columns [0,32) = values, [32,64) = their gates (load-time row interleave); BN % 64 == 0 (host-checked)
 #pragma unroll
