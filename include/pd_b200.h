@@ -68,6 +68,8 @@ int pd_prof_dump(const char* path_host);
 int pd_debug_timeline(void* dev_buf);
 /* tile-shape override of the tcgen05 conv engine: 0 auto, 1 single-CTA 128-row tiles, 2 CTA-pair 256-row tiles */
 int pd_debug_force_cta_group(int32_t cg);
+/* experiments: pin the N extent of the tile (multiple of 32 up to 256; 0 = heuristic) */
+int pd_debug_force_bn(int32_t bn);
 /* timing experiments on the conv engine (results are WRONG when non-zero): 1 = issue no MMAs, 2 = issue no TMA loads */
 int pd_debug_gemm_mode(int32_t mode);
 /* 1 (default): GroupNorm is one cooperative launch; 0: statistics kernel + apply kernel */
@@ -110,6 +112,8 @@ typedef struct pd_conv_params {
   int32_t out_dtype;   /* dtype of out and res                              */
   int32_t engine;      /* PD_ENGINE_*                                       */
   float alpha;
+  int32_t w_blocked;   /* 0: w is [Cout][K] (K contiguous).  1: k-block-major [K/64][Cout][64] (tcgen05 engine only,
+                        * K % 64 == 0): the B tile of a k-block is one contiguous run in HBM (measured: no gain) */
 } pd_conv_params;
 int pd_conv2d(const pd_conv_params* p, void* stream);
 

@@ -29,7 +29,7 @@ class ConvParams(C.Structure):
         ("ldx", C.c_int32), ("ldx2", C.c_int32), ("ldr", C.c_int32), ("ldo", C.c_int32),
         ("ldrv", C.c_int32),
         ("act", C.c_int32), ("dtype", C.c_int32), ("out_dtype", C.c_int32), ("engine", C.c_int32),
-        ("alpha", C.c_float),
+        ("alpha", C.c_float), ("w_blocked", C.c_int32),
     ]
 
 
@@ -44,6 +44,7 @@ SIGNATURES = {
     "pd_prof_dump": (C.c_int, [C.c_char_p]),
     "pd_debug_timeline": (C.c_int, [C.c_void_p]),
     "pd_debug_force_cta_group": (C.c_int, [C.c_int32]),
+    "pd_debug_force_bn": (C.c_int, [C.c_int32]),
     "pd_debug_gemm_mode": (C.c_int, [C.c_int32]),
     "pd_debug_group_norm_fused": (C.c_int, [C.c_int32]),
     "pd_debug_attention_timeline": (C.c_int, [C.c_void_p]),

@@ -33,6 +33,9 @@ constexpr float FA_RESCALE_THRESHOLD = 8.0f;   // log2 units
 #ifndef FA_ORDERED
 #define FA_ORDERED 0
 #endif
+#ifndef FA_POLY
+#define FA_POLY 0          // of every 8 element pairs, how many take the FMA-pipe exp2 (0..8); measured: 2 -> 792 us vs 0 -> 763 us (B16 h8 N4096 d40): the section is issue-bound, not SFU-bound
+#endif
 static unsigned long long* g_fa_dbg_host = nullptr;   // optional phase timeline (block 0 only), passed by value
 
 #define FA_DBG(slot, tile)                                                                       \
@@ -300,7 +303,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       if (g == 0) { if (j > 0) asm volatile("bar.sync 3, 256;" ::: "memory"); }
       else asm volatile("bar.sync 4, 256;" ::: "memory");
 #endif
-      // scale-and-subtract (packed FFMA2), exp2 (MUFU), row sum (packed FADD2), bf16 pack, P -> TMEM
+      // scale-and-subtract (packed FFMA2), exp2, row sum (packed FADD2), bf16 pack, P -> TMEM.  FA_POLY of every 8
+      // element pairs take the polynomial exp2 on the FMA pipe, the rest MUFU.EX2: the section is otherwise bound
+      // by the SFU alone (128 MUFU per row and tile) while the FMA pipe idles.
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
@@ -310,7 +315,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           float x0, x1, x2, x3;
           ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sc, sc, nm, nm);
           ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sc, sc, nm, nm);
-          x0 = ex2_approx(x0); x1 = ex2_approx(x1); x2 = ex2_approx(x2); x3 = ex2_approx(x3);
+          // pairs are numbered (e >> 1) and (e >> 1) + 1 within the 16-pair chunk; pair k mod 8 >= 8 - FA_POLY -> polynomial
+          if (((e >> 1) & 7) >= 8 - FA_POLY) exp2_poly2(x0, x1); else { x0 = ex2_approx(x0); x1 = ex2_approx(x1); }
+          if ((((e >> 1) + 1) & 7) >= 8 - FA_POLY) exp2_poly2(x2, x3); else { x2 = ex2_approx(x2); x3 = ex2_approx(x3); }
           fadd2(l0, l1, l0, l1, x0, x1);
           fadd2(l2, l3, l2, l3, x2, x3);
           pk[e >> 1] = pack_bf16x2(x0, x1);

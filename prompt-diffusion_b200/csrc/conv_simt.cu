@@ -255,9 +255,17 @@ int pd_conv2d(const pd_conv_params* p, void* stream) {
     set_error("pd_conv2d: the GEGLU epilogue exists on the tcgen05 engine only (use pd_conv2d + pd_geglu)");
     return PD_ERR_UNSUPPORTED;
   }
+  if (p->w_blocked && p->engine == PD_ENGINE_SIMT) {
+    set_error("pd_conv2d: k-block-major weights (w_blocked) are read by the tcgen05 engine only");
+    return PD_ERR_UNSUPPORTED;
+  }
   if (p->engine == PD_ENGINE_SIMT) return conv2d_simt(p, s);
   const char* why = "";
   bool tc_ok = conv2d_tc_supported(p, &why);
+  if (p->w_blocked && !tc_ok) {
+    set_error("pd_conv2d: w_blocked weights but the tcgen05 engine cannot run this shape: %s", why);
+    return PD_ERR_UNSUPPORTED;
+  }
   if (p->act == PD_ACT_GEGLU && !tc_ok) {
     set_error("pd_conv2d: GEGLU epilogue: tcgen05 engine cannot run this shape: %s", why);
     return PD_ERR_UNSUPPORTED;

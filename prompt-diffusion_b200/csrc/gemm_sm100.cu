@@ -43,6 +43,7 @@ struct TcArgs {
   int bw, bh, bn;               // pixel box of one 128-row M tile
   int tiles_x, tiles_y, tiles_b, m_tiles, n_tiles, BN, stages;   // BN = N extent of the (CG x 128) x BN tile
   unsigned long long* dbg;      // optional timeline buffer [3 roles][64 tiles][2] (globaltimer ns), CTA 0 only
+  int w_blocked;                // weights are k-block-major [K/64][Cout][64]: B tiles are contiguous in HBM (3-D map)
   int dbg_mode;                 // timing experiments only (wrong results): 1 = no MMAs issued, 2 = no TMA loads issued
   int epi_tma;                  // 1: bf16 output staged in smem and written by TMA (residual read by TMA too)
   uint32_t idesc;
@@ -155,10 +156,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(CG * stage_bytes));
             if (CG == 2) {
               tma_load_4d_2sm(sa, am, &full_bar[stage], ac0, ax, ay, b0);
-              tma_load_2d_2sm(sb, &map_w, &full_bar[stage], wk, n0);
+              if (a.w_blocked) tma_load_3d_2sm(sb, &map_w, &full_bar[stage], 0, n0, wk >> 6);
+              else tma_load_2d_2sm(sb, &map_w, &full_bar[stage], wk, n0);
             } else {
               tma_load_4d(sa, am, &full_bar[stage], ac0, ax, ay, b0);
-              tma_load_2d(sb, &map_w, &full_bar[stage], wk, n0);
+              if (a.w_blocked) tma_load_3d(sb, &map_w, &full_bar[stage], 0, n0, wk >> 6);
+              else tma_load_2d(sb, &map_w, &full_bar[stage], wk, n0);
             }
           }
           __syncwarp();
@@ -461,6 +464,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, ksize, stride, BN, m_tiles, n_tiles, stages, grid, cg; };
 static bool g_prof_on = false;
 static int g_dbg_mode = 0;
+static int g_force_bn = 0;   // experiments: pin the N extent of the tile (multiple of 32, <= 256)
 static int g_force_cg = 0;   // 0 auto, 1 single-CTA tiles only, 2 CTA pairs whenever the epilogue allows (tests / A-B timing)
 static unsigned long long* g_dbg = nullptr;
 static std::vector<ProfRec> g_prof;
@@ -573,6 +577,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
   for (int cg = cg_max; cg >= (force_cg == 2 && cg_max == 2 ? 2 : 1); --cg) {
     for (int bn = 256; bn >= 32; bn -= 32) {
       if (p->act == PD_ACT_GEGLU && bn % 64 != 0) continue;
+      if (g_force_bn != 0 && bn != g_force_bn) continue;
       int n_tiles = (p->Cout + bn - 1) / bn;
       int64_t tiles = (int64_t)((a.m_tiles + cg - 1) / cg) * n_tiles;
       int64_t workers = sms / cg;
@@ -612,7 +617,15 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
   } else {
     map_a1 = map_a0;
   }
-  {
+  a.w_blocked = p->w_blocked ? 1 : 0;
+  if (a.w_blocked) {
+    uint64_t dims[3] = {(uint64_t)TC_BK, (uint64_t)p->Cout, (uint64_t)(Ktot / TC_BK)};
+    uint64_t strides[2] = {(uint64_t)TC_BK * 2, (uint64_t)p->Cout * TC_BK * 2};
+    uint32_t box[3] = {TC_BK, (uint32_t)(a.BN / CGv), 1};
+    uint32_t es[3] = {1, 1, 1};
+    int rc = encode_map(&map_w, p->w, 3, dims, strides, box, es, "Wblocked");
+    if (rc) return rc;
+  } else {
     uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)p->Cout};
     uint64_t strides[1] = {(uint64_t)Ktot * 2};
     uint32_t box[2] = {TC_BK, (uint32_t)(a.BN / CGv)};
@@ -760,6 +773,7 @@ extern "C" {
 int pd_debug_timeline(void* dev_buf) { pd::g_dbg = (unsigned long long*)dev_buf; return 0; }
 // tile-shape override of the tcgen05 engine: 0 auto, 1 single-CTA tiles, 2 CTA-pair (cta_group::2) tiles
 int pd_debug_gemm_mode(int mode) { pd::g_dbg_mode = mode; return 0; }
+int pd_debug_force_bn(int bn) { pd::g_force_bn = (bn >= 32 && bn <= 256 && bn % 32 == 0) ? bn : 0; return 0; }
 int pd_debug_force_cta_group(int cg) { pd::g_force_cg = (cg == 1 || cg == 2) ? cg : 0; return 0; }
 // enable (1) / disable (0) per-launch timing of the tcgen05 engine; enabling clears the log
 int pd_prof_enable(int on) {

@@ -66,6 +66,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -257,6 +262,11 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* ma
       "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(s_u32(dst)), "l"(map), "r"(s_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -282,6 +292,26 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(s_u32(bar)), "r"(rank) : "memory");
+}
+
+
+// exp2 of two values on the FMA / ALU pipes (no SFU): Cody-Waite split x = n + f with the 1.5 * 2^23 magic-number
+// add, degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max rel. error 1.9e-4: far below the bf16 rounding the
+// result gets as an MMA operand), exponent insertion by integer add.  Used for a fraction of the softmax
+// exponentials so that MUFU.EX2 (16 lanes / clk / SM) stops being the only pipe the attention kernel waits on.
+__device__ __forceinline__ void exp2_poly2(float& x0, float& x1) {
+  const float MAGIC = 12582912.0f;                       // 1.5 * 2^23: round-to-nearest-integer in the low mantissa bits
+  x0 = fmaxf(x0, -125.0f);                               // keeps the biased exponent positive (also maps -inf)
+  x1 = fmaxf(x1, -125.0f);
+  float t0, t1, n0, n1, f0, f1, p0, p1;
+  fadd2(t0, t1, x0, x1, MAGIC, MAGIC);
+  fadd2(n0, n1, t0, t1, -MAGIC, -MAGIC);
+  ffma2(f0, f1, n0, n1, -1.0f, -1.0f, x0, x1);           // f = x - round(x)
+  ffma2(p0, p1, f0, f1, 0.0558755025f, 0.0558755025f, 0.2422944456f, 0.2422944456f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.6931272745f, 0.6931272745f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.9999482632f, 0.9999482632f);
+  x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -66,6 +66,7 @@ def conv2d(x, w, out, B, H, W, *, ksize=1, stride=1, upsample=False, bias=None, 
     p.ldo = _ld(out)
     p.ldrv = 0 if rowvec is None else _ld(rowvec)
     p.act, p.dtype, p.out_dtype, p.engine, p.alpha = act, dt_code(x), dt_code(out), engine, float(alpha)
+    p.w_blocked = int(bool(getattr(w, "_pd_blocked", False)))
     if w.dtype != x.dtype or (x2 is not None and x2.dtype != x.dtype):
         raise TypeError("x, x2 and w must share a dtype")
     if res is not None and res.dtype != out.dtype:
@@ -89,6 +90,18 @@ def geglu_interleave(w: torch.Tensor) -> torch.Tensor:
     idx = torch.arange(F, device=w.device).reshape(F // 32, 32)
     perm = torch.cat([idx, idx + F], dim=1).reshape(-1)
     return w.index_select(0, perm).contiguous()
+
+
+def block_weight(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, K] (K contiguous, K % 64 == 0) -> the same storage size laid out k-block-major [K/64][Cout][64] and
+    tagged so that ``conv2d`` passes ``w_blocked=1`` (see pd_conv_params).  The returned tensor keeps the logical
+    shape [Cout, K]; only the tcgen05 engine can read it."""
+    cout, k = w.shape
+    if k % 64 != 0:
+        raise ValueError("block_weight needs K % 64 == 0")
+    out = w.reshape(cout, k // 64, 64).permute(1, 0, 2).contiguous().reshape(cout, k)
+    out._pd_blocked = True
+    return out
 
 
 def linear(x, w, out, **kw):

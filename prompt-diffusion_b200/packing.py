@@ -20,6 +20,12 @@ from . import ops
 from .config import CLDMConfig, Conv, Down, HINT_STACK, Res, ST, Up, build_topology
 
 
+# k-block-major weight layout (ops.block_weight): supported by the tcgen05 engine, measured on B200 at BASELINE
+# config 2 and found ~3 % SLOWER than plain [Cout][K] rows (18.2 vs 17.6 ms of GEMM time per denoising step: the
+# strided 128-byte pieces spread over more HBM channels than one contiguous 12-32 KiB run), so it stays off.
+BLOCK_WEIGHTS = False
+
+
 def pad_channels(c: int, dt: torch.dtype) -> int:
     if dt == torch.bfloat16 and c >= 16 and c % 64 != 0:
         return (c + 63) // 64 * 64
@@ -96,9 +102,22 @@ class Packer:
             bias = (bias + self.vec(skip_key + ".bias")).contiguous()
         if cout_pad != cout and bias is not None:
             bias = torch.cat([bias, torch.zeros(cout_pad - cout, dtype=bias.dtype, device=bias.device)]).contiguous()
-        pc = PConv(out, bias, cin, cin_pad, cout, kh, stride, c2)
+        pc = PConv(self.block(out), bias, cin, cin_pad, cout, kh, stride, c2)
         pc.cout_pad = cout_pad
         return pc
+
+    def block(self, w: torch.Tensor) -> torch.Tensor:
+        """Optional k-block-major weight layout for the layers the tcgen05 engine runs (see BLOCK_WEIGHTS)."""
+        if BLOCK_WEIGHTS and self.dt == torch.bfloat16 and w.shape[1] % 64 == 0 and w.shape[0] % 8 == 0:
+            return ops.block_weight(w)
+        return w
+
+    def unblocked(self, key: str) -> torch.Tensor:
+        """[Cout, K] K-major weight of a linear layer in the compute dtype (before any blocking)."""
+        w = self.t(key + ".weight")
+        out = torch.empty((w.shape[0], w.shape[1]), dtype=self.dt, device=self.device)
+        ops.repack_conv_weight(w, out)
+        return out
 
     def stacked_linear(self, keys: List[str], with_bias: bool) -> PConv:
         ws = [self.t(k + ".weight") for k in keys]
@@ -110,7 +129,7 @@ class Packer:
             ops.repack_conv_weight(w, out[r:r + w.shape[0]])
             r += w.shape[0]
         bias = torch.cat([self.vec(k + ".bias") for k in keys]).contiguous() if with_bias else None
-        return PConv(out, bias, cin, cin, cout, 1, 1)
+        return PConv(self.block(out), bias, cin, cin, cout, 1, 1)
 
     def res(self, layer: Res) -> PRes:
         k = layer.key
@@ -141,8 +160,8 @@ class Packer:
         # bf16 mode: GEGLU runs in ff1's GEMM epilogue -> rows interleaved (32 values | 32 gates), see ops.geglu_interleave
         s.ff1_geglu = None
         if self.dt == torch.bfloat16 and (4 * layer.ch) % 64 == 0:
-            s.ff1_geglu = PConv(ops.geglu_interleave(s.ff1.w), ops.geglu_interleave(s.ff1.bias), s.ff1.cin, s.ff1.cin_pad,
-                                s.ff1.cout, 1, 1)
+            s.ff1_geglu = PConv(self.block(ops.geglu_interleave(self.unblocked(tb + ".ff.net.0.proj"))),
+                                ops.geglu_interleave(s.ff1.bias), s.ff1.cin, s.ff1.cin_pad, s.ff1.cout, 1, 1)
             s.ff1 = None            # the plain layout is not needed (saves 0.4 GB of weights)
         s.ff2 = self.conv(tb + ".ff.net.2")
         s.proj_out = self.conv(k + ".proj_out")

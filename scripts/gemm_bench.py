@@ -9,10 +9,13 @@ from prompt_diffusion_b200 import ops
 from prompt_diffusion_b200._lib import PD_ENGINE_TC
 
 dev = "cuda"
+BLOCKED = False
 def run(B, H, W, C, N, ks, res, iters=20, warm=3, rowvec=False):
     M = B * H * W
     x = torch.randn(M, C, device=dev).to(torch.bfloat16)
     w = (torch.randn(N, ks * ks * C, device=dev) / math.sqrt(ks * ks * C)).to(torch.bfloat16)
+    if BLOCKED:
+        w = ops.block_weight(w)
     bias = torch.randn(N, device=dev)
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     r = torch.randn(M, N, device=dev).to(torch.bfloat16) if res else None
@@ -40,9 +43,11 @@ def run(B, H, W, C, N, ks, res, iters=20, warm=3, rowvec=False):
 ap = argparse.ArgumentParser()
 ap.add_argument("--one", nargs=7, type=int, default=None, help="B H W C N ks res")
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--blocked", action="store_true", help="k-block-major weight layout")
 ap.add_argument("--small", action="store_true", help="fixed-overhead study: tiny and short-K GEMMs")
 ap.add_argument("--modes", action="store_true", help="timing experiment: full kernel vs no-MMA vs no-TMA, per tile shape")
 a = ap.parse_args()
+BLOCKED = a.blocked
 if a.small:
     print("   B   HxW     C     N ks res |     us")
     for s_ in [(1, 1, 128, 64, 64, 1, 0), (1, 1, 128 * 148, 64, 64, 1, 0), (1, 1, 128 * 148, 320, 128, 1, 0), (1, 1, 128 * 148, 320, 256, 1, 0),

@@ -35,7 +35,7 @@ def _pm(x):
 
 
 def _conv_case(dt, engine, B, H, W, C, Cout, ksize, stride=1, upsample=False, C2=0, rowvec=False, res=False,
-               act=0, alpha=1.0, out_dt=None, ldo_extra=0, seed=0):
+               act=0, alpha=1.0, out_dt=None, ldo_extra=0, seed=0, blocked=False):
     ops = _ops()
     g = torch.Generator(device=DEV).manual_seed(seed)
     out_dt = dt if out_dt is None else out_dt
@@ -72,6 +72,8 @@ def _conv_case(dt, engine, B, H, W, C, Cout, ksize, stride=1, upsample=False, C2
     M = B * Ho * Wo
     full = torch.full((M, Cout + ldo_extra), 7.0, dtype=out_dt, device=DEV)
     out = full[:, ldo_extra:] if ldo_extra else full
+    if blocked:
+        wp = ops.block_weight(wp)          # k-block-major layout (what the packed model weights use)
     ops.conv2d(_pm(x).to(dt), wp, out, B, H, W, ksize=ksize, stride=stride, upsample=upsample, bias=bias,
                rowvec=rv, res=res_pm, x2=x2_pm, act=act, alpha=alpha, engine=engine)
     torch.cuda.synchronize()
@@ -128,6 +130,20 @@ def test_conv_tcgen05_bf16(case):
     from prompt_diffusion_b200._lib import PD_ENGINE_TC
     err = _conv_case(torch.bfloat16, PD_ENGINE_TC, **case)
     assert err < 6e-3, err
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05_bf16_blocked_weights(case):
+    """Same cases with the weights in the k-block-major layout [K/64][Cout][64] (3-D tensor map for B)."""
+    from prompt_diffusion_b200._lib import PD_ENGINE_TC
+    err = _conv_case(torch.bfloat16, PD_ENGINE_TC, blocked=True, **case)
+    assert err < 6e-3, err
+
+
+def test_conv_blocked_weights_rejected_by_simt():
+    from prompt_diffusion_b200._lib import PD_ENGINE_SIMT
+    with pytest.raises(RuntimeError):
+        _conv_case(torch.bfloat16, PD_ENGINE_SIMT, B=1, H=8, W=8, C=64, Cout=64, ksize=3, blocked=True)
 
 
 @pytest.mark.parametrize("cg", [1, 2])
