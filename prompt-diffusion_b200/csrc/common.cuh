@@ -38,7 +38,15 @@ template <> struct Dt<bf16> {
   __device__ __forceinline__ static void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// bf16-path SiLU (an IEEE divide + expf here made the bf16 GroupNorm pass ~55 % issue-bound, ncu: profiles/).
+// silu(x) = x * sigmoid(x) = h + h * tanh(h), h = x / 2: ONE SFU op (tanh.approx, max rel. error 2^-11 — an order
+// below bf16 rounding) and two FMA-pipe ops
+__device__ __forceinline__ float silu_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 // accurate variant for the fp32 mode (expf, IEEE divide)
 __device__ __forceinline__ float silu_acc(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) {

@@ -338,13 +338,12 @@ gn_fused_kernel(const T* __restrict__ x, int ldx, TO* __restrict__ out, int ldo,
     const int j = tx + ps * g.tx_n;
     if (j >= g.vpr) break;
     const int c0 = j * V;
-    float mean[V], a[V], bt[V];
+    float a[V], bt[V];                     // y = x * a + bt with a = rstd * gamma, bt = beta - mean * a
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const int gi = (c0 + k) / cpg;
-      mean[k] = s_g[2 * gi];
       a[k] = s_g[2 * gi + 1] * gamma[c0 + k];
-      bt[k] = beta[c0 + k];
+      bt[k] = fmaf(-s_g[2 * gi], a[k], beta[c0 + k]);
     }
     const T* xc = base + c0;
     TO* oc = out + (int64_t)b * HW * ldo + c0;
@@ -355,8 +354,8 @@ gn_fused_kernel(const T* __restrict__ x, int ldx, TO* __restrict__ out, int ldo,
       if (two) VecIO<T>::ld(xc + (int64_t)(r + g.ty_n) * ldx, f1);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        float y0 = (f0[k] - mean[k]) * a[k] + bt[k];
-        float y1 = two ? (f1[k] - mean[k]) * a[k] + bt[k] : 0.f;
+        float y0 = fmaf(f0[k], a[k], bt[k]);
+        float y1 = two ? fmaf(f1[k], a[k], bt[k]) : 0.f;
         if (act == PD_ACT_SILU) {
           y0 = sizeof(TO) == 4 ? silu_acc(y0) : silu_f(y0);
           y1 = sizeof(TO) == 4 ? silu_acc(y1) : silu_f(y1);
