@@ -153,7 +153,8 @@ def run_reference(args):
             times.append(r["seconds_per_image_step"])
     t = sum(times) / len(times)
     val = 1.0 / (args.ddim_steps * t)
-    line = {"impl": "reference", "metric": "images_per_s_512x512_50step_ddim_cfg", "value": val, "unit": "images/s",
+    line = {"impl": "reference", "metric": f"images_per_s_{args.size}x{args.size}_{args.ddim_steps}step_ddim_cfg", "value": val,
+            "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t * args.ddim_steps * args.batch * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -263,7 +264,7 @@ def main():
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
     del host_inputs
 
-    line = {"metric": "images_per_s_512x512_50step_ddim_cfg", "value": value, "unit": "images/s", "n_gpus": world,
+    line = {"metric": f"images_per_s_{size}x{size}_{S}step_ddim_cfg", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "ms_per_denoise_step": ms_per_step / S, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.mode, "data": "synthetic", "config": workload_config(args, "gpu"),
@@ -295,9 +296,20 @@ def main():
         _lib.lib.pd_prof_enable(0)
         step_ms = ev0.elapsed_time(ev1) / reps
         achieved = fl.value / (ms.value * 1e-3) / 1e12
+        # DRAM traffic of the same kernel set from the committed ncu pass over one denoising step
+        # (scripts/gpu_final_profile.sh -> profiles/r01_conv_tc_traffic.json): bytes per launch, like `achieved`
+        traffic, traffic_note = None, "no ncu traffic capture committed"
+        try:
+            tj = json.load(open(os.path.join(REPO, "profiles", "r01_conv_tc_traffic.json")))
+            traffic = tj["dram_bytes_per_denoise_step"] / tj["launches_per_denoise_step"]
+            traffic_note = (f"ncu dram__bytes_read+write summed over the {tj['launches_per_denoise_step']} conv_tc launches of one "
+                            f"denoising step ({tj['dram_bytes_per_denoise_step'] / 1e9:.2f} GB), divided by the launch count; "
+                            f"algorithmic operand bytes of the same launches: {tj.get('algorithmic_bytes_per_denoise_step', 0) / 1e9:.2f} GB")
+        except Exception:
+            pass
         line["roofline"] = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM: conv3x3/conv1x1/linear)",
                             "achieved": achieved, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": None,
+                            "frac": achieved / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_note": traffic_note,
                             "peak_source": f"{pk['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                             "launches_per_denoise_step": int(n.value // reps),
                             "kernel_ms_per_denoise_step": ms.value / reps,
