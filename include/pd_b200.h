@@ -70,6 +70,9 @@ int pd_debug_timeline(void* dev_buf);
 int pd_debug_force_cta_group(int32_t cg);
 /* experiments: pin the N extent of the tile (multiple of 32 up to 256; 0 = heuristic) */
 int pd_debug_force_bn(int32_t bn);
+/* together with a forced CTA group: 1 = stream-K schedule of the tcgen05 conv engine wherever it applies (the (tile, k-block)
+ * space is cut evenly over the CTAs; partial tiles are summed in K order by the last CTA to arrive), 0 = data-parallel */
+int pd_debug_force_stream_k(int32_t on);
 /* timing experiments on the conv engine (results are WRONG when non-zero): 1 = issue no MMAs, 2 = issue no TMA loads */
 int pd_debug_gemm_mode(int32_t mode);
 /* 1 (default): GroupNorm is one cooperative launch; 0: statistics kernel + apply kernel */
@@ -114,6 +117,13 @@ typedef struct pd_conv_params {
   float alpha;
   int32_t w_blocked;   /* 0: w is [Cout][K] (K contiguous).  1: k-block-major [K/64][Cout][64] (tcgen05 engine only,
                         * K % 64 == 0): the B tile of a k-block is one contiguous run in HBM (measured: no gain) */
+  /* LayerNorm folded into a linear layer (tcgen05 engine, bf16, ksize 1, act NONE or GEGLU, no res / rowvec, alpha 1):
+   * x is the UN-normalised tensor, w holds W[n,k] * gamma[k], bias holds bias[n] + sum_k W[n,k] * beta[k], and
+   *   out[m,n] = rstd[m] * (acc[m,n] - mean[m] * ln_colsum[n]) + bias[n]      (then GEGLU if requested)
+   * which equals Linear(LayerNorm(x)) (attention.py:271-275: attn1 / attn2.to_q / ff of BasicTransformerBlock)
+   * without ever writing the normalised tensor.  NULL = off. */
+  const float* ln_stats;   /* [rows][2] fp32 (mean, rstd) from pd_layer_norm_stats */
+  const float* ln_colsum;  /* [Cout] fp32: sum_k of the (rounded) scaled weights of row n */
 } pd_conv_params;
 int pd_conv2d(const pd_conv_params* p, void* stream);
 
@@ -135,6 +145,11 @@ int pd_group_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const floa
                   const float* beta, float* partial, int32_t B, int32_t HW, int32_t C,
                   int32_t groups, float eps, int32_t act, int32_t dtype, int32_t out_dtype,
                   void* stream);
+
+/* Row statistics of LayerNorm: stats[row] = (mean, 1/sqrt(var + eps)) in fp32, for the folded form of
+ * LayerNorm -> Linear (pd_conv_params.ln_stats). */
+int pd_layer_norm_stats(const void* x, int32_t ldx, float* stats, int64_t rows, int32_t C, float eps,
+                        int32_t dtype, void* stream);
 
 /* LayerNorm over the last dim (nn.LayerNorm, attention.py:263-265, eps 1e-5). */
 int pd_layer_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const float* gamma,

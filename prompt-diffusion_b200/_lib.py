@@ -30,6 +30,7 @@ class ConvParams(C.Structure):
         ("ldrv", C.c_int32),
         ("act", C.c_int32), ("dtype", C.c_int32), ("out_dtype", C.c_int32), ("engine", C.c_int32),
         ("alpha", C.c_float), ("w_blocked", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p),
     ]
 
 
@@ -45,6 +46,8 @@ SIGNATURES = {
     "pd_debug_timeline": (C.c_int, [C.c_void_p]),
     "pd_debug_force_cta_group": (C.c_int, [C.c_int32]),
     "pd_debug_force_bn": (C.c_int, [C.c_int32]),
+    "pd_debug_force_stream_k": (C.c_int, [C.c_int32]),
+    "pd_layer_norm_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "pd_debug_gemm_mode": (C.c_int, [C.c_int32]),
     "pd_debug_group_norm_fused": (C.c_int, [C.c_int32]),
     "pd_debug_attention_timeline": (C.c_int, [C.c_void_p]),

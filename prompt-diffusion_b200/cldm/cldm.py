@@ -166,28 +166,43 @@ class _Net:
         ops.group_norm(x, g, s.gn.gamma, s.gn.beta, B, N, eps=1e-6, act=PD_ACT_NONE)
         a = self.buf("t_a", M, Cc)
         self.conv(s.proj_in, g, a, 1, 1, M)
-        ln = self.buf("t_ln", M, Cc)
-        # attn1 (self)
-        ops.layer_norm(a, ln, s.ln1.gamma, s.ln1.beta)
+        fold = s.ln_folded
+        ln = None if fold else self.buf("t_ln", M, Cc)
+        st = self.buf("t_lnstats", M, 2, dtype=torch.float32) if fold else None
+        # attn1 (self).  Folded form: row statistics only, the GEMM reads the raw stream (packing.Packer.folded)
         qkv = self.buf("t_qkv", M, 3 * Cc)
-        ops.linear(ln, s.wqkv.w, qkv)
+        if fold:
+            ops.layer_norm_stats(a, st)
+            ops.linear(a, s.wqkv.w, qkv, bias=s.wqkv.bias, ln_stats=st, ln_colsum=s.wqkv.colsum)
+        else:
+            ops.layer_norm(a, ln, s.ln1.gamma, s.ln1.beta)
+            ops.linear(ln, s.wqkv.w, qkv)
         att = self.buf("t_att", M, Cc)
         ops.attention(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], att, B, s.heads, N, N, s.d)
         b = self.buf("t_b", M, Cc)
         ops.linear(att, s.out1.w, b, bias=s.out1.bias, res=a)
         # attn2 (cross, 77 keys)
-        ops.layer_norm(b, ln, s.ln2.gamma, s.ln2.beta)
         q2 = self.buf("t_q", M, Cc)
-        ops.linear(ln, s.wq2.w, q2)
+        if fold:
+            ops.layer_norm_stats(b, st)
+            ops.linear(b, s.wq2.w, q2, bias=s.wq2.bias, ln_stats=st, ln_colsum=s.wq2.colsum)
+        else:
+            ops.layer_norm(b, ln, s.ln2.gamma, s.ln2.beta)
+            ops.linear(ln, s.wq2.w, q2)
         kv = ctx_kv[s.key]
         ops.attention(q2, kv[:, :Cc], kv[:, Cc:], att, B, s.heads, N, ctx_len, s.d)
         ops.linear(att, s.out2.w, a, bias=s.out2.bias, res=b)
         # feed-forward (GEGLU)
-        ops.layer_norm(a, ln, s.ln3.gamma, s.ln3.beta)
         gg = self.buf("t_gg", M, 4 * Cc)
-        if s.ff1_geglu is not None:        # bf16: x * gelu(gate) in the GEMM epilogue, the [M, 8C] tensor never exists
+        if fold:
+            ops.layer_norm_stats(a, st)
+            ops.linear(a, s.ff1_geglu.w, gg, bias=s.ff1_geglu.bias, act=PD_ACT_GEGLU, ln_stats=st,
+                       ln_colsum=s.ff1_geglu.colsum)
+        elif s.ff1_geglu is not None:      # bf16: x * gelu(gate) in the GEMM epilogue, the [M, 8C] tensor never exists
+            ops.layer_norm(a, ln, s.ln3.gamma, s.ln3.beta)
             ops.linear(ln, s.ff1_geglu.w, gg, bias=s.ff1_geglu.bias, act=PD_ACT_GEGLU)
         else:
+            ops.layer_norm(a, ln, s.ln3.gamma, s.ln3.beta)
             ff = self.buf("t_ff", M, 8 * Cc)
             ops.linear(ln, s.ff1.w, ff, bias=s.ff1.bias)
             ops.geglu(ff, gg)

@@ -255,6 +255,14 @@ int pd_conv2d(const pd_conv_params* p, void* stream) {
     set_error("pd_conv2d: the GEGLU epilogue exists on the tcgen05 engine only (use pd_conv2d + pd_geglu)");
     return PD_ERR_UNSUPPORTED;
   }
+  if (p->ln_stats != nullptr || p->ln_colsum != nullptr) {
+    const char* why_ln = "";
+    if (p->engine == PD_ENGINE_SIMT || !conv2d_tc_supported(p, &why_ln)) {
+      set_error("pd_conv2d: the folded-LayerNorm epilogue exists on the tcgen05 engine only%s%s",
+                p->engine == PD_ENGINE_SIMT ? "" : ": ", why_ln);
+      return PD_ERR_UNSUPPORTED;
+    }
+  }
   if (p->w_blocked && p->engine == PD_ENGINE_SIMT) {
     set_error("pd_conv2d: k-block-major weights (w_blocked) are read by the tcgen05 engine only");
     return PD_ERR_UNSUPPORTED;

@@ -10,7 +10,7 @@
 //   use the tensor map's element strides.  An optional second K segment (1x1 tap of a
 //   second tensor) fuses ResBlock's skip_connection into out_layers' conv.
 // * Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
-//   alloc), warps 2-5 = epilogue.  smem ring (full/empty mbarriers) between TMA and MMA,
+//   alloc), warps 4-11 = epilogue (registers moved to them with setmaxnreg).  smem ring (full/empty mbarriers) between TMA and MMA,
 //   two TMEM accumulators (2 x 256 columns) between MMA and epilogue, so tile i's
 //   epilogue overlaps tile i+1's MMAs.
 // * Epilogue: tcgen05.ld -> alpha*(acc+bias) + timestep row-vector + residual (ControlNet
@@ -27,7 +27,12 @@ namespace pd {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps
+constexpr int TC_THREADS = 384;            // warp group 0: TMA warp, MMA warp, 2 idle; warp groups 1-2: 8 epilogue warps
+// Register budget (setmaxnreg, per warp group): the kernel launches with 168 registers per thread (65536 / 384);
+// the control warp group gives back all but 88, which lets each epilogue warp group grow to 208:
+// 128 * 88 + 256 * 208 = 64512 <= 65536.
+constexpr int TC_REGS_CTRL = 88;
+constexpr int TC_REGS_EPI = 208;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_BUDGET = 227 * 1024 - 2048;
@@ -45,8 +50,51 @@ struct TcArgs {
   unsigned long long* dbg;      // optional timeline buffer [3 roles][64 tiles][2] (globaltimer ns), CTA 0 only
   int w_blocked;                // weights are k-block-major [K/64][Cout][64]: B tiles are contiguous in HBM (3-D map)
   int dbg_mode;                 // timing experiments only (wrong results): 1 = no MMAs issued, 2 = no TMA loads issued
-  int epi_tma;                  // 1: bf16 output staged in smem and written by TMA (residual read by TMA too)
+  int epi_tma;                  // 1: bf16 output staged in smem and written by TMA
+  int sk;                       // 1: stream-K schedule (the (tile, k-block) space is cut evenly over the workers)
+  float* sk_ws;                 // stream-K partial accumulators [worker][2 slots][CG][256 cols][128 rows] fp32
+  int* sk_cnt;                  // stream-K arrival counters [tile][CG], zero between launches (the reducer resets its own)
+  const float2* ln_stats;       // folded LayerNorm: (mean, rstd) per GEMM row
+  const float* ln_colsum;       // folded LayerNorm: column sums of the gamma-scaled weights
   uint32_t idesc;
+};
+
+constexpr int SK_SLOT_FLOATS = 256 * 128;   // one CTA's half of a partial tile: up to 256 columns x 128 rows
+
+// Work decomposition shared by the three roles of a CTA.  Data-parallel: whole tiles, strided over the workers.
+// Stream-K: the U = tiles * nkb (tile, k-block) units are cut into `nworkers` equal contiguous ranges, so a worker
+// runs at most one tail piece of a tile (its first piece), whole tiles, and one head piece (its last piece); no
+// wave quantisation, and every CTA streams the same number of k-blocks.
+struct PieceIter {
+  int sk, nkb, num_tiles, step, tile;
+  long long u, u_end;
+  __device__ PieceIter(int sk_, int worker, int nworkers, int num_tiles_, int nkb_) {
+    sk = sk_; nkb = nkb_; num_tiles = num_tiles_; step = nworkers; tile = worker; u = 0; u_end = 0;
+    if (sk) {
+      const long long U = (long long)num_tiles * nkb;
+      u = U * worker / nworkers;
+      u_end = U * (worker + 1) / nworkers;
+    }
+  }
+  __device__ bool next(int& t, int& kb0, int& kb1) {
+    if (!sk) {
+      if (tile >= num_tiles) return false;
+      t = tile; kb0 = 0; kb1 = nkb; tile += step;
+      return true;
+    }
+    if (u >= u_end) return false;
+    t = (int)(u / nkb);
+    kb0 = (int)(u - (long long)t * nkb);
+    const long long rem = u_end - u;
+    kb1 = rem < (long long)(nkb - kb0) ? kb0 + (int)rem : nkb;
+    u += kb1 - kb0;
+    return true;
+  }
+  // tile of the piece the following next() will return, -1 if none (called after next())
+  __device__ int peek_tile() const {
+    if (!sk) return tile < num_tiles ? tile : -1;
+    return u < u_end ? (int)(u / nkb) : -1;
+  }
 };
 
 #define PD_DBG(role, tileidx, which)                                                        \
@@ -60,10 +108,12 @@ struct TcArgs {
 // 9 = GEGLU (FeedForward's first linear, attention.py:54-56): weight rows interleaved in blocks of 32 (value | gate),
 //     every 64-column accumulator slab becomes 32 output columns value * gelu(gate) — the [M, 8C] intermediate and the
 //     separate GEGLU pass over it never exist
+// 10 / 11 = plain / GEGLU epilogue of a linear layer with the preceding LayerNorm folded in: the accumulator of the
+//     raw rows against gamma-scaled weights becomes rstd[m] * (acc - mean[m] * colsum[n]) + bias'[n]
 // CG: 1 = one CTA per 128-row tile; 2 = CTA pair (cluster of 2, tcgen05 cta_group::2) per 256-row tile: each CTA
 // stages its own 128 A rows and HALF of the B tile, which halves the L2 -> smem weight traffic per FLOP (the
 // 1-CTA kernel is bound by exactly that traffic: 128 x (128 + BN) bytes per 128 x BN x 64 MACs).
-template <int EPI, int CG>
+template <int EPI, int CG, int SK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_o64,
@@ -76,6 +126,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ __align__(8) uint64_t res_full[4];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ int sk_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // SWIZZLE_128B atoms need 1024-byte aligned stage bases
@@ -96,7 +147,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CG * (EPI == 8 ? 4 : 8)); }
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
-    if (EPI != 8) { tma_prefetch_desc(&map_o64); if (EPI & 1) tma_prefetch_desc(&map_r64); }
+    if (EPI != 8) { tma_prefetch_desc(&map_o64); if (EPI < 8 && (EPI & 1)) tma_prefetch_desc(&map_r64); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -114,25 +165,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const uint32_t tmem_base = tmem_base_slot;
   griddep_wait();                        // everything above overlapped the previous kernel's tail (PDL)
 
+  if (warp < 4) {
+  // control warp group: one setmaxnreg for all four warps (warps 2, 3 have no other role), then the role split
+  if (EPI != 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_CTRL));
   if (warp == 0) {
     // ================= TMA producer (both CTAs of a pair); warp-uniform loop, one elected lane issues =================
     {
       int stage = 0; uint32_t phase = 0;
       const int pad = a.ksize >> 1;
-      for (int tile = worker; tile < num_tiles; tile += nworkers) {
+      PieceIter pit(SK, worker, nworkers, num_tiles, nkb);
+      int tile, kb0, kb1, tix = 0;
+      for (; pit.next(tile, kb0, kb1); ++tix) {
         const int nt = tile / pm_tiles, mt = (tile - nt * pm_tiles) * CG + (int)cta_rank;
         const int txi = mt % a.tiles_x;
         const int tyi = (mt / a.tiles_x) % a.tiles_y;
         const int tbi = mt / (a.tiles_x * a.tiles_y);   // >= tiles_b for the phantom half of an odd last pair: TMA zero-fills
         const int x0 = txi * a.bw, y0 = tyi * a.bh, b0 = tbi * a.bn, n0 = nt * a.BN + (int)cta_rank * b_rows;
-        const int tix = (tile - worker) / nworkers;
-        if (tile + nworkers >= num_tiles && lane == 0) griddep_launch();   // last tile of this CTA: let the next kernel in
+        if (!SK && tile + nworkers >= num_tiles && lane == 0) griddep_launch();   // last tile of this CTA: let the next kernel in
         if (lane == 0) PD_DBG(0, tix, 0);
         // (tap, channel block) walk of segment 0 kept in counters: no integer divisions on the issue path
-        int cb = 0, dx = 0, dy = 0, wk0 = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
+        // (one division per piece when a stream-K piece starts inside a tile)
+        int cb = 0, dx = 0, dy = 0, wk0 = kb0 * TC_BK;
+        if (kb0 != 0 && kb0 < a.nk0) {
+          const int tap = kb0 / a.cpt0;
+          cb = kb0 - tap * a.cpt0; dy = tap / a.ksize; dx = tap - dy * a.ksize;
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-          if (kb == nkb - 1 && lane == 0) PD_DBG(0, tix, 1);
+          if (kb == kb1 - 1 && lane == 0) PD_DBG(0, tix, 1);
           unsigned char* sa = smem + stage * stage_bytes;
           unsigned char* sb = sa + TC_A_BYTES;
           if (a.dbg_mode == 2) {
@@ -174,14 +234,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (cta_rank == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
+      PieceIter pit(SK, worker, nworkers, num_tiles, nkb);
+      int tile, kb0, kb1;
+      for (; pit.next(tile, kb0, kb1); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
         if (lane == 0) PD_DBG(1, it, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase, 300 + stage);
           tc_fence_after();
           const uint32_t sa = s_u32(smem + stage * stage_bytes);
@@ -192,13 +254,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             for (int k = 0; k < TC_BK / 16; ++k) {
               if (a.dbg_mode == 1) break;
               // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 field
-              if (CG == 2) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, (kb | k) != 0 ? 1u : 0u);
+              const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;
+              if (CG == 2) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, accum);
+              else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, accum);
             }
             // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
             if (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
             // accumulator complete -> epilogue (of both CTAs)
-            if (kb == nkb - 1) { if (CG == 2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]); }
+            if (kb == kb1 - 1) { if (CG == 2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]); }
           }
           __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -206,9 +269,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (lane == 0) PD_DBG(1, it, 1);
       }
     }
+  }
   } else if (EPI == 8) {
-    // ================= legacy epilogue (fp32 output: the tiny timestep-embedding GEMMs), warps 2..5 =================
-    if (warp < 6) {
+    // ================= legacy epilogue (fp32 output: the tiny timestep-embedding GEMMs), warps 4..7 =================
+    if (warp >= 4 && warp < 8) {
     const int qd = warp & 3;               // TMEM lane quadrant this warp may touch
     const int r = qd * 32 + lane;          // accumulator row == tile pixel
     const int rx = r % a.bw;
@@ -298,14 +362,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     }
   } else {
-    // ================= epilogue, warps 2..9: two independent groups of 4 warps =================
+    // ================= epilogue, warps 4..11: two independent groups of 4 warps =================
     // Group g owns the 64-column slabs s = g, g+2 of every tile, two 16 KiB staging buffers, one named barrier and
     // one elected thread that drives its TMA traffic.  Per tile: (a) residual slabs are prefetched by TMA while the
     // MMAs of the tile are still running, (b) TMEM -> registers, (c) +bias, *alpha, +emb row, +residual, act in
     // registers/smem (flags are template parameters: no branches in the unrolled code), (d) TMA store.
-    constexpr bool GEGLU = EPI == 9;
-    constexpr bool RES = !GEGLU && (EPI & 1) != 0, RV = !GEGLU && (EPI & 2) != 0, ACT = !GEGLU && (EPI & 4) != 0;
-    const int ew = warp - 2, grp = ew >> 2;
+    // Stream-K kernels (SK = 1; a separate instantiation, so the data-parallel kernels do not carry this code):
+    // a piece that covers only part of a tile's K range dumps its raw accumulator to the workspace and bumps the
+    // tile's arrival counter; the CTA that arrives last sums all pieces IN K ORDER (its own included, re-read from
+    // the workspace), so the result does not depend on the arrival order, and then runs (a), (c), (d).
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
+    constexpr bool GEGLU = EPI == 9 || EPI == 11;
+    constexpr bool LNF = EPI == 10 || EPI == 11;
+    constexpr int EF = EPI < 8 ? EPI : 0;
+    constexpr bool RES = (EF & 1) != 0, RV = (EF & 2) != 0, ACT = (EF & 4) != 0;
+    const int ew = warp - 4, grp = ew >> 2;
     const int qd = warp & 3;               // TMEM lane quadrant this warp may touch
     const int r = qd * 32 + lane;          // accumulator row == tile pixel
     const int rx = r % a.bw;
@@ -313,13 +384,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int rb = r / (a.bw * a.bh);
     unsigned char* gstg = smem + a.stages * stage_bytes + grp * 32768;   // 1024-aligned
     uint64_t* rbar = &res_full[grp * 2];
+    uint32_t res_phase = 0;                // residual barriers complete once per tile that loads a residual
     const bool elected = (ew & 3) == 0 && lane == 0;
     const int bar_id = 1 + grp;
     const int n64 = a.BN >> 6, nslabs = n64 + ((a.BN & 63) ? 1 : 0);
     const int ns_mine = (nslabs > grp ? 1 : 0) + (nslabs > grp + 2 ? 1 : 0);
     const float alpha = a.alpha;
+    const long long sk_units = (long long)num_tiles * nkb;
     int it = 0;
-    for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
+    PieceIter pit(SK, worker, nworkers, num_tiles, nkb);
+    int tile, kb0, kb1;
+    for (; pit.next(tile, kb0, kb1); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int nt = tile / pm_tiles, mt = (tile - nt * pm_tiles) * CG + (int)cta_rank;
@@ -331,47 +406,118 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const bool row_ok = x < a.Wo && y < a.Ho && b < a.B;
       const int64_t m = ((int64_t)b * a.Ho + y) * a.Wo + x;
       const int n0 = nt * a.BN;
-
-      if (RES) {
-        // the residual slabs are prefetched INTO the staging buffers: both must have been drained by their stores
-        if (elected) {
-          tma_store_wait_read<0>();
-          for (int i = 0; i < ns_mine; ++i) {
-            const int sl = grp + 2 * i;
-            const int w = sl < n64 ? 64 : 32;
-            mbar_expect_tx(&rbar[i], (uint32_t)(128 * w * 2));
-            tma_load_4d(gstg + i * 16384, w == 64 ? &map_r64 : &map_r32, &rbar[i], n0 + sl * 64, x0, y0, b0);
+      // residual slabs are fetched by TMA INTO the staging buffers (the sum is formed in place): both buffers must
+      // have been drained by their stores.  Issued before the accumulator wait so that the MMAs of the tile hide the
+      // latency; the slabs of the worker's NEXT tile are pulled into L2 at the same time (the short-K layers have
+      // no MMA time to hide an HBM round trip behind).
+      auto load_res = [&]() {
+        if constexpr (RES) {
+          if (elected) {
+            tma_store_wait_read<0>();
+            for (int i = 0; i < ns_mine; ++i) {
+              const int sl = grp + 2 * i;
+              const int w = sl < n64 ? 64 : 32;
+              mbar_expect_tx(&rbar[i], (uint32_t)(128 * w * 2));
+              tma_load_4d(gstg + i * 16384, w == 64 ? &map_r64 : &map_r32, &rbar[i], n0 + sl * 64, x0, y0, b0);
+            }
+            const int ntile = pit.peek_tile();
+            if (ntile >= 0) {
+              const int nnt = ntile / pm_tiles, nmt = (ntile - nnt * pm_tiles) * CG + (int)cta_rank;
+              const int nx0 = (nmt % a.tiles_x) * a.bw, ny0 = ((nmt / a.tiles_x) % a.tiles_y) * a.bh;
+              const int nb0 = (nmt / (a.tiles_x * a.tiles_y)) * a.bn;
+              for (int i = 0; i < ns_mine; ++i) {
+                const int sl = grp + 2 * i;
+                tma_prefetch_4d(sl < n64 ? &map_r64 : &map_r32, nnt * a.BN + sl * 64, nx0, ny0, nb0);
+              }
+            }
           }
+          epi_bar_sync(bar_id);
         }
-        epi_bar_sync(bar_id);
-      }
+      };
+      const bool partial = SK != 0 && (kb1 - kb0) != nkb;
+      if (!partial) load_res();
+
       mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
       tc_fence_after();
       if (ew == 0 && lane == 0) PD_DBG(2, it, 0);
       const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)acc * 256u;
-      if (ns_mine == 0) {                  // BN <= 64: group 1 has no slab, it only hands the accumulator back
+
+      int w_first = 0, w_last = 0;
+      if (partial) {
+        // ---- stream-K: dump the partial accumulator, arrive on the tile; only the last arriver goes on ----
+        float* wsl = a.sk_ws + ((size_t)(worker * 2 + (it == 0 ? 0 : 1)) * CG + cta_rank) * SK_SLOT_FLOATS + r;
+        for (int i = 0; i < ns_mine; ++i) {
+          const int sl = grp + 2 * i;
+          const int w = sl < n64 ? 64 : 32;
+          uint32_t v[64];
+          tmem_ld32(t_row + (uint32_t)(sl * 64), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          if (w == 64) tmem_ld32(t_row + (uint32_t)(sl * 64) + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+          float* dst = wsl + (size_t)(sl * 64) * 128;   // [column][row]: a warp writes 128 contiguous bytes per column
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c < w) __stcg(dst + c * 128, __uint_as_float(v[c]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
+        const long long ub = (long long)tile * nkb;
+        w_first = (int)(((ub + 1) * nworkers + sk_units - 1) / sk_units) - 1;
+        w_last = (int)(((ub + nkb) * nworkers + sk_units - 1) / sk_units) - 1;
+        __threadfence();
+        epi_bar_sync_all(3);
+        if (ew == 0 && lane == 0) {
+          int* cnt = a.sk_cnt + tile * CG + (int)cta_rank;
+          const int old = atomicAdd(cnt, 1);
+          const int last = old == (w_last - w_first) ? 1 : 0;
+          if (last) *cnt = 0;
+          __threadfence();
+          sk_last = last;
+        }
+        epi_bar_sync_all(3);
+        if (sk_last == 0) continue;
+        load_res();
+      } else if (ns_mine == 0) {             // BN <= 64: group 1 has no slab, it only hands the accumulator back
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
       }
       const float* rvp = nullptr;
       if (RV) rvp = a.rowvec + (row_ok ? (m / a.hw_real) : 0) * a.ldrv;
+      float ln_mu = 0.f, ln_rs = 0.f;
+      if (LNF && row_ok) { const float2 st = __ldg(a.ln_stats + m); ln_mu = st.x; ln_rs = st.y; }
       for (int i = 0; i < ns_mine; ++i) {
         const int sl = grp + 2 * i;
         const int w = sl < n64 ? 64 : 32;
         const int col0 = sl * 64;
         unsigned char* stg = gstg + i * 16384;
         uint32_t v[64];
-        tmem_ld32(t_row + (uint32_t)col0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        if (w == 64) tmem_ld32(t_row + (uint32_t)col0 + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-        tmem_ld_wait();
-        if (i == ns_mine - 1) {            // accumulator drained by this warp: hand it back to the MMA warp early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
+        if (!partial) {
+          tmem_ld32(t_row + (uint32_t)col0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          if (w == 64) tmem_ld32(t_row + (uint32_t)col0 + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+          if (i == ns_mine - 1) {            // accumulator drained by this warp: hand it back to the MMA warp early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
+          }
+        } else {
+          // pieces of this tile in K order: worker p's piece sits in its slot 0 when the tile is where p's range starts
+          for (int pw = w_first; pw <= w_last; ++pw) {
+            const long long pb = sk_units * pw / nworkers;
+            const int slot = pb >= (long long)tile * nkb ? 0 : 1;
+            const float* src = a.sk_ws + ((size_t)(pw * 2 + slot) * CG + cta_rank) * SK_SLOT_FLOATS + (size_t)col0 * 128 + r;
+            if (pw == w_first) {
+#pragma unroll
+              for (int c = 0; c < 64; ++c) if (c < w) v[c] = __float_as_uint(__ldcg(src + c * 128));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 64; ++c) if (c < w) v[c] = __float_as_uint(__uint_as_float(v[c]) + __ldcg(src + c * 128));
+            }
+          }
         }
         if (RES) {
-          mbar_wait(&rbar[i], (uint32_t)it & 1u, 500 + grp * 2 + i);
+          mbar_wait(&rbar[i], res_phase, 500 + grp * 2 + i);
         } else {
           // with two slabs per tile, buffer i was last read by the store issued two slabs ago: the most recent store
           // (other buffer) may still be in flight, so its latency overlaps this slab instead of stalling every tile
@@ -390,9 +536,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const float bx[8] = {x0v.x, x0v.y, x0v.z, x0v.w, x1v.x, x1v.y, x1v.z, x1v.w};
             const float bg[8] = {g0v.x, g0v.y, g0v.z, g0v.w, g1v.x, g1v.y, g1v.z, g1v.w};
             float f[8];
+            if constexpr (LNF) {
+              const float4 sx0 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n));
+              const float4 sx1 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n + 4));
+              const float4 sg0 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n + 32));
+              const float4 sg1 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n + 36));
+              const float sx[8] = {sx0.x, sx0.y, sx0.z, sx0.w, sx1.x, sx1.y, sx1.z, sx1.w};
+              const float sg[8] = {sg0.x, sg0.y, sg0.z, sg0.w, sg1.x, sg1.y, sg1.z, sg1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float val = (__uint_as_float(v[g * 8 + e]) - ln_mu * sx[e]) * ln_rs + bx[e];
+                const float gate = (__uint_as_float(v[32 + g * 8 + e]) - ln_mu * sg[e]) * ln_rs + bg[e];
+                f[e] = val * gelu_erf_fast(gate);
+              }
+            } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e)
               f[e] = (__uint_as_float(v[g * 8 + e]) + bx[e]) * gelu_erf_fast(__uint_as_float(v[32 + g * 8 + e]) + bg[e]);
+            }
             const int off = r * 64 + ((g ^ ((r >> 1) & 3)) << 4);     // SWIZZLE_64B rows of the 32-column output box
             *reinterpret_cast<bf16x8*>(stg + off) = pack8(f);
           }
@@ -405,6 +566,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+            if constexpr (LNF) {
+              const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n));
+              const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n + 4));
+              const float cs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = (f[e] - ln_mu * cs[e]) * ln_rs;
+            }
             {
               const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
               const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
@@ -443,6 +611,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           tma_store_commit();
         }
       }
+      if (RES) res_phase ^= 1u;
       if (ew == 0 && lane == 0) PD_DBG(2, it, 1);
     }
     if (elected) tma_store_wait_all();     // smem must outlive the bulk stores
@@ -461,7 +630,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 // Optional per-launch CUDA-event timing of this engine (bench.py's roofline leg; never on in a
 // captured graph): every launch is bracketed by two events on ITS stream and logged with its
 // algorithmic FLOPs (2*M*Cout*K of the layer, padding excluded).
-struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, ksize, stride, BN, m_tiles, n_tiles, stages, grid, cg; };
+struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, ksize, stride, BN, m_tiles, n_tiles, stages, grid, cg, sk; };
 static bool g_prof_on = false;
 static int g_dbg_mode = 0;
 static int g_force_bn = 0;   // experiments: pin the N extent of the tile (multiple of 32, <= 256)
@@ -526,13 +695,46 @@ bool conv2d_tc_supported(const pd_conv_params* p, const char** why) {
   if (p->act == PD_ACT_GEGLU && (p->out_dtype != PD_BF16 || p->Cout % 64 != 0 || p->res != nullptr || p->rowvec != nullptr ||
                                  p->alpha != 1.0f))
     PD_NO("GEGLU epilogue needs bf16 output, Cout % 64 == 0, no residual / row vector / alpha");
+  if ((p->ln_stats != nullptr) != (p->ln_colsum != nullptr)) PD_NO("ln_stats and ln_colsum go together");
+  if (p->ln_stats && (p->out_dtype != PD_BF16 || p->ksize != 1 || p->stride != 1 || p->C2 != 0 || p->res != nullptr ||
+                      p->rowvec != nullptr || p->alpha != 1.0f || p->bias == nullptr ||
+                      (p->act != PD_ACT_NONE && p->act != PD_ACT_GEGLU) || (uintptr_t)p->ln_stats % 8 != 0 ||
+                      (uintptr_t)p->ln_colsum % 16 != 0))
+    PD_NO("folded LayerNorm needs a bf16 1x1 layer with bias, act NONE/GEGLU, no residual / row vector / alpha");
   if (p->stride == 2 && p->ksize != 3) PD_NO("stride 2 only with 3x3");
   if (p->stride == 2 && (p->H % 2 != 0 || p->W % 2 != 0)) PD_NO("stride 2 needs even H, W");
 #undef PD_NO
   return true;
 }
 
-static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg) {
+// Launch variant: cg 0 = heuristic, 1 = single-CTA tiles, 2 = CTA pairs; sk = stream-K schedule (needs cg != 0;
+// 1 = required, else PD_ERR_UNSUPPORTED; 2 = where it applies);
+// bn = N extent override (0 = heuristic)
+struct TcVariant { int cg, sk, bn; };
+
+// stream-K scratch, one per device: partial accumulators (2 slots per CTA) and self-resetting arrival counters
+constexpr int SK_MAX_TILES = 32768;
+static int sk_scratch(float** ws, int** cnt) {
+  static float* g_ws[16] = {nullptr};
+  static int* g_cnt[16] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) { set_error("conv_tc: bad device for stream-K scratch"); return PD_ERR_NO_DEVICE; }
+  if (g_ws[dev] == nullptr) {
+    float* w = nullptr; int* c = nullptr;
+    const size_t wbytes = (size_t)num_sms() * 2 * SK_SLOT_FLOATS * sizeof(float);
+    if (cudaMalloc(&w, wbytes) != cudaSuccess || cudaMalloc(&c, (size_t)SK_MAX_TILES * 2 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(c, 0, (size_t)SK_MAX_TILES * 2 * sizeof(int)) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("conv_tc: cannot allocate the stream-K scratch"); return PD_ERR_NO_DEVICE;
+    }
+    g_ws[dev] = w; g_cnt[dev] = c;
+  }
+  *ws = g_ws[dev]; *cnt = g_cnt[dev];
+  return 0;
+}
+
+static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var) {
+  const int force_cg = var.cg;
   TcArgs a;
   const int pad = p->ksize / 2;
   const int Ho = (p->H + 2 * pad - p->ksize) / p->stride + 1;
@@ -542,6 +744,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
   a.alpha = p->alpha;
   a.dbg = g_dbg;
   a.dbg_mode = g_dbg_mode;
+  a.ln_stats = reinterpret_cast<const float2*>(p->ln_stats); a.ln_colsum = p->ln_colsum;
   a.ksize = p->ksize; a.stride = p->stride; a.C = p->C; a.C2 = p->C2; a.Cout = p->Cout;
   a.cpt0 = p->C / TC_BK;
   a.nk0 = p->ksize * p->ksize * a.cpt0;
@@ -574,16 +777,19 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
   a.epi_tma = p->out_dtype == PD_BF16 ? 1 : 0;
   int best_bn = 64, best_cg = 1; double best_cost = 1e30;
   const int cg_max = (a.epi_tma && force_cg != 1) ? 2 : 1;
+  const bool want_sk = var.sk != 0 && a.epi_tma && force_cg != 0;
   for (int cg = cg_max; cg >= (force_cg == 2 && cg_max == 2 ? 2 : 1); --cg) {
     for (int bn = 256; bn >= 32; bn -= 32) {
       if (p->act == PD_ACT_GEGLU && bn % 64 != 0) continue;
       if (g_force_bn != 0 && bn != g_force_bn) continue;
+      if (var.bn != 0 && bn != var.bn) continue;
       int n_tiles = (p->Cout + bn - 1) / bn;
       int64_t tiles = (int64_t)((a.m_tiles + cg - 1) / cg) * n_tiles;
       int64_t workers = sms / cg;
       int64_t waves = (tiles + workers - 1) / workers;
       double per_kb = fmax(2.0 * bn, 3.3 * (128.0 + (double)bn / cg));
-      double cost = (double)waves * per_kb;
+      // stream-K has no waves: every worker streams tiles * nkb / workers k-blocks
+      double cost = want_sk ? (double)tiles / (double)workers * per_kb : (double)waves * per_kb;
       if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; best_cg = cg; }
     }
   }
@@ -657,22 +863,26 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
   const size_t smem = (size_t)a.stages * stage_bytes + epi_bytes + 1024;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                            const CUtensorMap, const CUtensorMap, const TcArgs);
-  static const KernelFn kernels[2][10] = {
-      {conv_tc_kernel<0, 1>, conv_tc_kernel<1, 1>, conv_tc_kernel<2, 1>, conv_tc_kernel<3, 1>, conv_tc_kernel<4, 1>,
-       conv_tc_kernel<5, 1>, conv_tc_kernel<6, 1>, conv_tc_kernel<7, 1>, conv_tc_kernel<8, 1>, conv_tc_kernel<9, 1>},
-      {conv_tc_kernel<0, 2>, conv_tc_kernel<1, 2>, conv_tc_kernel<2, 2>, conv_tc_kernel<3, 2>, conv_tc_kernel<4, 2>,
-       conv_tc_kernel<5, 2>, conv_tc_kernel<6, 2>, conv_tc_kernel<7, 2>, nullptr, conv_tc_kernel<9, 2>}};
+#define PD_TC_ROW(CGv_, SKv_)                                                                                          \
+  {conv_tc_kernel<0, CGv_, SKv_>, conv_tc_kernel<1, CGv_, SKv_>, conv_tc_kernel<2, CGv_, SKv_>,                      \
+   conv_tc_kernel<3, CGv_, SKv_>, conv_tc_kernel<4, CGv_, SKv_>, conv_tc_kernel<5, CGv_, SKv_>,                      \
+   conv_tc_kernel<6, CGv_, SKv_>, conv_tc_kernel<7, CGv_, SKv_>, nullptr, conv_tc_kernel<9, CGv_, SKv_>,            \
+   conv_tc_kernel<10, CGv_, SKv_>, conv_tc_kernel<11, CGv_, SKv_>}
+  static KernelFn kernels[2][2][12] = {{PD_TC_ROW(1, 0), PD_TC_ROW(2, 0)}, {PD_TC_ROW(1, 1), PD_TC_ROW(2, 1)}};
+#undef PD_TC_ROW
   static bool attr_set = false;
   if (!attr_set) {
-    for (int c = 0; c < 2; ++c)
-      for (int i = 0; i < 10; ++i) {
-        if (kernels[c][i] == nullptr) continue;
-        cudaError_t e = cudaFuncSetAttribute(kernels[c][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-        if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-      }
+    kernels[0][0][8] = conv_tc_kernel<8, 1, 0>;      // fp32 output: legacy epilogue, single CTA, data-parallel only
+    for (int k = 0; k < 2; ++k)
+      for (int c = 0; c < 2; ++c)
+        for (int i = 0; i < 12; ++i) {
+          if (kernels[k][c][i] == nullptr) continue;
+          cudaError_t e = cudaFuncSetAttribute(kernels[k][c][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+          if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        }
     attr_set = true;
   }
-  const int epi = !a.epi_tma ? 8 : p->act == PD_ACT_GEGLU ? 9
+  const int epi = !a.epi_tma ? 8 : p->ln_stats != nullptr ? (p->act == PD_ACT_GEGLU ? 11 : 10) : p->act == PD_ACT_GEGLU ? 9
                   : ((p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0));
   static const float* zero_bias = nullptr;   // the TMA epilogue always adds a bias vector
   if (a.epi_tma && a.bias == nullptr) {
@@ -689,6 +899,18 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
   int64_t tiles = (int64_t)((a.m_tiles + CGv - 1) / CGv) * a.n_tiles;
   const int64_t workers = sms / CGv;
   int grid = (int)(tiles < workers ? tiles : workers) * CGv;
+  // stream-K only where it can change anything: more than one k-block per worker, tile count not a multiple of the
+  // worker count, counters in range
+  const int nkb_tot = a.nk0 + a.nk1;
+  a.sk = 0; a.sk_ws = nullptr; a.sk_cnt = nullptr;
+  if (want_sk && epi != 8 && tiles * nkb_tot >= 2 * workers && tiles % workers != 0 && tiles <= SK_MAX_TILES) {
+    int rc = sk_scratch(&a.sk_ws, &a.sk_cnt);
+    if (rc) return rc;
+    a.sk = 1;
+    grid = (int)workers * CGv;
+  } else if (var.sk == 1) {
+    return PD_ERR_UNSUPPORTED;       // the tuner skips this candidate (sk == 2: fall back to data-parallel)
+  }
   ProfRec rec;
   if (g_prof_on) {
     cudaEventCreate(&rec.e0);
@@ -696,12 +918,12 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
     rec.flops = 2.0 * (double)p->B * Ho * Wo * (double)p->Cout * (double)(p->ksize * p->ksize * p->C + p->C2);
     rec.M = p->B * Ho * Wo; rec.N = p->Cout; rec.K = p->ksize * p->ksize * p->C + p->C2; rec.ksize = p->ksize;
     rec.stride = p->stride; rec.BN = a.BN; rec.m_tiles = a.m_tiles; rec.n_tiles = a.n_tiles; rec.stages = a.stages;
-    rec.grid = grid; rec.cg = CGv;
+    rec.grid = grid; rec.cg = CGv; rec.sk = a.sk;
     cudaEventRecord(rec.e0, s);
   }
   {
-    cudaError_t e = launch_pdl(kernels[CGv - 1][epi], dim3((unsigned)grid), dim3(TC_THREADS), smem, s, (unsigned)CGv, map_a0,
-                               map_a1, map_w, map_o64, map_o32, map_r64, map_r32, a);
+    cudaError_t e = launch_pdl(kernels[a.sk][CGv - 1][epi], dim3((unsigned)grid), dim3(TC_THREADS), smem, s, (unsigned)CGv,
+                               map_a0, map_a1, map_w, map_o64, map_o32, map_r64, map_r32, a);
     if (e != cudaSuccess) { set_error("conv_tc: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
   }
   if (g_prof_on) {
@@ -711,45 +933,55 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, int force_cg)
   return check_launch("conv_tc");
 }
 
-// Tile-shape autotuning.  Single-CTA vs CTA-pair tiles trade L2 / shared-memory operand traffic against per-tile
-// synchronisation cost, and which wins depends on (M, N, K) in ways a closed-form model gets wrong for the short-K
-// layers; both variants produce bit-identical results (same K order per output element), so the first idempotent
-// call of each layer shape simply times both (CUDA events on the caller's stream; that one call is synchronous) and
-// the choice is cached.  Calls that accumulate in place, calls during stream capture and profiled calls never tune.
+// Launch-variant autotuning.  Single-CTA vs CTA-pair tiles trade L2 / shared-memory operand traffic against per-tile
+// synchronisation cost, and stream-K trades wave quantisation against a partial-tile exchange through L2; which one
+// wins depends on (M, N, K) in ways a closed-form model gets wrong for the short-K and small-M layers.  So the first
+// idempotent call of each layer shape times the candidates (CUDA events on the caller's stream; that one call is
+// synchronous), the choice is cached, and the call is finished with the winner so that its output carries the same
+// bits as every later call.  Every variant is deterministic (stream-K sums its pieces in K order whatever the
+// arrival order); data-parallel variants are bit-identical to each other, stream-K differs from them by fp32
+// reassociation only.  Calls that accumulate in place, calls during stream capture and profiled calls never tune.
 struct TuneKey {
   int M, N, K, ksize, stride, c2, epi;
   bool operator<(const TuneKey& o) const {
     return std::tie(M, N, K, ksize, stride, c2, epi) < std::tie(o.M, o.N, o.K, o.ksize, o.stride, o.c2, o.epi);
   }
 };
-static std::map<TuneKey, int> g_tune;
+static std::map<TuneKey, TcVariant> g_tune;
 static int g_autotune = -1;
+static int g_force_sk = 0;
 
 int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   if (g_autotune < 0) {
     const char* e = getenv("PD_B200_AUTOTUNE");
     g_autotune = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  if (g_force_cg != 0 || !g_autotune || p->out_dtype != PD_BF16 || g_dbg_mode != 0) return conv2d_tc_impl(p, s, g_force_cg);
+  if (g_force_cg != 0 || !g_autotune || p->out_dtype != PD_BF16 || g_dbg_mode != 0)
+    return conv2d_tc_impl(p, s, TcVariant{g_force_cg, g_force_cg != 0 && g_force_sk ? 2 : 0, 0});
   const int pad = p->ksize / 2;
   const int Ho = (p->H + 2 * pad - p->ksize) / p->stride + 1, Wo = (p->W + 2 * pad - p->ksize) / p->stride + 1;
   const TuneKey key{p->B * Ho * Wo, p->Cout, p->ksize * p->ksize * p->C + p->C2, p->ksize, p->stride, p->C2 > 0 ? 1 : 0,
                     (p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0) |
-                        (p->act == PD_ACT_GEGLU ? 8 : 0)};
+                        (p->act == PD_ACT_GEGLU ? 8 : 0) | (p->ln_stats != nullptr ? 16 : 0)};
   auto it = g_tune.find(key);
   if (it != g_tune.end()) return conv2d_tc_impl(p, s, it->second);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
   const bool in_place = p->res == p->out || p->x == p->out || (p->x2 != nullptr && p->x2 == p->out);
-  if (cap != cudaStreamCaptureStatusNone || in_place || g_prof_on) return conv2d_tc_impl(p, s, 0);
+  if (cap != cudaStreamCaptureStatusNone || in_place || g_prof_on) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0});
   cudaEvent_t e0, e1;
-  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaGetLastError(); return conv2d_tc_impl(p, s, 0); }
-  float best_ms = 1e30f; int best = 1;
-  for (int cg = 1; cg <= 2; ++cg) {
-    int rc = conv2d_tc_impl(p, s, cg);                     // warm (tensor maps, L2)
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaGetLastError(); return conv2d_tc_impl(p, s, TcVariant{0, 0, 0}); }
+  // stream-K with the model's tile width, and with 128-wide tiles: fewer pieces per tile (cheaper fix-up) against
+  // more operand traffic per FLOP
+  const TcVariant cands[6] = {{1, 0, 0}, {2, 0, 0}, {2, 1, 0}, {1, 1, 0}, {2, 1, 128}, {1, 1, 128}};
+  float best_ms = 1e30f; TcVariant best = cands[0]; int last_run = -1, best_idx = 0;
+  for (int c = 0; c < 6; ++c) {
+    if (cands[c].bn != 0 && (p->Cout < cands[c].bn || p->act == PD_ACT_GEGLU)) continue;
+    int rc = conv2d_tc_impl(p, s, cands[c]);                // warm (tensor maps, L2)
+    if (rc == PD_ERR_UNSUPPORTED && cands[c].sk) continue;  // stream-K does not apply to this shape
     if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
     cudaEventRecord(e0, s);
-    for (int i = 0; i < 3 && rc == 0; ++i) rc = conv2d_tc_impl(p, s, cg);
+    for (int i = 0; i < 3 && rc == 0; ++i) rc = conv2d_tc_impl(p, s, cands[c]);
     cudaEventRecord(e1, s);
     if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
     float ms = 0.f;
@@ -759,11 +991,15 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
       set_error("conv_tc autotune: %s", cudaGetErrorString(e));
       return (int)(e != cudaSuccess ? e : cudaErrorUnknown);
     }
-    if (ms < best_ms) { best_ms = ms; best = cg; }
+    last_run = c;
+    // stream-K must win clearly: it is the variant whose sums are associated differently
+    if (ms * (cands[c].sk ? 1.03f : 1.0f) < best_ms) { best_ms = ms; best = cands[c]; best_idx = c; }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   g_tune[key] = best;
-  return 0;                                                  // the output already holds the result
+  // the output holds the last candidate's result: finish with the winner so this call's bits match every later call
+  if (last_run != best_idx) return conv2d_tc_impl(p, s, best);
+  return 0;
 }
 
 }  // namespace pd
@@ -775,6 +1011,8 @@ int pd_debug_timeline(void* dev_buf) { pd::g_dbg = (unsigned long long*)dev_buf;
 int pd_debug_gemm_mode(int mode) { pd::g_dbg_mode = mode; return 0; }
 int pd_debug_force_bn(int bn) { pd::g_force_bn = (bn >= 32 && bn <= 256 && bn % 32 == 0) ? bn : 0; return 0; }
 int pd_debug_force_cta_group(int cg) { pd::g_force_cg = (cg == 1 || cg == 2) ? cg : 0; return 0; }
+// with a forced CTA group: 1 = stream-K schedule wherever it applies (falls back to data-parallel elsewhere)
+int pd_debug_force_stream_k(int on) { pd::g_force_sk = on != 0; return 0; }
 // enable (1) / disable (0) per-launch timing of the tcgen05 engine; enabling clears the log
 int pd_prof_enable(int on) {
   for (auto& r : pd::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -786,13 +1024,13 @@ int pd_prof_enable(int on) {
 int pd_prof_dump(const char* path) {
   FILE* f = fopen(path, "w");
   if (!f) { pd::set_error("pd_prof_dump: cannot open %s", path); return PD_ERR_BAD_ARG; }
-  fprintf(f, "M,N,K,ksize,stride,BN,m_tiles,n_tiles,stages,grid,cg,ms,tflops\n");
+  fprintf(f, "M,N,K,ksize,stride,BN,m_tiles,n_tiles,stages,grid,cg,sk,ms,tflops\n");
   for (auto& r : pd::g_prof) {
     float t = 0.f;
     cudaEventSynchronize(r.e1);
     cudaEventElapsedTime(&t, r.e0, r.e1);
-    fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.5f,%.1f\n", r.M, r.N, r.K, r.ksize, r.stride, r.BN, r.m_tiles,
-            r.n_tiles, r.stages, r.grid, r.cg, t, r.flops / (t * 1e-3) / 1e12);
+    fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.5f,%.1f\n", r.M, r.N, r.K, r.ksize, r.stride, r.BN, r.m_tiles,
+            r.n_tiles, r.stages, r.grid, r.cg, r.sk, t, r.flops / (t * 1e-3) / 1e12);
   }
   fclose(f);
   return 0;

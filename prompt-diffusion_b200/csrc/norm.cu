@@ -502,6 +502,65 @@ layer_norm_grouped_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out,
   }
 }
 
+// Statistics-only pass of the grouped-lane LayerNorm: stats[row] = (mean, rstd).  The normalisation itself is folded
+// into the consuming GEMM (weights pre-scaled by gamma, epilogue rstd * (acc - mean * colsum) + bias'), so the
+// normalised tensor is never written or re-read.
+template <typename T, int LPR, int NV>
+__global__ void __launch_bounds__(256)
+layer_norm_stats_kernel(const T* __restrict__ x, int ldx, float2* __restrict__ stats, int64_t rows, int C, float eps) {
+  constexpr int V = VecIO<T>::V;
+  constexpr int RPW = 32 / LPR;
+  griddep_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, li = lane % LPR;
+  const float invC = 1.0f / (float)C;
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5) * RPW;
+  for (int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * RPW; row0 < rows; row0 += stride) {
+    const int64_t row = row0 + sub;
+    const bool ok = row < rows;
+    const T* xr = x + (ok ? row : 0) * ldx;
+    float f[NV][V];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) VecIO<T>::ld(xr + (li + i * LPR) * V, f[i]);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int k = 0; k < V; ++k) sum += f[i][k];
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * invC;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int k = 0; k < V; ++k) { const float d = f[i][k] - mean; var += d * d; }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    if (ok && li == 0) stats[row] = make_float2(mean, rsqrtf(var * invC + eps));
+  }
+}
+
+template <typename T>
+static int ln_stats_launch(const void* x, int ldx, float* stats, int64_t rows, int C, float eps, cudaStream_t s) {
+  constexpr int V = VecIO<T>::V;
+  const int nvec = C / V;
+#define PD_LNS(L, N)                                                                                              \
+  if (nvec == (L) * (N)) {                                                                                        \
+    int64_t blocks = (rows + 8 * (32 / (L)) - 1) / (8 * (32 / (L)));                                              \
+    const int64_t cap = (int64_t)num_sms() * 8;                                                                   \
+    if (blocks > cap) blocks = cap;                                                                               \
+    cudaError_t le = launch_pdl(layer_norm_stats_kernel<T, L, N>, dim3((unsigned)blocks), dim3(256), 0, s, 1,     \
+                                (const T*)x, ldx, (float2*)stats, rows, C, eps);                                  \
+    if (le != cudaSuccess) { set_error("pd_layer_norm_stats: launch failed: %s", cudaGetErrorString(le)); return (int)le; } \
+    return check_launch("pd_layer_norm_stats");                                                                   \
+  }
+  PD_LNS(8, 5) PD_LNS(16, 5) PD_LNS(32, 5) PD_LNS(32, 10) PD_LNS(8, 1) PD_LNS(16, 1) PD_LNS(32, 1) PD_LNS(32, 2) PD_LNS(32, 4)
+#undef PD_LNS
+  set_error("pd_layer_norm_stats: unsupported width C=%d", C);
+  return PD_ERR_UNSUPPORTED;
+}
+
 template <typename T, typename TO>
 static int gn_launch(const void* x, int ldx, void* out, int ldo, const float* gamma, const float* beta,
                      float* partial, int B, int HW, int C, int groups, float eps, int act, cudaStream_t s) {
@@ -640,6 +699,18 @@ int pd_layer_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const floa
   if (dtype == PD_F32) return ln_launch<float>(x, ldx, out, ldo, gamma, beta, rows, C, eps, s);
   if (dtype == PD_BF16) return ln_launch<bf16>(x, ldx, out, ldo, gamma, beta, rows, C, eps, s);
   PD_REQUIRE(false, "pd_layer_norm: bad dtype %d", dtype);
+}
+
+int pd_layer_norm_stats(const void* x, int32_t ldx, float* stats, int64_t rows, int32_t C, float eps, int32_t dtype,
+                        void* stream) {
+  PD_REQUIRE(x && stats && rows > 0 && C > 0 && ldx >= C, "pd_layer_norm_stats: bad args");
+  const int V = dtype == PD_BF16 ? 8 : 4;
+  PD_REQUIRE(C % V == 0 && ldx % V == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)stats % 8) == 0,
+             "pd_layer_norm_stats: C and pitch must be multiples of %d, x 16B aligned, stats 8B aligned", V);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == PD_F32) return ln_stats_launch<float>(x, ldx, stats, rows, C, eps, s);
+  if (dtype == PD_BF16) return ln_stats_launch<bf16>(x, ldx, stats, rows, C, eps, s);
+  PD_REQUIRE(false, "pd_layer_norm_stats: bad dtype %d", dtype);
 }
 
 }  // extern "C"

@@ -49,10 +49,11 @@ def _cuda(*ts):
 
 
 def conv2d(x, w, out, B, H, W, *, ksize=1, stride=1, upsample=False, bias=None, rowvec=None, res=None,
-           x2=None, act=PD_ACT_NONE, alpha=1.0, engine=PD_ENGINE_AUTO):
+           x2=None, act=PD_ACT_NONE, alpha=1.0, engine=PD_ENGINE_AUTO, ln_stats=None, ln_colsum=None):
     """out[B*Ho*Wo, Cout] = act(alpha*(conv(x) [+ x2 @ Wskip] + bias) + rowvec[b] + res).
-    ``act=PD_ACT_GEGLU``: w / bias hold 2F rows (see ``geglu_interleave``), out has F columns."""
-    _cuda(x, w, out, bias, rowvec, res, x2)
+    ``act=PD_ACT_GEGLU``: w / bias hold 2F rows (see ``geglu_interleave``), out has F columns.
+    ``ln_stats`` / ``ln_colsum``: LayerNorm folded into the layer (see ``fold_layer_norm``)."""
+    _cuda(x, w, out, bias, rowvec, res, x2, ln_stats, ln_colsum)
     p = ConvParams()
     p.x, p.x2, p.w, p.bias, p.rowvec, p.res, p.out = _p(x), _p(x2), _p(w), _p(bias), _p(rowvec), _p(res), _p(out)
     p.B, p.H, p.W, p.C = B, H, W, x.shape[1]
@@ -67,6 +68,11 @@ def conv2d(x, w, out, B, H, W, *, ksize=1, stride=1, upsample=False, bias=None, 
     p.ldrv = 0 if rowvec is None else _ld(rowvec)
     p.act, p.dtype, p.out_dtype, p.engine, p.alpha = act, dt_code(x), dt_code(out), engine, float(alpha)
     p.w_blocked = int(bool(getattr(w, "_pd_blocked", False)))
+    p.ln_stats, p.ln_colsum = _p(ln_stats), _p(ln_colsum)
+    if ln_stats is not None and (ln_stats.dtype != torch.float32 or ln_stats.shape != (x.shape[0], 2) or
+                                 not ln_stats.is_contiguous() or ln_colsum is None or ln_colsum.dtype != torch.float32 or
+                                 ln_colsum.numel() != p.Cout):
+        raise ValueError("ln_stats must be contiguous fp32 [rows, 2] and ln_colsum fp32 [Cout]")
     if w.dtype != x.dtype or (x2 is not None and x2.dtype != x.dtype):
         raise TypeError("x, x2 and w must share a dtype")
     if res is not None and res.dtype != out.dtype:
@@ -135,6 +141,31 @@ def group_norm(x, out, gamma, beta, B, HW, *, groups=32, eps=1e-5, act=PD_ACT_NO
                             scratch.data_ptr(), B, HW, x.shape[1], groups, float(eps), act, dt_code(x),
                             dt_code(out), _stream()), "pd_group_norm")
     return out
+
+
+def layer_norm_stats(x, stats, eps=1e-5):
+    """stats[row] = (mean, rstd) of LayerNorm over the last dim; consumed by ``conv2d(..., ln_stats=stats)``."""
+    _cuda(x, stats)
+    if stats.dtype != torch.float32 or stats.shape != (x.shape[0], 2) or not stats.is_contiguous():
+        raise ValueError("stats must be contiguous fp32 [rows, 2]")
+    check(lib.pd_layer_norm_stats(x.data_ptr(), _ld(x), stats.data_ptr(), x.shape[0], x.shape[1], float(eps),
+                                  dt_code(x), _stream()), "pd_layer_norm_stats")
+    return stats
+
+
+def fold_layer_norm(w, bias, gamma, beta, dtype):
+    """Fold LayerNorm's affine into the linear layer that consumes it (attention.py:271-275):
+        Linear(LN(x))[m, n] = rstd[m] * (sum_k x[m,k] * (W[n,k] gamma[k]) - mean[m] * sum_k W[n,k] gamma[k])
+                              + (bias[n] + sum_k W[n,k] beta[k])
+    Returns (w_scaled in ``dtype``, bias', colsum) where colsum sums the ROUNDED scaled weights (so the mean
+    correction cancels exactly what the tensor cores accumulate).  w: fp32 [N, K]."""
+    w32 = w.float()
+    ws = (w32 * gamma.float()[None, :]).to(dtype).contiguous()
+    colsum = ws.float().sum(dim=1).contiguous()
+    b = w32 @ beta.float()
+    if bias is not None:
+        b = b + bias.float()
+    return ws, b.contiguous(), colsum
 
 
 def layer_norm(x, out, gamma, beta, eps=1e-5):

@@ -7,6 +7,9 @@ load-time fusions the kernels rely on:
   matrix ``[Cout, 9*Cout + Cin]`` (second K segment) and one summed bias;
 * attn1 ``to_q|to_k|to_v`` -> one ``[3C, C]`` matrix; attn2 ``to_k|to_v`` -> ``[2C, ctx]``;
 * all ``emb_layers.1`` of a net -> one ``[sum Cout, 4*mc]`` matrix (one GEMM per step);
+* bf16 mode folds each LayerNorm of BasicTransformerBlock into the linear layer that consumes it (``ops.fold_layer_norm``:
+  gamma-scaled weights, beta pushed through into the bias, column sums for the mean correction): the normalised
+  tensor is never written, the GEMM reads the raw residual stream and a per-row (mean, rstd) pair;
 * bf16 mode pads input channels that are >= 16 but not a multiple of 64 (hint stacks:
   16, 32, 96) up to 64/128 so those convs also run on the tcgen05 engine.
 """
@@ -25,6 +28,10 @@ from .config import CLDMConfig, Conv, Down, HINT_STACK, Res, ST, Up, build_topol
 # strided 128-byte pieces spread over more HBM channels than one contiguous 12-32 KiB run), so it stays off.
 BLOCK_WEIGHTS = False
 
+# Fold every LayerNorm of the transformer blocks into the linear layer behind it (bf16 mode).  Off = separate
+# pd_layer_norm passes (the fp32 mode always uses those).
+FOLD_LAYER_NORM = True
+
 
 def pad_channels(c: int, dt: torch.dtype) -> int:
     if dt == torch.bfloat16 and c >= 16 and c % 64 != 0:
@@ -33,11 +40,12 @@ def pad_channels(c: int, dt: torch.dtype) -> int:
 
 
 class PConv:
-    __slots__ = ("w", "bias", "cin", "cin_pad", "cout", "cout_pad", "ksize", "stride", "c2", "role")
+    __slots__ = ("w", "bias", "cin", "cin_pad", "cout", "cout_pad", "ksize", "stride", "c2", "role", "colsum")
 
     def __init__(self, w, bias, cin, cin_pad, cout, ksize, stride, c2=0, role="conv"):
         self.w, self.bias, self.cin, self.cin_pad, self.cout = w, bias, cin, cin_pad, cout
         self.cout_pad = cout
+        self.colsum = None          # set when a LayerNorm is folded into this layer (ops.fold_layer_norm)
         self.ksize, self.stride, self.c2, self.role = ksize, stride, c2, role
 
 
@@ -54,7 +62,7 @@ class PRes:
 
 class PST:
     __slots__ = ("key", "ch", "heads", "d", "gn", "proj_in", "ln1", "wqkv", "out1", "ln2", "wq2", "wkv2",
-                 "out2", "ln3", "ff1", "ff1_geglu", "ff2", "proj_out")
+                 "out2", "ln3", "ff1", "ff1_geglu", "ff2", "proj_out", "ln_folded")
 
 
 class Packer:
@@ -165,7 +173,25 @@ class Packer:
             s.ff1 = None            # the plain layout is not needed (saves 0.4 GB of weights)
         s.ff2 = self.conv(tb + ".ff.net.2")
         s.proj_out = self.conv(k + ".proj_out")
+        # bf16 mode: LayerNorm folded into its consumer (same condition as the tcgen05 engine: C % 64 == 0)
+        s.ln_folded = False
+        if FOLD_LAYER_NORM and s.ff1_geglu is not None and layer.ch % 64 == 0:
+            wq, wk, wv = (self.t(tb + f".attn1.to_{n}.weight") for n in "qkv")
+            s.wqkv = self.folded(torch.cat([wq, wk, wv], 0), None, s.ln1)
+            s.wq2 = self.folded(self.t(tb + ".attn2.to_q.weight"), None, s.ln2)
+            s.ff1_geglu = self.folded(self.t(tb + ".ff.net.0.proj.weight"), self.vec(tb + ".ff.net.0.proj.bias"), s.ln3,
+                                      interleave=True)
+            s.ln_folded = True
         return s
+
+    def folded(self, w: torch.Tensor, bias: Optional[torch.Tensor], ln: PNorm, interleave: bool = False) -> PConv:
+        """Linear layer with the LayerNorm ``ln`` that feeds it folded in (bf16 weights, fp32 bias' and colsum)."""
+        ws, b, cs = ops.fold_layer_norm(w, bias, ln.gamma, ln.beta, self.dt)
+        if interleave:
+            ws, b, cs = ops.geglu_interleave(ws), ops.geglu_interleave(b), ops.geglu_interleave(cs)
+        pc = PConv(self.block(ws.contiguous()), b.contiguous(), w.shape[1], w.shape[1], w.shape[0], 1, 1)
+        pc.colsum = cs.contiguous()
+        return pc
 
     def layer(self, layer):
         if isinstance(layer, Res):

@@ -84,12 +84,12 @@ else:
         (16, 8, 8, 1280, 1280, 1, 0),
     ]
     from prompt_diffusion_b200 import _lib
-    print("   B   HxW     C     N ks res |  auto us  TFLOP/s |  cg1 us  TFLOP/s |  cg2 us  TFLOP/s")
+    print("   B   HxW     C     N ks res |  auto us  TFLOP/s |  cg1 us  TFLOP/s |  cg2 us  TFLOP/s | cg1+sk us TFLOP/s | cg2+sk us TFLOP/s")
     for s in shapes:
         row = []
-        for cg in (0, 1, 2):
-            _lib.lib.pd_debug_force_cta_group(cg)
+        for cg, sk in ((0, 0), (1, 0), (2, 0), (1, 1), (2, 1)):
+            _lib.lib.pd_debug_force_cta_group(cg); _lib.lib.pd_debug_force_stream_k(sk)
             us, tf, gb = run(*s, iters=a.iters)
             row += [us, tf]
-        _lib.lib.pd_debug_force_cta_group(0)
-        print("%4d %3dx%-3d %5d %5d %2d %3d | %8.1f %8.0f | %7.1f %8.0f | %7.1f %8.0f" % (s[0], s[1], s[2], s[3], s[4], s[5], s[6], *row))
+        _lib.lib.pd_debug_force_cta_group(0); _lib.lib.pd_debug_force_stream_k(0)
+        print("%4d %3dx%-3d %5d %5d %2d %3d | %8.1f %8.0f | %7.1f %8.0f | %7.1f %8.0f | %8.1f %8.0f | %8.1f %8.0f" % (s[0], s[1], s[2], s[3], s[4], s[5], s[6], *row))

@@ -44,7 +44,7 @@ def test_conv_params_struct_matches_header():
         if m:
             names += [n.strip(" *") for n in m.group(3).split(",")]
     assert names == [f[0] for f in ConvParams._fields_]
-    assert ctypes.sizeof(ConvParams) == 7 * 8 + 20 * 4  # 7 pointers, 19 int32 + float
+    assert ctypes.sizeof(ConvParams) == 7 * 8 + 20 * 4 + 2 * 8  # 7 pointers, 19 int32 + float, 2 pointers
 
 
 def test_schedule_matches_reference_golden(golden):

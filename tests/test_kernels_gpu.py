@@ -160,6 +160,35 @@ def test_conv_tcgen05_bf16_forced_tile(case, cg):
     assert err < 6e-3, err
 
 
+SK_CASES = TC_CASES + [
+    dict(B=16, H=8, W=8, C=1280, Cout=1280, ksize=3, res=True),                  # 8x8 level at the bench batch: 8 M tiles
+    dict(B=16, H=8, W=8, C=1280, Cout=1280, ksize=3, rowvec=True, act=1),
+    dict(B=4, H=16, W=16, C=640, Cout=1280, ksize=3, C2=640),                    # piece boundaries inside the skip segment
+    dict(B=16, H=8, W=8, C=1280, Cout=1280, ksize=3, stride=2),
+    dict(B=5, H=16, W=16, C=320, Cout=672, ksize=1, res=True, alpha=0.5, ldo_extra=64),  # partial last N tile
+]
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("case", SK_CASES)
+def test_conv_tcgen05_bf16_stream_k(case, cg):
+    """Stream-K schedule forced on: partial tiles exchanged through the L2 workspace, reduced in K order by the
+    last-arriving CTA.  Run twice: the arrival counters must have been left at zero, and the result is deterministic."""
+    from prompt_diffusion_b200 import _lib
+    if case.get("out_dt") is torch.float32:
+        pytest.skip("fp32-output launches use the legacy epilogue (data-parallel only)")
+    _lib.lib.pd_debug_force_cta_group(cg)
+    _lib.lib.pd_debug_force_stream_k(1)
+    try:
+        err = _conv_case(torch.bfloat16, _lib.PD_ENGINE_TC, **case)
+        err2 = _conv_case(torch.bfloat16, _lib.PD_ENGINE_TC, **case)
+    finally:
+        _lib.lib.pd_debug_force_cta_group(0)
+        _lib.lib.pd_debug_force_stream_k(0)
+    assert err < 6e-3, err
+    assert err2 == err
+
+
 def test_conv_tc_rejects_unsupported():
     from prompt_diffusion_b200._lib import PD_ENGINE_TC
     with pytest.raises(RuntimeError):
@@ -223,12 +252,65 @@ def test_layer_norm(dt, tol, C):
     assert rel_l2(out.float(), F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)) < tol
 
 
+@pytest.mark.parametrize("geglu", [0, 1])
+@pytest.mark.parametrize("M,C,N", [(4096, 320, 960), (1000, 640, 640), (640, 1280, 1280), (300, 320, 320)])
+def test_linear_with_folded_layer_norm(M, C, N, geglu):
+    """LayerNorm -> Linear (BasicTransformerBlock, attention.py:271-275) in the folded form: row statistics kernel +
+    GEMM on the raw rows with gamma-scaled weights and the rstd * (acc - mean * colsum) + bias' epilogue, against torch
+    fp32 LayerNorm -> Linear (-> GEGLU) on the same bf16 input.  Rows carry a large common offset so that the mean
+    correction is a real cancellation."""
+    from prompt_diffusion_b200._lib import PD_ACT_GEGLU, PD_ACT_NONE, PD_ENGINE_TC
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = (torch.randn(M, C, device=DEV, generator=g) * 1.7 + 3.0).to(torch.bfloat16)
+    gamma = 1.0 + 0.3 * torch.randn(C, device=DEV, generator=g)
+    beta = 0.2 * torch.randn(C, device=DEV, generator=g)
+    NW = 2 * N if geglu else N
+    w = torch.randn(NW, C, device=DEV, generator=g) / C ** 0.5
+    b = torch.randn(NW, device=DEV, generator=g)
+    ws, bf, cs = ops.fold_layer_norm(w, b, gamma, beta, torch.bfloat16)
+    if geglu:
+        ws, bf, cs = ops.geglu_interleave(ws), ops.geglu_interleave(bf), ops.geglu_interleave(cs)
+    stats = torch.empty(M, 2, device=DEV)
+    ops.layer_norm_stats(x, stats)
+    xf = x.float()
+    assert torch.allclose(stats[:, 0], xf.mean(1), atol=1e-4, rtol=1e-5)
+    assert torch.allclose(stats[:, 1], (xf.var(1, unbiased=False) + 1e-5).rsqrt(), atol=1e-5, rtol=1e-4)
+    out = torch.full((M, N + 8), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.linear(x, ws.contiguous(), out[:, :N], bias=bf.contiguous(), act=PD_ACT_GEGLU if geglu else PD_ACT_NONE,
+               engine=PD_ENGINE_TC, ln_stats=stats, ln_colsum=cs.contiguous())
+    torch.cuda.synchronize()
+    assert bool((out[:, N:] == 7.0).all()), "wrote past the output columns"
+    y = F.layer_norm(xf, (C,), gamma, beta, 1e-5) @ w.t() + b
+    if geglu:
+        val, gate = y.chunk(2, dim=-1)
+        y = val * F.gelu(gate)
+    assert rel_l2(out[:, :N].float(), y) < 6e-3
+
+
+def test_folded_layer_norm_rejected_off_the_tcgen05_engine():
+    from prompt_diffusion_b200._lib import PD_ENGINE_SIMT
+    ops = _ops()
+    x = torch.randn(128, 64, device=DEV).to(torch.bfloat16)
+    w = torch.randn(64, 64, device=DEV).to(torch.bfloat16)
+    out = torch.empty(128, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.linear(x, w, out, bias=torch.zeros(64, device=DEV), engine=PD_ENGINE_SIMT,
+                   ln_stats=torch.zeros(128, 2, device=DEV), ln_colsum=torch.zeros(64, device=DEV))
+
+
+@pytest.mark.parametrize("sk", [0, 1])
 @pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (640, 1280)])
-def test_linear_geglu_epilogue_matches_linear_then_geglu(M, C):
+def test_linear_geglu_epilogue_matches_linear_then_geglu(M, C, sk, request):
     """FeedForward's first linear with GEGLU fused into the tcgen05 epilogue (interleaved weight rows) vs torch fp32
-    on the same bf16 operands: x @ W^T + b -> chunk(2) -> value * gelu(gate) (attention.py:54-56)."""
+    on the same bf16 operands: x @ W^T + b -> chunk(2) -> value * gelu(gate) (attention.py:54-56).  sk=1: stream-K."""
+    from prompt_diffusion_b200 import _lib
     from prompt_diffusion_b200._lib import PD_ACT_GEGLU, PD_ENGINE_TC
     ops = _ops()
+    if sk:
+        _lib.lib.pd_debug_force_cta_group(2)
+        _lib.lib.pd_debug_force_stream_k(1)
+        request.addfinalizer(lambda: (_lib.lib.pd_debug_force_cta_group(0), _lib.lib.pd_debug_force_stream_k(0)))
     g = torch.Generator(device=DEV).manual_seed(11)
     F4 = 4 * C
     x = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
