@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpd_b200.so")
+# PD_B200_LIB selects another build of the same library (kernel A/B experiments under scripts/); never a fallback
+LIB_PATH = os.environ.get("PD_B200_LIB") or os.path.join(_HERE, "libpd_b200.so")
 
 PD_F32, PD_BF16 = 0, 1
 PD_ACT_NONE, PD_ACT_SILU, PD_ACT_GEGLU = 0, 1, 2
