@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("PD_B200_LIB") or os.path.join(_HERE, "libpd_b200.so")
 PD_F32, PD_BF16 = 0, 1
 PD_ACT_NONE, PD_ACT_SILU, PD_ACT_GEGLU = 0, 1, 2
 PD_ENGINE_AUTO, PD_ENGINE_SIMT, PD_ENGINE_TC = 0, 1, 2
-PD_ATTN_AUTO, PD_ATTN_SIMT, PD_ATTN_MMA, PD_ATTN_TC = 0, 1, 2, 3
+PD_ATTN_AUTO, PD_ATTN_SIMT, PD_ATTN_MMA, PD_ATTN_TC, PD_ATTN_SHORT = 0, 1, 2, 3, 4
 
 
 class ConvParams(C.Structure):

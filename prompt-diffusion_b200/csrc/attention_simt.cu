@@ -6,6 +6,8 @@
 // P.V all in fp32 FFMA, expf) and the generic fallback for head dims the tensor-core
 // engine does not cover.  One CTA = 64 queries of one (batch, head); keys/values stream
 // through shared memory in tiles of 64 with the usual running max / running sum.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pd {
@@ -193,6 +195,15 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
     set_error("pd_attention: tcgen05 engine needs sm_100, bf16, d <= 128 (multiple of 8), 16B-aligned tensors and pitches");
     return PD_ERR_UNSUPPORTED;
   }
+  const bool short_ok = attention_short_supported(dtype, d, Nk, ldq, ldk, ldv, ldo, q, k, v, out);
+  if (engine == 4 && !short_ok) {
+    set_error("pd_attention: short-key engine needs bf16, Nk <= 128, d <= 80 (multiple of 8), 16B-aligned k/v");
+    return PD_ERR_UNSUPPORTED;
+  }
+  static int auto_short = -1;          // PD_B200_ATTN_SHORT=0: auto never picks the short-key engine (A/B timing)
+  if (auto_short < 0) { const char* e = getenv("PD_B200_ATTN_SHORT"); auto_short = (e && e[0] == '0') ? 0 : 1; }
+  if (engine == 4 || (engine == 0 && short_ok && auto_short))
+    return attention_short(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   if (engine == 3 || (engine == 0 && tc_ok)) return attention_tc(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   if (engine == 2 && !mma_ok) {
     set_error("pd_attention: tensor-core engine needs bf16, d in {32,40,48,64,80,128,160}, 16B-aligned q/k/v");

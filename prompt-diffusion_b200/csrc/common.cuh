@@ -116,6 +116,10 @@ int attention_simt(const void* q, int ldq, const void* k, int ldk, const void* v
 int attention_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
                   int ldo, int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
 
+bool attention_short_supported(int dtype, int d, int Nk, int ldq, int ldk, int ldv, int ldo, const void* q,
+                               const void* k, const void* v, const void* out);
+int attention_short(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
+                    int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
 bool attention_tc_supported(int dtype, int d, int ldq, int ldk, int ldv, int ldo, const void* q, const void* k,
                             const void* v, const void* out);
 int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,

@@ -399,6 +399,40 @@ def test_attention_tcgen05(B, heads, Nq, Nk, d):
     assert err < 1e-2, err
 
 
+SHORT_ATTN_CASES = [(2, 8, 100, 77, 40), (1, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 2, 640, 1, 40),
+                    (1, 4, 130, 128, 64), (2, 3, 257, 81, 16), (1, 8, 333, 16, 80), (1, 5, 64, 100, 48)]
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", SHORT_ATTN_CASES)
+def test_attention_short_keys(B, heads, Nq, Nk, d):
+    """Single-pass short-key attention (engine 4: the 77-token cross-attention, attention.py:163-194) vs torch fp32
+    on the same bf16 operands; ragged Nq / Nk, one key, full 128 keys; tolerance 1e-2 rel-L2 (bf16 P)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(11)
+    Cc = heads * d
+    q = torch.randn(B * Nq, Cc, device=DEV, generator=g).to(torch.bfloat16)
+    kv = torch.randn(B * Nk, 2 * Cc, device=DEV, generator=g).to(torch.bfloat16)
+    k, v = kv[:, :Cc], kv[:, Cc:]
+    out = torch.full((B * Nq, Cc + 8), 3.0, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q, k, v, out[:, :Cc], B, heads, Nq, Nk, d, engine=4)
+    torch.cuda.synchronize()
+    assert bool((out[:, Cc:] == 3.0).all()), "wrote past the head columns"
+    ref = _attn_ref(q.reshape(B, Nq, Cc), k.reshape(B, Nk, Cc), v.reshape(B, Nk, Cc), heads, d ** -0.5)
+    err = rel_l2(out[:, :Cc].float().reshape(B, Nq, Cc), ref)
+    assert err < 1e-2, err
+    # auto dispatch takes the same engine for this shape: bit-identical result
+    out2 = torch.empty(B * Nq, Cc, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q, k, v, out2, B, heads, Nq, Nk, d)
+    assert torch.equal(out2, out[:, :Cc])
+
+
+def test_attention_short_keys_rejects_long():
+    ops = _ops()
+    q = torch.zeros(256, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.attention(q, q, q, torch.empty_like(q), 1, 1, 256, 256, 64, engine=4)
+
+
 def test_timestep_embedding_matches_oracle(golden):
     ops = _ops()
     t = torch.tensor(golden["temb_t"], device=DEV, dtype=torch.int64)
