@@ -26,5 +26,10 @@ python scripts/gn_one.py > gpurun_out/gn_one.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:gn_fused -s 2 -c 1 -f -o gpurun_out/prof_gn \
     python scripts/gn_one.py > gpurun_out/ncu_gn.log 2>&1
 echo "gn full rc=$?"
+python scripts/attn_one.py > /dev/null 2>&1; python scripts/xattn_one.py > gpurun_out/xattn_one.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:attention_short -s 2 -c 1 -f -o gpurun_out/prof_xattn \
+    python scripts/xattn_one.py > gpurun_out/ncu_xattn.log 2>&1
+echo "short attention full rc=$?"
+CROSS=1 python scripts/attn_quick.py > gpurun_out/attn_quick.log 2>&1
 python scripts/attn_bench.py > gpurun_out/attn_bench.log 2>&1; python scripts/norm_bench.py > gpurun_out/norm_bench.log 2>&1
 python scripts/gemm_bench.py > gpurun_out/gemm_bench.txt 2>&1

@@ -57,6 +57,34 @@ __global__ void k(float* out, int iters, float seed) {
       for (int i = 0; i < N; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
 #pragma unroll
       for (int i = 0; i < N; i += 4) { fadd2(l0, l1, x[i], x[i+1]); fadd2(l2, l3, x[i+2], x[i+3]); }
+    } else if (MODE == 7) {  // softmax mix with a forced software pipeline: the consumers of element pair p carry a
+      // (numerically void) dependency on the MUFU result DIST elements later, so ptxas cannot schedule them right
+      // behind their own MUFU.EX2 (its default: 2 MUFU, then FADD2 + F2FP on those results -> the warp stalls for the
+      // full SFU latency every pair)
+      constexpr int DIST = 8;
+      float x[N];
+#pragma unroll
+      for (int i = 0; i < N; i += 2) ffma2(x[i], x[i+1], a[i], a[i+1], 0.25f, -seed);
+#pragma unroll
+      for (int i = 0; i < N; ++i) asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+#pragma unroll
+      for (int i = 0; i < N; i += 4) {
+        float y0 = x[i], y1 = x[i+1], y2 = x[i+2], y3 = x[i+3];
+        if (i + DIST < N) {
+          asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tmov.b64 rc, {%4, %4};\n\t"
+              "fma.rn.f32x2 ra, rb, rc, ra;\n\tmov.b64 {%0, %1}, ra;\n\t}" : "+f"(y0), "+f"(y1) : "f"(x[i+DIST]), "f"(x[i+DIST+1]), "f"(0.0f));
+          asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tmov.b64 rc, {%4, %4};\n\t"
+              "fma.rn.f32x2 ra, rb, rc, ra;\n\tmov.b64 {%0, %1}, ra;\n\t}" : "+f"(y2), "+f"(y3) : "f"(x[i+DIST+2]), "f"(x[i+DIST+3]), "f"(0.0f));
+        }
+        asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}" : "+f"(l0), "+f"(l1) : "f"(y0), "f"(y1));
+        asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}" : "+f"(l2), "+f"(l3) : "f"(y2), "f"(y3));
+        uint32_t r0, r1;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r0) : "f"(y1), "f"(y0));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r1) : "f"(y3), "f"(y2));
+        acc ^= r0 ^ r1;
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) a[i] += 1e-7f * l0;
     } else if (MODE == 6) {  // FMNMX3
 #pragma unroll
       for (int i = 0; i < N; i += 2) asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(l0) : "f"(a[i]), "f"(a[i+1]));
@@ -89,7 +117,7 @@ int main() {
     run<3>("FADD2 (per instr)", N / 2, wps);
     run<6>("FMNMX3 (per instr)", N / 2, wps);
     run<4>("softmax mix (per element)", N, wps);
-    run<5>("mix w/o cvt, volatile order", N, wps);
+    run<7>("mix, forced sw pipeline", N, wps);
   }
   return 0;
 }
