@@ -146,3 +146,52 @@ def test_sharded_sampling_equals_single_process_gloo(world, batch, chunk, tmp_pa
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out.decode()[-2000:]
+
+
+# ---- checkpoint ingest (cldm/model.py:8-28, tool_add_control.py:17-48) ---------------------------------------
+def test_load_state_dict_reads_ckpt_and_safetensors(tmp_path):
+    from prompt_diffusion_b200.cldm.model import get_state_dict, load_state_dict
+    sd = {"control_model.zero_convs.0.0.weight": torch.randn(4, 4, 1, 1),
+          "model.diffusion_model.out.2.bias": torch.randn(4), "first_stage_model.decoder.conv_in.weight": torch.randn(2, 2)}
+    assert get_state_dict({"state_dict": sd}) is sd and get_state_dict(sd) is sd
+    p1 = str(tmp_path / "a.ckpt")
+    torch.save({"state_dict": sd, "global_step": 7}, p1)            # Lightning envelope
+    p2 = str(tmp_path / "b.pth")
+    torch.save(sd, p2)                                              # bare dict
+    import safetensors.torch
+    p3 = str(tmp_path / "c.safetensors")
+    safetensors.torch.save_file(sd, p3)
+    for p in (p1, p2, p3):
+        got = load_state_dict(p, location="cpu")
+        assert set(got) == set(sd)
+        for k in sd:
+            assert torch.equal(got[k], sd[k])
+
+
+def test_add_control_key_scheme():
+    """control_<x> copies model.diffusion_<x>; other keys copy themselves; missing ones keep the scratch init."""
+    from prompt_diffusion_b200.cldm.model import add_control, get_node_name, path_keys
+    assert get_node_name("control_model.a", "control_") == (True, "model.a")
+    assert get_node_name("control_", "control_") == (False, "")
+    assert get_node_name("model.diffusion_model.a", "control_") == (False, "")
+    pre = {"state_dict": {"model.diffusion_model.input_blocks.1.0.in_layers.2.weight": torch.full((2, 2), 3.0),
+                          "model.diffusion_model.out.2.weight": torch.full((2,), 5.0),
+                          "first_stage_model.x": torch.ones(1)}}
+    scratch = {"control_model.input_blocks.1.0.in_layers.2.weight": torch.zeros(2, 2),
+               "control_model.zero_convs.0.0.weight": torch.full((1,), 9.0),
+               "model.diffusion_model.input_blocks.1.0.in_layers.2.weight": torch.zeros(2, 2),
+               "model.diffusion_model.out.2.weight": torch.zeros(2),
+               "first_stage_model.x": torch.zeros(1)}
+    tgt, added = add_control(pre, scratch, verbose=False)
+    assert set(tgt) == set(scratch) and added == ["control_model.zero_convs.0.0.weight"]
+    assert float(tgt["control_model.input_blocks.1.0.in_layers.2.weight"][0, 0]) == 3.0      # copied from the UNet
+    assert float(tgt["model.diffusion_model.out.2.weight"][0]) == 5.0
+    assert float(tgt["control_model.zero_convs.0.0.weight"][0]) == 9.0                       # scratch value kept
+    assert tgt["first_stage_model.x"].data_ptr() != pre["state_dict"]["first_stage_model.x"].data_ptr()   # clones
+    assert sorted(path_keys(tgt)) == sorted(k for k in scratch if not k.startswith("first_stage"))
+
+
+def test_create_model_refuses_cpu():
+    from prompt_diffusion_b200.cldm.model import create_model
+    with pytest.raises(RuntimeError):
+        create_model(os.path.join(REPO, "tests", "golden", "cldm_v15_topology.yaml"), device="cpu")

@@ -6,6 +6,8 @@
 Gates (BASELINE.json north_star): per-step eps rel-L2 <= 1e-4 in fp32 mode, <= 1e-2 in bf16 mode;
 final-latent cosine >= 0.999.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -220,3 +222,23 @@ def test_apply_model_config2_shape_vs_oracle_gpu(models, cfg, state_dict_cpu):
         err = rel_l2(eps, ref)
         print(f"[parity] apply_model 512^2 {mode} vs oracle(gpu fp32): eps rel-L2 = {err:.3e}")
         assert err <= TOL[mode], (mode, err)
+
+
+def test_create_model_and_full_checkpoint_dict(models, cfg, state_dict_cpu):
+    """Notebook set-up lines (cldm/model.py:8-28): create_model(yaml) + load_state_dict(get_state_dict(ckpt)) must give
+    the same eps as the fixture's model, with the Lightning envelope and foreign entries (VAE / CLIP / EMA) present.
+    (Reading .ckpt / .safetensors files is covered on CPU in tests/test_host_cpu.py; a 4.9 GB file is not written here.)"""
+    from prompt_diffusion_b200.cldm.model import create_model, get_state_dict
+    from prompt_diffusion_b200.synth import make_conds, synthetic_inputs
+    full = dict(state_dict_cpu)
+    full["first_stage_model.decoder.conv_in.weight"] = torch.zeros(2, 2)
+    full["cond_stage_model.transformer.text_model.embeddings.position_ids"] = torch.zeros(1, 77, dtype=torch.long)
+    full["model_ema.decay"] = torch.tensor(0.9999)
+    m = create_model(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cldm_v15_topology.yaml"))
+    m.load_state_dict(get_state_dict({"state_dict": full, "global_step": 1}))
+    inp = synthetic_inputs(cfg, 1, 64, 64, seed=5, device=DEV)
+    cond, _ = make_conds(inp)
+    t = torch.full((1,), 321, device=DEV, dtype=torch.long)
+    a = m.apply_model(inp["x_T"], t, cond)
+    b = models["bf16"].apply_model(inp["x_T"], t, cond)
+    assert torch.equal(a, b)
