@@ -7,14 +7,14 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 FLAGS_ACC="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 mkdir -p ../../build
 pids=()
-for f in elementwise norm conv_simt attention_simt; do
+for f in elementwise norm softmax conv_simt attention_simt; do
   nvcc $FLAGS_ACC -c $f.cu -o ../../build/$f.o & pids+=($!)
 done
 for f in attention_mma attention_tc attention_short gemm_sm100; do
   nvcc $FLAGS_ACC -c $f.cu -o ../../build/$f.o & pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -o $OUT.tmp ../../build/elementwise.o ../../build/norm.o ../../build/conv_simt.o \
+nvcc -shared -o $OUT.tmp ../../build/elementwise.o ../../build/norm.o ../../build/softmax.o ../../build/conv_simt.o \
   ../../build/attention_simt.o ../../build/attention_mma.o ../../build/attention_tc.o ../../build/attention_short.o ../../build/gemm_sm100.o -lcudart_static -ldl -lrt -lpthread
 mv -f $OUT.tmp $OUT
 echo "built $(realpath $OUT)"

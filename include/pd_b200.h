@@ -160,6 +160,13 @@ int pd_layer_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const floa
 int pd_geglu(const void* x, int32_t ldx, void* out, int32_t ldo, int64_t rows, int32_t F,
              int32_t dtype, void* stream);
 
+/* Row softmax of a materialised score matrix: out[r,:] = softmax(x[r,:] * scale) (fp32 statistics).
+ *   The first-stage decoder's single-head, 512-channel attention (AttnBlock.forward,
+ *   ldm/modules/diffusionmodules/model.py:190-193: bmm -> * c^-0.5 -> softmax(dim=2)) runs as
+ *   pd_conv2d (q k^T) -> pd_softmax_rows -> pd_conv2d (p v).  cols <= 16384 (bf16) / 8192 (fp32). */
+int pd_softmax_rows(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                    float scale, int32_t dtype, void* stream);
+
 /* Multi-head softmax attention without materialising the score matrix.
  *   replaces CrossAttention.forward's einsum/softmax/einsum (attention.py:171-193):
  *   q [B,Nq,heads*d] pitch ldq, k/v [B,Nk,heads*d] pitch ldk/ldv, out [B,Nq,heads*d];

@@ -441,6 +441,8 @@ class ControlLDM:
         self.supports_step_graph = True     # apply_model is capture-safe once its buffers and caches are warm
         self.parameterization = cfg.parameterization
         self.channels = cfg.in_channels
+        self.scale_factor = cfg.scale_factor
+        self.first_stage_model = None       # AutoencoderKLDecoder once first_stage_model.* weights are loaded
         self._register_schedule()
 
     # ddpm.py:138-158 (the buffers DDIMSampler.make_schedule reads)
@@ -462,7 +464,21 @@ class ControlLDM:
         as first_stage_model / cond_stage_model / schedule buffers are ignored — out of scope)."""
         self.control_model.load_state_dict(sd)
         self.model.diffusion_model.load_state_dict(sd)
+        if any(k.startswith("first_stage_model.decoder.") for k in sd):
+            from ..autoencoder import AutoencoderKLDecoder
+            self.first_stage_model = AutoencoderKLDecoder(self.mode, self.device).load_state_dict(
+                sd, scale_factor=self.scale_factor)
         return self
+
+    @torch.no_grad()
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
+        """LatentDiffusion.decode_first_stage (ldm/models/diffusion/ddpm.py:820-828): ``decode(z / scale_factor)`` on
+        the B200 first-stage decoder; needs ``first_stage_model.*`` weights in the loaded checkpoint."""
+        if predict_cids:
+            raise NotImplementedError("predict_cids: the KL autoencoder of cldm_v15 has no codebook")
+        if self.first_stage_model is None:
+            raise RuntimeError("decode_first_stage: the loaded checkpoint had no first_stage_model.decoder.* weights")
+        return self.first_stage_model.decode(z, scaled=True)
 
     def eval(self):
         return self

@@ -28,6 +28,7 @@ class CLDMConfig:
     linear_start: float = 0.00085
     linear_end: float = 0.0120
     parameterization: str = "eps"
+    scale_factor: float = 0.18215   # latent scaling of decode_first_stage (cldm_v15.yaml:17, ddpm.py:827)
 
     @property
     def time_embed_dim(self) -> int:
@@ -54,7 +55,7 @@ class CLDMConfig:
                    attention_resolutions=tuple(u["attention_resolutions"]),
                    num_heads=u["num_heads"], context_dim=u["context_dim"],
                    timesteps=p.get("timesteps", 1000), linear_start=p["linear_start"],
-                   linear_end=p["linear_end"])
+                   linear_end=p["linear_end"], scale_factor=float(p.get("scale_factor", 1.0)))
 
 
 CLDM_V15 = CLDMConfig()

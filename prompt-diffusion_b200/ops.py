@@ -182,6 +182,14 @@ def geglu(x, out):
     return out
 
 
+def softmax_rows(x, out, scale=1.0):
+    """out[r, :] = softmax(x[r, :] * scale) over a 2-D (possibly pitched) score matrix (model.py:190-193)."""
+    _cuda(x, out)
+    check(lib.pd_softmax_rows(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), x.shape[0], x.shape[1], float(scale),
+                              dt_code(x), _stream()), "pd_softmax_rows")
+    return out
+
+
 def attention(q, k, v, out, B, heads, Nq, Nk, d, scale=None, engine=0):
     _cuda(q, k, v, out)
     scale = d ** -0.5 if scale is None else scale

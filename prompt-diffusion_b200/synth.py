@@ -186,3 +186,44 @@ def make_conds(inp: Dict[str, torch.Tensor]):
     un_cond = {"c_crossattn": [inp["uc_crossattn"]], "example_pair": [inp["example_pair"]],
                "query": [inp["query"]]}
     return cond, un_cond
+
+
+# ---- first-stage decoder: AutoencoderKL.decode = post_quant_conv -> Decoder ------------------
+VAE_PREFIX = "first_stage_model."
+
+
+def vae_decoder_specs(ch: int = 128, ch_mult=(1, 2, 4, 4), num_res_blocks: int = 2, z_channels: int = 4,
+                      embed_dim: int = 4, out_ch: int = 3) -> List[Spec]:
+    """(key, shape, kind, fan_in) of ``post_quant_conv`` + ``decoder.*`` exactly as
+    ldm/modules/diffusionmodules/model.py:546-616 and ldm/models/autoencoder.py:44-45 create them
+    (cldm_v15.yaml first_stage_config.ddconfig: ch 128, ch_mult [1,2,4,4], num_res_blocks 2, no up-path attention)."""
+    def res(key, cin, cout):
+        s = _norm_specs(f"{key}.norm1", cin) + _conv_specs(f"{key}.conv1", cin, cout, 3)
+        s += _norm_specs(f"{key}.norm2", cout) + _conv_specs(f"{key}.conv2", cout, cout, 3)
+        if cin != cout:
+            s += _conv_specs(f"{key}.nin_shortcut", cin, cout, 1)
+        return s
+    s = _conv_specs("post_quant_conv", embed_dim, z_channels, 1)
+    block_in = ch * ch_mult[-1]
+    s += _conv_specs("decoder.conv_in", z_channels, block_in, 3)
+    s += res("decoder.mid.block_1", block_in, block_in)
+    s += _norm_specs("decoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        s += _conv_specs(f"decoder.mid.attn_1.{n}", block_in, block_in, 1)
+    s += res("decoder.mid.block_2", block_in, block_in)
+    for i_level in reversed(range(len(ch_mult))):
+        block_out = ch * ch_mult[i_level]
+        for i_block in range(num_res_blocks + 1):
+            s += res(f"decoder.up.{i_level}.block.{i_block}", block_in, block_out)
+            block_in = block_out
+        if i_level != 0:
+            s += _conv_specs(f"decoder.up.{i_level}.upsample.conv", block_in, block_in, 3)
+    s += _norm_specs("decoder.norm_out", block_in)
+    s += _conv_specs("decoder.conv_out", block_in, out_ch, 3)
+    return [(VAE_PREFIX + k, shp, kind, fan) for (k, shp, kind, fan) in s]
+
+
+def synthetic_vae_state_dict(seed: int = 0, device="cpu", **kw) -> "OrderedDict[str, torch.Tensor]":
+    """Procedural ``first_stage_model.{post_quant_conv,decoder}.*`` checkpoint (same per-key generators as above)."""
+    return OrderedDict((key, synth_tensor(key, shape, kind, fan, seed, device))
+                       for key, shape, kind, fan in vae_decoder_specs(**kw))

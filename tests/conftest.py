@@ -20,6 +20,18 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_vae():
+    """Reference Decoder outputs (tests/golden/make_golden_vae.py)."""
+    return dict(np.load(os.path.join(REPO, "tests", "golden", "vae_decoder_golden.npz")))
+
+
+@pytest.fixture(scope="session")
+def vae_state_dict_cpu():
+    from prompt_diffusion_b200.synth import synthetic_vae_state_dict
+    return synthetic_vae_state_dict(seed=0)
+
+
+@pytest.fixture(scope="session")
 def cfg():
     from prompt_diffusion_b200.config import CLDM_V15
     return CLDM_V15

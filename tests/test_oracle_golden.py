@@ -76,3 +76,16 @@ def test_sampler_matches_reference(golden, cfg, state_dict_cpu):
                                log_every_t=5, max_steps=1)
     assert rel_l2(inter["x_inter"][1], golden["sample_cfg1_x_inter"][1]) < 1e-5
     assert rel_l2(inter["pred_x0"][1], golden["sample_cfg1_pred_x0"][1]) < 1e-5
+
+
+def test_vae_decode_oracle_vs_reference_golden(golden_vae, vae_state_dict_cpu):
+    """oracle/vae_oracle.py (decode_first_stage -> AutoencoderKL.decode -> Decoder.forward) against the reference's own
+    Decoder output on the same procedural checkpoint; also pins the parameter census (49.5 M)."""
+    from oracle import vae_oracle as V
+    assert int(golden_vae["n_params"]) == sum(v.numel() for v in vae_state_dict_cpu.values())
+    torch.set_grad_enabled(False)
+    for name in ("z16", "z8x24"):
+        z = torch.tensor(golden_vae[name + "_z"])
+        img = V.decode_first_stage(vae_state_dict_cpu, z, float(golden_vae["scale_factor"]))
+        assert img.shape == golden_vae[name + "_img"].shape
+        assert rel_l2(img, golden_vae[name + "_img"]) < 1e-5, name
