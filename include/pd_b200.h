@@ -182,6 +182,22 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
                     int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
                     int32_t Nk, int32_t d, float scale, int32_t dtype, int32_t engine, void* stream);
 
+/* Causal self-attention (query i attends keys <= i), Nq == Nk == N: the CLIP text tower behind FrozenCLIPEmbedder
+ * (ldm/modules/encoders/modules.py:117-128 -> transformers CLIPTextModel, 77 tokens, 12 heads, d 64).  bf16: the
+ * single-pass short-key kernel (N <= 128, d <= 80); otherwise / fp32: the SIMT engine. */
+int pd_attention_causal(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
+                        int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t N,
+                        int32_t d, float scale, int32_t dtype, void* stream);
+
+/* CLIP text embeddings: out[r,:] = token_embedding[ids[r],:] + position_embedding[r % L,:] (fp32 tables, ids int64,
+ * out in `dtype`, pitch ldo); ids outside [0, vocab) are clamped. */
+int pd_embedding_lookup(const int64_t* ids, const float* tok, const float* pos, void* out, int32_t ldo,
+                        int64_t rows, int32_t L, int32_t C, int32_t vocab, int32_t dtype, void* stream);
+
+/* quick-GELU of the CLIP MLP: out = x * sigmoid(1.702 x), row-pitched 2-D tensors (in place allowed). */
+int pd_quick_gelu(const void* x, int32_t ldx, void* out, int32_t ldo, int64_t rows, int32_t C,
+                  int32_t dtype, void* stream);
+
 /* timestep_embedding (util.py:154-174): t [B] int64 -> [B, dim] = [cos(t f), sin(t f)].
  * `freqs` (optional, dim/2 device floats) is the frequency table exp(-ln(max_period) j / half) as the
  * caller's host library rounds it (the reference builds it with torch.exp on the host, util.py:165-167);

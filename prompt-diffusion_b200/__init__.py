@@ -15,6 +15,9 @@ def __getattr__(name):
     if name in ("ControlLDM", "ControlNet", "ControlledUnetModel", "DDIMSampler"):
         from . import cldm as _cldm
         return getattr(_cldm, name)
+    if name == "FrozenCLIPTextEncoder":
+        from .clip_text import FrozenCLIPTextEncoder
+        return FrozenCLIPTextEncoder
     if name == "AutoencoderKLDecoder":
         from .autoencoder import AutoencoderKLDecoder
         return AutoencoderKLDecoder

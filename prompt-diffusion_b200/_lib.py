@@ -60,6 +60,13 @@ SIGNATURES = {
                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "pd_layer_norm": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "pd_attention_causal": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,
+                                      C.c_void_p]),
+    "pd_embedding_lookup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "pd_quick_gelu": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                C.c_void_p]),
     "pd_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_float,
                                   C.c_int32, C.c_void_p]),
     "pd_geglu": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,

@@ -443,6 +443,7 @@ class ControlLDM:
         self.channels = cfg.in_channels
         self.scale_factor = cfg.scale_factor
         self.first_stage_model = None       # AutoencoderKLDecoder once first_stage_model.* weights are loaded
+        self.cond_stage_model = None        # FrozenCLIPTextEncoder once cond_stage_model.transformer.* weights are loaded
         self._register_schedule()
 
     # ddpm.py:138-158 (the buffers DDIMSampler.make_schedule reads)
@@ -464,11 +465,27 @@ class ControlLDM:
         as first_stage_model / cond_stage_model / schedule buffers are ignored — out of scope)."""
         self.control_model.load_state_dict(sd)
         self.model.diffusion_model.load_state_dict(sd)
-        if any(k.startswith("first_stage_model.decoder.") for k in sd):
+        # optional neighbours of the path (SURVEY 8f): built only when the checkpoint carries their complete weight sets
+        if ("cond_stage_model.transformer.text_model.embeddings.token_embedding.weight" in sd and
+                "cond_stage_model.transformer.text_model.final_layer_norm.weight" in sd):
+            from ..clip_text import FrozenCLIPTextEncoder
+            self.cond_stage_model = FrozenCLIPTextEncoder(self.mode, self.device).load_state_dict(sd)
+        if "first_stage_model.post_quant_conv.weight" in sd and "first_stage_model.decoder.mid.attn_1.q.weight" in sd:
             from ..autoencoder import AutoencoderKLDecoder
             self.first_stage_model = AutoencoderKLDecoder(self.mode, self.device).load_state_dict(
                 sd, scale_factor=self.scale_factor)
         return self
+
+    @torch.no_grad()
+    def get_learned_conditioning(self, c):
+        """LatentDiffusion.get_learned_conditioning (ldm/models/diffusion/ddpm.py:554-565) for token-id input: the
+        reference passes strings through ``cond_stage_model.encode`` (tokenizer + CLIP text tower); tokenisation is
+        host-side string work outside this path, so ``c`` is the tokenizer's ``input_ids`` [B, 77]."""
+        if self.cond_stage_model is None:
+            raise RuntimeError("get_learned_conditioning: the loaded checkpoint had no cond_stage_model.transformer.* weights")
+        if not torch.is_tensor(c):
+            raise TypeError("get_learned_conditioning wants token ids (int64 [B, 77]); tokenise with CLIPTokenizer first")
+        return self.cond_stage_model.encode(c)
 
     @torch.no_grad()
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):

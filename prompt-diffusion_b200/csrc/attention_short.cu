@@ -48,8 +48,9 @@ __device__ __forceinline__ float xs_ex2(float x) {
   return y;
 }
 
-// DP: head dim padded to a multiple of 16; NK16: key capacity in units of 16
-template <int DP, int NK16>
+// DP: head dim padded to a multiple of 16; NK16: key capacity in units of 16; CAUSAL: query i sees keys <= i (the
+// CLIP text tower's self-attention, 77 tokens; a separate instantiation, the cross-attention code is unchanged)
+template <int DP, int NK16, bool CAUSAL>
 __global__ void __launch_bounds__(XTHREADS)
 attention_short_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k, int ldk,
                        const bf16* __restrict__ v, int ldv, bf16* __restrict__ out, int ldo, int Nq, int Nk, int d,
@@ -133,7 +134,8 @@ attention_short_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restri
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int key = kbase + j * 8 + (e & 1);
-      const float val = key < Nk ? s[j][e] * scale_log2 : -INFINITY;
+      const bool vis = key < Nk && (!CAUSAL || key <= ((e >> 1) ? row1 : row0));
+      const float val = vis ? s[j][e] * scale_log2 : -INFINITY;
       s[j][e] = val;
       mx[e >> 1] = fmaxf(mx[e >> 1], val);
     }
@@ -190,12 +192,12 @@ attention_short_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restri
   }
 }
 
-template <int DP, int NK16>
+template <int DP, int NK16, bool CAUSAL>
 static int launch_attn_short(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
                              int ldo, int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s) {
   constexpr int LD = DP + 8;
   const size_t smem = (size_t)2 * NK16 * 16 * LD * sizeof(bf16);
-  auto kern = attention_short_kernel<DP, NK16>;
+  auto kern = attention_short_kernel<DP, NK16, CAUSAL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -220,9 +222,13 @@ bool attention_short_supported(int dtype, int d, int Nk, int ldq, int ldk, int l
 }
 
 int attention_short(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
-                    int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s) {
+                    int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s, int causal) {
   const bool wide = d > 48, longk = Nk > 80;
-#define PD_XS(DPv, NKv) return launch_attn_short<DPv, NKv>(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s)
+#define PD_XS(DPv, NKv)                                                                                                   \
+  do {                                                                                                                    \
+    if (causal) return launch_attn_short<DPv, NKv, true>(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s); \
+    return launch_attn_short<DPv, NKv, false>(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);            \
+  } while (0)
   if (!wide && !longk) PD_XS(48, 5);
   if (!wide && longk) PD_XS(48, 8);
   if (wide && !longk) PD_XS(80, 5);

@@ -18,7 +18,7 @@ template <typename T, int NC>  // NC = ceil(d / 16); D = 16*NC padded head dim
 __global__ void __launch_bounds__(ATHREADS)
 attention_simt_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k, int ldk,
                       const T* __restrict__ v, int ldv, T* __restrict__ out, int ldo, int Nq, int Nk, int d,
-                      float scale) {
+                      float scale, int causal) {
   constexpr int D = 16 * NC;
   extern __shared__ float sm[];
   float* Qs = sm;                       // [ABQ][D+1]
@@ -80,7 +80,9 @@ attention_simt_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k,
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        s[i][j] = (k0 + tx + 16 * j < Nk) ? s[i][j] * scale : -INFINITY;
+        const int key = k0 + tx + 16 * j;
+        // causal (CLIP text tower): query i sees keys <= i; key 0 is visible to every row, so m_run is finite from tile 0 on
+        s[i][j] = (key < Nk && (!causal || key <= q0 + ty * 4 + i)) ? s[i][j] * scale : -INFINITY;
         mx = fmaxf(mx, s[i][j]);
       }
 #pragma unroll
@@ -135,7 +137,7 @@ attention_simt_kernel(const T* __restrict__ q, int ldq, const T* __restrict__ k,
 
 template <typename T, int NC>
 static int launch_attn_simt(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
-                            int ldo, int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s) {
+                            int ldo, int B, int heads, int Nq, int Nk, int d, float scale, int causal, cudaStream_t s) {
   constexpr int D = 16 * NC;
   size_t smem = sizeof(float) * (ABQ * (D + 1) + ABK * (D + 1) + ABK * D + ABQ * (ABK + 1));
   auto kern = attention_simt_kernel<T, NC>;
@@ -146,16 +148,16 @@ static int launch_attn_simt(const void* q, int ldq, const void* k, int ldk, cons
   }
   dim3 grid((Nq + ABQ - 1) / ABQ, heads, B);
   kern<<<grid, ATHREADS, smem, s>>>((const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, (T*)out, ldo, Nq, Nk,
-                                    d, scale);
+                                    d, scale, causal);
   return check_launch("attention_simt");
 }
 
 template <typename T>
 static int attn_simt_t(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
-                       int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s) {
+                       int B, int heads, int Nq, int Nk, int d, float scale, int causal, cudaStream_t s) {
   int nc = (d + 15) / 16;
 #define PD_CASE(N) \
-  if (nc <= N) return launch_attn_simt<T, N>(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s)
+  if (nc <= N) return launch_attn_simt<T, N>(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, causal, s)
   PD_CASE(1); PD_CASE(2); PD_CASE(3); PD_CASE(4); PD_CASE(5); PD_CASE(8); PD_CASE(10);
 #undef PD_CASE
   set_error("pd_attention: head dim %d > 160 unsupported", d);
@@ -163,9 +165,9 @@ static int attn_simt_t(const void* q, int ldq, const void* k, int ldk, const voi
 }
 
 int attention_simt(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
-                   int B, int heads, int Nq, int Nk, int d, float scale, int dtype, cudaStream_t s) {
-  if (dtype == PD_F32) return attn_simt_t<float>(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
-  return attn_simt_t<bf16>(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
+                   int B, int heads, int Nq, int Nk, int d, float scale, int dtype, cudaStream_t s, int causal) {
+  if (dtype == PD_F32) return attn_simt_t<float>(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, causal, s);
+  return attn_simt_t<bf16>(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, causal, s);
 }
 
 }  // namespace pd
@@ -211,6 +213,21 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
   }
   if (engine != 1 && mma_ok) return attention_mma(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   return attention_simt(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, dtype, s);
+}
+
+int pd_attention_causal(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* out,
+                        int32_t ldo, int32_t B, int32_t heads, int32_t N, int32_t d, float scale, int32_t dtype,
+                        void* stream) {
+  PD_REQUIRE(q && k && v && out, "pd_attention_causal: null pointer");
+  PD_REQUIRE(B > 0 && heads > 0 && N > 0 && d > 0 && d <= 160, "pd_attention_causal: bad geometry");
+  PD_REQUIRE(ldq >= heads * d && ldk >= heads * d && ldv >= heads * d && ldo >= heads * d,
+             "pd_attention_causal: pitch smaller than heads*d");
+  PD_REQUIRE(dtype == PD_F32 || dtype == PD_BF16, "pd_attention_causal: bad dtype %d", dtype);
+  PD_REQUIRE(heads <= 65535 && B <= 65535, "pd_attention_causal: grid too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (attention_short_supported(dtype, d, N, ldq, ldk, ldv, ldo, q, k, v, out))
+    return attention_short(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, N, N, d, scale, s, 1);
+  return attention_simt(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, N, N, d, scale, dtype, s, 1);
 }
 
 int pd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* out,

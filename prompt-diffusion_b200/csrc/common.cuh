@@ -112,14 +112,14 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s);       // gemm_sm100.cu
 bool conv2d_tc_supported(const pd_conv_params* p, const char** why);
 int attention_simt(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
                    int ldo, int B, int heads, int Nq, int Nk, int d, float scale, int dtype,
-                   cudaStream_t s);
+                   cudaStream_t s, int causal = 0);
 int attention_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out,
                   int ldo, int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
 
 bool attention_short_supported(int dtype, int d, int Nk, int ldq, int ldk, int ldv, int ldo, const void* q,
                                const void* k, const void* v, const void* out);
 int attention_short(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo,
-                    int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
+                    int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t s, int causal = 0);
 bool attention_tc_supported(int dtype, int d, int ldq, int ldk, int ldv, int ldo, const void* q, const void* k,
                             const void* v, const void* out);
 int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,

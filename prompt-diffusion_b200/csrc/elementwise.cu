@@ -154,6 +154,33 @@ __global__ void silu_kernel(const T* __restrict__ x, T* __restrict__ out, int64_
     Dt<T>::st(out + i, silu_acc(Dt<T>::ld(x + i)));
 }
 
+// ---- CLIP text tower pieces (FrozenCLIPEmbedder -> CLIPTextModel, ldm/modules/encoders/modules.py:117-128) ----------
+// embeddings: out[r, :] = token_embedding[ids[r], :] + position_embedding[r % L, :]   (fp32 tables -> compute dtype)
+template <typename T>
+__global__ void embedding_lookup_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok,
+                                        const float* __restrict__ pos, T* __restrict__ out, int ldo, int64_t rows, int L,
+                                        int C, int vocab) {
+  const int64_t n = rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    int64_t id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);           // out-of-range ids are clamped, never read out of bounds
+    Dt<T>::st(out + r * ldo + c, tok[id * C + c] + pos[(r % L) * (int64_t)C + c]);
+  }
+}
+// quick-GELU of the CLIP MLP: x * sigmoid(1.702 x)
+template <typename T>
+__global__ void quick_gelu_kernel(const T* __restrict__ x, int ldx, T* __restrict__ out, int ldo, int64_t rows, int C) {
+  const int64_t n = rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    const float v = Dt<T>::ld(x + r * ldx + c);
+    Dt<T>::st(out + r * ldo + c, v / (1.0f + expf(-1.702f * v)));
+  }
+}
+
 // ---- nearest x2 upsample ----------------------------------------------------------
 // Each thread moves one 16-byte channel vector of one OUTPUT pixel (contiguous writes,
 // reads hit L1/L2 four times per source vector).
@@ -349,6 +376,31 @@ int pd_silu(const void* x, void* out, int64_t n, int32_t dtype, void* stream) {
   else
     PD_REQUIRE(false, "pd_silu: bad dtype %d", dtype);
   return check_launch("pd_silu");
+}
+
+int pd_embedding_lookup(const int64_t* ids, const float* tok, const float* pos, void* out, int32_t ldo, int64_t rows,
+                        int32_t L, int32_t C, int32_t vocab, int32_t dtype, void* stream) {
+  PD_REQUIRE(ids && tok && pos && out && rows > 0 && L > 0 && C > 0 && vocab > 0 && ldo >= C, "pd_embedding_lookup: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == PD_F32)
+    embedding_lookup_kernel<float><<<grid_for(rows * C, 256), 256, 0, s>>>(ids, tok, pos, (float*)out, ldo, rows, L, C, vocab);
+  else if (dtype == PD_BF16)
+    embedding_lookup_kernel<bf16><<<grid_for(rows * C, 256), 256, 0, s>>>(ids, tok, pos, (bf16*)out, ldo, rows, L, C, vocab);
+  else
+    PD_REQUIRE(false, "pd_embedding_lookup: bad dtype %d", dtype);
+  return check_launch("pd_embedding_lookup");
+}
+
+int pd_quick_gelu(const void* x, int32_t ldx, void* out, int32_t ldo, int64_t rows, int32_t C, int32_t dtype, void* stream) {
+  PD_REQUIRE(x && out && rows > 0 && C > 0 && ldx >= C && ldo >= C, "pd_quick_gelu: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == PD_F32)
+    quick_gelu_kernel<float><<<grid_for(rows * C, 256), 256, 0, s>>>((const float*)x, ldx, (float*)out, ldo, rows, C);
+  else if (dtype == PD_BF16)
+    quick_gelu_kernel<bf16><<<grid_for(rows * C, 256), 256, 0, s>>>((const bf16*)x, ldx, (bf16*)out, ldo, rows, C);
+  else
+    PD_REQUIRE(false, "pd_quick_gelu: bad dtype %d", dtype);
+  return check_launch("pd_quick_gelu");
 }
 
 int pd_upsample2x(const void* x, int32_t ldx, void* out, int32_t ldo, int32_t B, int32_t H, int32_t W,

@@ -182,6 +182,34 @@ def geglu(x, out):
     return out
 
 
+def attention_causal(q, k, v, out, B, heads, N, d, scale=None):
+    """Causal self-attention over N tokens (CLIP text tower): query i attends keys <= i."""
+    _cuda(q, k, v, out)
+    scale = d ** -0.5 if scale is None else scale
+    check(lib.pd_attention_causal(q.data_ptr(), _ld(q), k.data_ptr(), _ld(k), v.data_ptr(), _ld(v), out.data_ptr(),
+                                  _ld(out), B, heads, N, d, float(scale), dt_code(q), _stream()), "pd_attention_causal")
+    return out
+
+
+def embedding_lookup(ids, tok, pos, out, L):
+    """out[r] = tok[ids[r]] + pos[r % L]; ids int64 [rows], tok / pos fp32 tables, out [rows, C] in its own dtype."""
+    _cuda(ids, tok, pos, out)
+    if ids.dtype != torch.int64 or not ids.is_contiguous() or tok.dtype != torch.float32 or pos.dtype != torch.float32 \
+            or not tok.is_contiguous() or not pos.is_contiguous() or tok.shape[1] != out.shape[1] or pos.shape[0] < L:
+        raise TypeError("embedding_lookup wants contiguous int64 ids and contiguous fp32 [vocab, C] / [>=L, C] tables")
+    check(lib.pd_embedding_lookup(ids.data_ptr(), tok.data_ptr(), pos.data_ptr(), out.data_ptr(), _ld(out),
+                                  ids.numel(), L, out.shape[1], tok.shape[0], dt_code(out), _stream()),
+          "pd_embedding_lookup")
+    return out
+
+
+def quick_gelu(x, out):
+    _cuda(x, out)
+    check(lib.pd_quick_gelu(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), x.shape[0], x.shape[1], dt_code(x),
+                            _stream()), "pd_quick_gelu")
+    return out
+
+
 def softmax_rows(x, out, scale=1.0):
     """out[r, :] = softmax(x[r, :] * scale) over a 2-D (possibly pitched) score matrix (model.py:190-193)."""
     _cuda(x, out)

@@ -144,6 +144,8 @@ def synth_tensor(key: str, shape, kind: str, fan: int, seed: int = 0, device="cp
         return 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
     if kind == "nb":
         return 0.1 * torch.randn(shape, generator=g, device=device)
+    if kind == "e":                                       # embedding table (fan = 1 / std)
+        return torch.randn(shape, generator=g, device=device) / float(fan)
     raise ValueError(kind)
 
 
@@ -227,3 +229,40 @@ def synthetic_vae_state_dict(seed: int = 0, device="cpu", **kw) -> "OrderedDict[
     """Procedural ``first_stage_model.{post_quant_conv,decoder}.*`` checkpoint (same per-key generators as above)."""
     return OrderedDict((key, synth_tensor(key, shape, kind, fan, seed, device))
                        for key, shape, kind, fan in vae_decoder_specs(**kw))
+
+
+# ---- CLIP text encoder (SURVEY.md 8f-3): FrozenCLIPEmbedder's CLIPTextModel, ViT-L/14 text tower ---------------
+CLIP_PREFIX = "cond_stage_model.transformer."
+
+
+def clip_text_specs(vocab: int = 49408, width: int = 768, layers: int = 12, mlp: int = 3072, max_len: int = 77) -> List[Spec]:
+    """(key, shape, kind, fan) of ``CLIPTextModel("openai/clip-vit-large-patch14")`` as the LDM checkpoint stores it under
+    ``cond_stage_model.transformer.`` (ldm/modules/encoders/modules.py:96-97): 196 tensors, 123 060 480 parameters."""
+    t = "text_model"
+    s: List[Spec] = [(f"{t}.embeddings.token_embedding.weight", (vocab, width), "e", 50),
+                     (f"{t}.embeddings.position_embedding.weight", (max_len, width), "e", 100)]
+    for i in range(layers):
+        L = f"{t}.encoder.layers.{i}"
+        for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            s += _lin_specs(f"{L}.self_attn.{n}", width, width)
+        s += _norm_specs(f"{L}.layer_norm1", width)
+        s += _lin_specs(f"{L}.mlp.fc1", width, mlp) + _lin_specs(f"{L}.mlp.fc2", mlp, width)
+        s += _norm_specs(f"{L}.layer_norm2", width)
+    s += _norm_specs(f"{t}.final_layer_norm", width)
+    return [(CLIP_PREFIX + k, shp, kind, fan) for (k, shp, kind, fan) in s]
+
+
+def synthetic_clip_state_dict(seed: int = 0, device="cpu", **kw) -> "OrderedDict[str, torch.Tensor]":
+    return OrderedDict((key, synth_tensor(key, shape, kind, fan, seed, device))
+                       for key, shape, kind, fan in clip_text_specs(**kw))
+
+
+def synthetic_tokens(batch: int, seed: int = 2, max_len: int = 77, vocab: int = 49408) -> torch.Tensor:
+    """Token ids shaped like the CLIP tokenizer's output (modules.py:118-120): BOS, a random-length prompt, EOS padding."""
+    g = _gen(seed, "tokens", "cpu")
+    ids = torch.randint(0, vocab - 2, (batch, max_len), generator=g)
+    lens = torch.randint(3, max_len - 1, (batch,), generator=g)
+    ids[:, 0] = vocab - 2                                   # <|startoftext|> = 49406
+    for b in range(batch):
+        ids[b, int(lens[b]):] = vocab - 1                   # <|endoftext|> = 49407 (also the pad token of this tokenizer)
+    return ids

@@ -32,6 +32,18 @@ def vae_state_dict_cpu():
 
 
 @pytest.fixture(scope="session")
+def golden_clip():
+    """transformers.CLIPTextModel outputs (tests/golden/make_golden_clip.py)."""
+    return dict(np.load(os.path.join(REPO, "tests", "golden", "clip_text_golden.npz")))
+
+
+@pytest.fixture(scope="session")
+def clip_state_dict_cpu():
+    from prompt_diffusion_b200.synth import synthetic_clip_state_dict
+    return synthetic_clip_state_dict(seed=0)
+
+
+@pytest.fixture(scope="session")
 def cfg():
     from prompt_diffusion_b200.config import CLDM_V15
     return CLDM_V15

@@ -89,3 +89,16 @@ def test_vae_decode_oracle_vs_reference_golden(golden_vae, vae_state_dict_cpu):
         img = V.decode_first_stage(vae_state_dict_cpu, z, float(golden_vae["scale_factor"]))
         assert img.shape == golden_vae[name + "_img"].shape
         assert rel_l2(img, golden_vae[name + "_img"]) < 1e-5, name
+
+
+def test_clip_text_oracle_vs_transformers_golden(golden_clip, clip_state_dict_cpu):
+    """oracle/clip_oracle.py against transformers.CLIPTextModel on the same procedural checkpoint and token ids; pins
+    the parameter census (123 060 480) and the tokenizer-shaped synthetic ids."""
+    from oracle import clip_oracle as C
+    from prompt_diffusion_b200.synth import synthetic_tokens
+    assert int(golden_clip["n_params"]) == sum(v.numel() for v in clip_state_dict_cpu.values()) == 123_060_480
+    tokens = torch.tensor(golden_clip["tokens"])
+    assert torch.equal(tokens, synthetic_tokens(3, seed=2))
+    with torch.no_grad():
+        z = C.clip_text_forward(clip_state_dict_cpu, tokens)
+    assert z.shape == golden_clip["z"].shape and rel_l2(z, golden_clip["z"]) < 1e-5
