@@ -49,7 +49,9 @@ struct TcArgs {
   int tiles_x, tiles_y, tiles_b, m_tiles, n_tiles, BN, stages;   // BN = N extent of the (CG x 128) x BN tile
   unsigned long long* dbg;      // optional timeline buffer [3 roles][64 tiles][2] (globaltimer ns), CTA 0 only
   int w_blocked;                // weights are k-block-major [K/64][Cout][64]: B tiles are contiguous in HBM (3-D map)
-  int dbg_mode;                 // timing experiments only (wrong results): 1 = no MMAs issued, 2 = no TMA loads issued
+  int dbg_mode;                 // timing experiments only (wrong results): 1 = no MMAs issued, 2 = no TMA loads issued;
+                                // epilogue: 3 = no TMA stores, 4 = no bias loads, 5 = no TMEM loads, 6 = no proxy fence, 7 = no group barriers,
+                                // 8 = no epilogue work at all, 9 = no MMA and no TMA loads, 10 = no per-element math / smem writes, 11 = no smem writes
   int epi_tma;                  // 1: bf16 output staged in smem and written by TMA
   int sk;                       // 1: stream-K schedule (the (tile, k-block) space is cut evenly over the workers)
   float* sk_ws;                 // stream-K partial accumulators [worker][2 slots][CG][256 cols][128 rows] fp32
@@ -195,7 +197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (kb == kb1 - 1 && lane == 0) PD_DBG(0, tix, 1);
           unsigned char* sa = smem + stage * stage_bytes;
           unsigned char* sb = sa + TC_A_BYTES;
-          if (a.dbg_mode == 2) {
+          if (a.dbg_mode == 2 || a.dbg_mode == 9) {
             if (cta_rank == 0 && elect_one()) mbar_arrive(&full_bar[stage]);
             __syncwarp();
             if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -252,7 +254,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
-              if (a.dbg_mode == 1) break;
+              if (a.dbg_mode == 1 || a.dbg_mode == 9) break;
               // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 field
               const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;
               if (CG == 2) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, accum);
@@ -482,6 +484,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         __syncwarp();
         if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
       }
+      if (a.dbg_mode == 8) {                 // timing experiment: hand the accumulator straight back, no epilogue work
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0 && ns_mine != 0 && !partial) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
+        if (RES) res_phase ^= 1u;
+        continue;
+      }
       const float* rvp = nullptr;
       if (RV) rvp = a.rowvec + (row_ok ? (m / a.hw_real) : 0) * a.ldrv;
       float ln_mu = 0.f, ln_rs = 0.f;
@@ -491,11 +500,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int w = sl < n64 ? 64 : 32;
         const int col0 = sl * 64;
         unsigned char* stg = gstg + i * 16384;
+        const uint32_t stg_s = s_u32(stg);
         uint32_t v[64];
         if (!partial) {
+          if (a.dbg_mode != 5) {
           tmem_ld32(t_row + (uint32_t)col0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           if (w == 64) tmem_ld32(t_row + (uint32_t)col0 + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
           tmem_ld_wait();
+          }
           if (i == ns_mine - 1) {            // accumulator drained by this warp: hand it back to the MMA warp early
             tc_fence_before();
             __syncwarp();
@@ -521,8 +533,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         } else {
           // with two slabs per tile, buffer i was last read by the store issued two slabs ago: the most recent store
           // (other buffer) may still be in flight, so its latency overlaps this slab instead of stalling every tile
-          if (elected) { if (ns_mine == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-          epi_bar_sync(bar_id);
+          if (elected && a.dbg_mode != 3) { if (ns_mine == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          if (a.dbg_mode != 7) epi_bar_sync(bar_id);
         }
         if constexpr (GEGLU) {
           // slab columns [0,32) = values, [32,64) = their gates (load-time row interleave); BN % 64 == 0 (host-checked)
@@ -555,9 +567,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               f[e] = (__uint_as_float(v[g * 8 + e]) + bx[e]) * gelu_erf_fast(__uint_as_float(v[32 + g * 8 + e]) + bg[e]);
             }
             const int off = r * 64 + ((g ^ ((r >> 1) & 3)) << 4);     // SWIZZLE_64B rows of the 32-column output box
-            *reinterpret_cast<bf16x8*>(stg + off) = pack8(f);
+            sts_bf16x8(stg_s + (uint32_t)off, pack8(f));
           }
-        } else {
+        } else if (a.dbg_mode != 10) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           if (g * 8 < w) {
@@ -573,7 +585,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = (f[e] - ln_mu * cs[e]) * ln_rs;
             }
-            {
+            if (a.dbg_mode != 4) {
               const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
               const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
               f[0] = (f[0] + q0.x) * alpha; f[1] = (f[1] + q0.y) * alpha; f[2] = (f[2] + q0.z) * alpha;
@@ -588,10 +600,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
             // 16-byte chunk g of row r inside the TMA-swizzled slab (SWIZZLE_128B / SWIZZLE_64B rows)
             const int off = w == 64 ? r * 128 + ((g ^ (r & 7)) << 4) : r * 64 + ((g ^ ((r >> 1) & 3)) << 4);
-            bf16x8* cell = reinterpret_cast<bf16x8*>(stg + off);
+            const uint32_t cell = stg_s + (uint32_t)off;
             if (RES) {
               float rf[8];
-              unpack8(*cell, rf);
+              unpack8(lds_bf16x8(cell), rf);
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] += rf[e];
             }
@@ -599,13 +611,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
             }
-            *cell = pack8(f);
+            if (a.dbg_mode != 11) sts_bf16x8(cell, pack8(f)); else if (f[0] == 1.2345f) sts_bf16x8(cell, pack8(f));
           }
         }
         }
-        fence_proxy_async();               // generic-proxy smem writes -> visible to the TMA engine
-        epi_bar_sync(bar_id);
-        if (elected) {
+        if (a.dbg_mode != 6) fence_proxy_async();               // generic-proxy smem writes -> visible to the TMA engine
+        if (a.dbg_mode != 7) epi_bar_sync(bar_id);
+        if (elected && a.dbg_mode != 3) {
           if constexpr (GEGLU) tma_store_4d(&map_o32, stg, (n0 + col0) >> 1, x0, y0, b0);
           else tma_store_4d(w == 64 ? &map_o64 : &map_o32, stg, n0 + col0, x0, y0, b0);
           tma_store_commit();

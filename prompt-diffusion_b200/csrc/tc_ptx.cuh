@@ -195,6 +195,19 @@ __device__ __forceinline__ void tmem_st16p(uint32_t taddr, const uint32_t* r) {
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
+// 16-byte shared-memory accesses by 32-bit shared address: a bf16x8 store through a GENERIC pointer derived from the
+// aligned dynamic-smem base compiles to four 4-byte generic ST.E (ptxas loses both the address space and the vector
+// width), which made the epilogue of the short-K layers instruction- and LSU-bound
+__device__ __forceinline__ void sts_bf16x8(uint32_t saddr, const bf16x8& v) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+}
+__device__ __forceinline__ bf16x8 lds_bf16x8(uint32_t saddr) {
+  bf16x8 v;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(saddr) : "memory");
+  return v;
+}
 // packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 halve the issue slots of the softmax inner loop)
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
   asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"

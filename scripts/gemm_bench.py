@@ -46,6 +46,7 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--blocked", action="store_true", help="k-block-major weight layout")
 ap.add_argument("--small", action="store_true", help="fixed-overhead study: tiny and short-K GEMMs")
 ap.add_argument("--modes", action="store_true", help="timing experiment: full kernel vs no-MMA vs no-TMA, per tile shape")
+ap.add_argument("--epi-modes", action="store_true", help="timing experiment on the epilogue of short-K layers (gemm_sm100.cu dbg_mode 3..7)")
 a = ap.parse_args()
 BLOCKED = a.blocked
 if a.small:
@@ -68,6 +69,19 @@ elif a.modes:
                 row.append(run(*s_, iters=a.iters)[0])
             _lib.lib.pd_debug_gemm_mode(0)
             print("%4d %3dx%-3d %5d %5d %2d %3d %2d | %8.1f | %8.1f | %8.1f" % (*s_, cg, *row))
+    _lib.lib.pd_debug_force_cta_group(0)
+elif a.epi_modes:
+    from prompt_diffusion_b200 import _lib
+    print("   B   HxW     C     N ks res |  full | noMMA | noTMA | noStore | noBias | noTMEMld | noFence | noBar | noEpi | noMMA+noTMA | noMath | noSTS (us)")
+    for s_ in [(16, 64, 64, 320, 320, 1, 0), (16, 64, 64, 320, 960, 1, 0), (16, 64, 64, 320, 2560, 1, 0), (16, 32, 32, 640, 640, 1, 0),
+               (16, 16, 16, 1280, 1280, 1, 0), (16, 64, 64, 320, 320, 3, 0)]:
+        _lib.lib.pd_debug_force_cta_group(1)
+        row = []
+        for mode in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11):
+            _lib.lib.pd_debug_gemm_mode(mode)
+            row.append(run(*s_, iters=a.iters)[0])
+        _lib.lib.pd_debug_gemm_mode(0)
+        print("%4d %3dx%-3d %5d %5d %2d %3d | " % s_ + " | ".join("%6.1f" % r for r in row))
     _lib.lib.pd_debug_force_cta_group(0)
 elif a.one:
     B, H, W, C, N, ks, res = a.one
