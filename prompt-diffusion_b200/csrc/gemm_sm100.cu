@@ -50,8 +50,8 @@ struct TcArgs {
   unsigned long long* dbg;      // optional timeline buffer [3 roles][64 tiles][2] (globaltimer ns), CTA 0 only
   int w_blocked;                // weights are k-block-major [K/64][Cout][64]: B tiles are contiguous in HBM (3-D map)
   int dbg_mode;                 // timing experiments only (wrong results): 1 = no MMAs issued, 2 = no TMA loads issued;
-                                // epilogue: 3 = no TMA stores, 4 = no bias loads, 5 = no TMEM loads, 6 = no proxy fence, 7 = no group barriers,
-                                // 8 = no epilogue work at all, 9 = no MMA and no TMA loads, 10 = no per-element math / smem writes, 11 = no smem writes
+                                // epilogue: 3 = no TMA stores, 8 = no epilogue work at all, 9 = no MMA and no TMA loads
+                                // (4..7, 10, 11 existed for the per-slab epilogue of commit "GEMM epilogue: 16-byte shared-space...")
   int epi_tma;                  // 1: bf16 output staged in smem and written by TMA
   int sk;                       // 1: stream-K schedule (the (tile, k-block) space is cut evenly over the workers)
   float* sk_ws;                 // stream-K partial accumulators [worker][2 slots][CG][256 cols][128 rows] fp32
@@ -479,10 +479,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         epi_bar_sync_all(3);
         if (sk_last == 0) continue;
         load_res();
-      } else if (ns_mine == 0) {             // BN <= 64: group 1 has no slab, it only hands the accumulator back
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
+      }
+      if (ns_mine == 0) {                    // BN <= 64: group 1 has no slab, it only hands the accumulator back
+        if (!partial) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
+        }
+        if (RES) res_phase ^= 1u;
+        continue;
       }
       if (a.dbg_mode == 8) {                 // timing experiment: hand the accumulator straight back, no epilogue work
         tc_fence_before();
@@ -495,26 +500,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       if (RV) rvp = a.rowvec + (row_ok ? (m / a.hw_real) : 0) * a.ldrv;
       float ln_mu = 0.f, ln_rs = 0.f;
       if (LNF && row_ok) { const float2 st = __ldg(a.ln_stats + m); ln_mu = st.x; ln_rs = st.y; }
-      for (int i = 0; i < ns_mine; ++i) {
-        const int sl = grp + 2 * i;
-        const int w = sl < n64 ? 64 : 32;
-        const int col0 = sl * 64;
-        unsigned char* stg = gstg + i * 16384;
-        const uint32_t stg_s = s_u32(stg);
-        uint32_t v[64];
-        if (!partial) {
-          if (a.dbg_mode != 5) {
-          tmem_ld32(t_row + (uint32_t)col0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          if (w == 64) tmem_ld32(t_row + (uint32_t)col0 + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          tmem_ld_wait();
-          }
-          if (i == ns_mine - 1) {            // accumulator drained by this warp: hand it back to the MMA warp early
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
-          }
-        } else {
-          // pieces of this tile in K order: worker p's piece sits in its slot 0 when the tile is where p's range starts
+      // ---- phase 1: BOTH slabs of this group leave TMEM in one round trip, the accumulator goes back to the MMA warp ----
+      // (measured, DESIGN 4.1b: the short-K layers were bound by the per-slab chain load -> wait -> barrier -> math ->
+      // fence -> barrier -> store run twice per tile while the accumulator stayed held for ~1.5 slab times)
+      uint32_t v0[64], v1[64];
+      if (!partial) {
+        {
+          const int sl = grp, w = sl < n64 ? 64 : 32;
+          tmem_ld32(t_row + (uint32_t)(sl * 64), *reinterpret_cast<uint32_t(*)[32]>(&v0[0]));
+          if (w == 64) tmem_ld32(t_row + (uint32_t)(sl * 64) + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v0[32]));
+        }
+        if (ns_mine > 1) {
+          const int sl = grp + 2, w = sl < n64 ? 64 : 32;
+          tmem_ld32(t_row + (uint32_t)(sl * 64), *reinterpret_cast<uint32_t(*)[32]>(&v1[0]));
+          if (w == 64) tmem_ld32(t_row + (uint32_t)(sl * 64) + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v1[32]));
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
+      } else {
+        // stream-K reducer: pieces of this tile in K order (worker p's piece sits in its slot 0 when the tile is where
+        // p's range starts)
+        auto gather = [&](int i, uint32_t (&v)[64]) {
+          const int sl = grp + 2 * i, w = sl < n64 ? 64 : 32, col0 = sl * 64;
           for (int pw = w_first; pw <= w_last; ++pw) {
             const long long pb = sk_units * pw / nworkers;
             const int slot = pb >= (long long)tile * nkb ? 0 : 1;
@@ -527,15 +536,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               for (int c = 0; c < 64; ++c) if (c < w) v[c] = __float_as_uint(__uint_as_float(v[c]) + __ldcg(src + c * 128));
             }
           }
-        }
-        if (RES) {
-          mbar_wait(&rbar[i], res_phase, 500 + grp * 2 + i);
-        } else {
-          // with two slabs per tile, buffer i was last read by the store issued two slabs ago: the most recent store
-          // (other buffer) may still be in flight, so its latency overlaps this slab instead of stalling every tile
-          if (elected && a.dbg_mode != 3) { if (ns_mine == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-          if (a.dbg_mode != 7) epi_bar_sync(bar_id);
-        }
+        };
+        gather(0, v0);
+        if (ns_mine > 1) gather(1, v1);
+      }
+      // ---- phase 2: staging buffers ready (residual slabs landed / previous tile's stores have read them) ----
+      if (RES) {
+        mbar_wait(&rbar[0], res_phase, 500 + grp * 2);
+        if (ns_mine > 1) mbar_wait(&rbar[1], res_phase, 501 + grp * 2);
+      } else {
+        if (elected && a.dbg_mode != 3) tma_store_wait_read<0>();   // issued a whole tile ago: normally no wait at all
+        epi_bar_sync(bar_id);
+      }
+      // ---- phase 3: per-element epilogue of each slab into its staging buffer ----
+      auto slab_math = [&](int i, const uint32_t (&v)[64]) {
+        const int sl = grp + 2 * i;
+        const int w = sl < n64 ? 64 : 32;
+        const int col0 = sl * 64;
+        const uint32_t stg_s = s_u32(gstg + i * 16384);
         if constexpr (GEGLU) {
           // slab columns [0,32) = values, [32,64) = their gates (load-time row interleave); BN % 64 == 0 (host-checked)
 #pragma unroll
@@ -563,65 +581,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               }
             } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              f[e] = (__uint_as_float(v[g * 8 + e]) + bx[e]) * gelu_erf_fast(__uint_as_float(v[32 + g * 8 + e]) + bg[e]);
+              for (int e = 0; e < 8; ++e)
+                f[e] = (__uint_as_float(v[g * 8 + e]) + bx[e]) * gelu_erf_fast(__uint_as_float(v[32 + g * 8 + e]) + bg[e]);
             }
             const int off = r * 64 + ((g ^ ((r >> 1) & 3)) << 4);     // SWIZZLE_64B rows of the 32-column output box
             sts_bf16x8(stg_s + (uint32_t)off, pack8(f));
           }
-        } else if (a.dbg_mode != 10) {
+        } else {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (g * 8 < w) {
-            // columns past Cout exist only in a partial last N tile; TMA clips them, the clamp keeps the reads legal
-            const int n = min(n0 + col0 + g * 8, a.Cout - 8);
-            float f[8];
+          for (int g = 0; g < 8; ++g) {
+            if (g * 8 < w) {
+              // columns past Cout exist only in a partial last N tile; TMA clips them, the clamp keeps the reads legal
+              const int n = min(n0 + col0 + g * 8, a.Cout - 8);
+              float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
-            if constexpr (LNF) {
-              const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n));
-              const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n + 4));
-              const float cs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+              if constexpr (LNF) {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n + 4));
+                const float cs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = (f[e] - ln_mu * cs[e]) * ln_rs;
-            }
-            if (a.dbg_mode != 4) {
-              const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
-              const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
-              f[0] = (f[0] + q0.x) * alpha; f[1] = (f[1] + q0.y) * alpha; f[2] = (f[2] + q0.z) * alpha;
-              f[3] = (f[3] + q0.w) * alpha; f[4] = (f[4] + q1.x) * alpha; f[5] = (f[5] + q1.y) * alpha;
-              f[6] = (f[6] + q1.z) * alpha; f[7] = (f[7] + q1.w) * alpha;
-            }
-            if (RV) {
-              const float4 q0 = __ldg(reinterpret_cast<const float4*>(rvp + n));
-              const float4 q1 = __ldg(reinterpret_cast<const float4*>(rvp + n + 4));
-              f[0] += q0.x; f[1] += q0.y; f[2] += q0.z; f[3] += q0.w;
-              f[4] += q1.x; f[5] += q1.y; f[6] += q1.z; f[7] += q1.w;
-            }
-            // 16-byte chunk g of row r inside the TMA-swizzled slab (SWIZZLE_128B / SWIZZLE_64B rows)
-            const int off = w == 64 ? r * 128 + ((g ^ (r & 7)) << 4) : r * 64 + ((g ^ ((r >> 1) & 3)) << 4);
-            const uint32_t cell = stg_s + (uint32_t)off;
-            if (RES) {
-              float rf[8];
-              unpack8(lds_bf16x8(cell), rf);
+                for (int e = 0; e < 8; ++e) f[e] = (f[e] - ln_mu * cs[e]) * ln_rs;
+              }
+              {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
+                f[0] = (f[0] + q0.x) * alpha; f[1] = (f[1] + q0.y) * alpha; f[2] = (f[2] + q0.z) * alpha;
+                f[3] = (f[3] + q0.w) * alpha; f[4] = (f[4] + q1.x) * alpha; f[5] = (f[5] + q1.y) * alpha;
+                f[6] = (f[6] + q1.z) * alpha; f[7] = (f[7] + q1.w) * alpha;
+              }
+              if (RV) {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(rvp + n));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(rvp + n + 4));
+                f[0] += q0.x; f[1] += q0.y; f[2] += q0.z; f[3] += q0.w;
+                f[4] += q1.x; f[5] += q1.y; f[6] += q1.z; f[7] += q1.w;
+              }
+              // 16-byte chunk g of row r inside the TMA-swizzled slab (SWIZZLE_128B / SWIZZLE_64B rows)
+              const int off = w == 64 ? r * 128 + ((g ^ (r & 7)) << 4) : r * 64 + ((g ^ ((r >> 1) & 3)) << 4);
+              const uint32_t cell = stg_s + (uint32_t)off;
+              if (RES) {
+                float rf[8];
+                unpack8(lds_bf16x8(cell), rf);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] += rf[e];
-            }
-            if (ACT) {
+                for (int e = 0; e < 8; ++e) f[e] += rf[e];
+              }
+              if (ACT) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+                for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+              }
+              sts_bf16x8(cell, pack8(f));
             }
-            if (a.dbg_mode != 11) sts_bf16x8(cell, pack8(f)); else if (f[0] == 1.2345f) sts_bf16x8(cell, pack8(f));
           }
         }
-        }
-        if (a.dbg_mode != 6) fence_proxy_async();               // generic-proxy smem writes -> visible to the TMA engine
-        if (a.dbg_mode != 7) epi_bar_sync(bar_id);
-        if (elected && a.dbg_mode != 3) {
+      };
+      slab_math(0, v0);
+      if (ns_mine > 1) slab_math(1, v1);
+      // ---- phase 4: one fence / barrier per tile, then both stores in one bulk group ----
+      fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
+      epi_bar_sync(bar_id);
+      if (elected && a.dbg_mode != 3) {
+        for (int i = 0; i < ns_mine; ++i) {
+          const int sl = grp + 2 * i, w = sl < n64 ? 64 : 32, col0 = sl * 64;
+          unsigned char* stg = gstg + i * 16384;
           if constexpr (GEGLU) tma_store_4d(&map_o32, stg, (n0 + col0) >> 1, x0, y0, b0);
           else tma_store_4d(w == 64 ? &map_o64 : &map_o32, stg, n0 + col0, x0, y0, b0);
-          tma_store_commit();
         }
+        tma_store_commit();
       }
       if (RES) res_phase ^= 1u;
       if (ew == 0 && lane == 0) PD_DBG(2, it, 1);
