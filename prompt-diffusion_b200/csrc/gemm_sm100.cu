@@ -500,55 +500,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       if (RV) rvp = a.rowvec + (row_ok ? (m / a.hw_real) : 0) * a.ldrv;
       float ln_mu = 0.f, ln_rs = 0.f;
       if (LNF && row_ok) { const float2 st = __ldg(a.ln_stats + m); ln_mu = st.x; ln_rs = st.y; }
-      // ---- phase 1: BOTH slabs of this group leave TMEM in one round trip, the accumulator goes back to the MMA warp ----
-      // (measured, DESIGN 4.1b: the short-K layers were bound by the per-slab chain load -> wait -> barrier -> math ->
-      // fence -> barrier -> store run twice per tile while the accumulator stayed held for ~1.5 slab times)
       uint32_t v0[64], v1[64];
-      if (!partial) {
-        {
-          const int sl = grp, w = sl < n64 ? 64 : 32;
-          tmem_ld32(t_row + (uint32_t)(sl * 64), *reinterpret_cast<uint32_t(*)[32]>(&v0[0]));
-          if (w == 64) tmem_ld32(t_row + (uint32_t)(sl * 64) + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v0[32]));
+      // stream-K reducer: pieces of this tile in K order (worker p's piece sits in its slot 0 when the tile is where
+      // p's range starts)
+      auto gather = [&](int i, uint32_t (&v)[64]) {
+        const int sl = grp + 2 * i, w = sl < n64 ? 64 : 32, col0 = sl * 64;
+        for (int pw = w_first; pw <= w_last; ++pw) {
+          const long long pb = sk_units * pw / nworkers;
+          const int slot = pb >= (long long)tile * nkb ? 0 : 1;
+          const float* src = a.sk_ws + ((size_t)(pw * 2 + slot) * CG + cta_rank) * SK_SLOT_FLOATS + (size_t)col0 * 128 + r;
+          if (pw == w_first) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) if (c < w) v[c] = __float_as_uint(__ldcg(src + c * 128));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) if (c < w) v[c] = __float_as_uint(__uint_as_float(v[c]) + __ldcg(src + c * 128));
+          }
         }
-        if (ns_mine > 1) {
-          const int sl = grp + 2, w = sl < n64 ? 64 : 32;
-          tmem_ld32(t_row + (uint32_t)(sl * 64), *reinterpret_cast<uint32_t(*)[32]>(&v1[0]));
-          if (w == 64) tmem_ld32(t_row + (uint32_t)(sl * 64) + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v1[32]));
-        }
-        tmem_ld_wait();
+      };
+      auto ld_slab = [&](int i, uint32_t (&v)[64]) {
+        const int sl = grp + 2 * i, w = sl < n64 ? 64 : 32;
+        tmem_ld32(t_row + (uint32_t)(sl * 64), *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        if (w == 64) tmem_ld32(t_row + (uint32_t)(sl * 64) + 32u, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      };
+      auto arrive_empty = [&]() {            // accumulator drained by this warp: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
-      } else {
-        // stream-K reducer: pieces of this tile in K order (worker p's piece sits in its slot 0 when the tile is where
-        // p's range starts)
-        auto gather = [&](int i, uint32_t (&v)[64]) {
-          const int sl = grp + 2 * i, w = sl < n64 ? 64 : 32, col0 = sl * 64;
-          for (int pw = w_first; pw <= w_last; ++pw) {
-            const long long pb = sk_units * pw / nworkers;
-            const int slot = pb >= (long long)tile * nkb ? 0 : 1;
-            const float* src = a.sk_ws + ((size_t)(pw * 2 + slot) * CG + cta_rank) * SK_SLOT_FLOATS + (size_t)col0 * 128 + r;
-            if (pw == w_first) {
-#pragma unroll
-              for (int c = 0; c < 64; ++c) if (c < w) v[c] = __float_as_uint(__ldcg(src + c * 128));
-            } else {
-#pragma unroll
-              for (int c = 0; c < 64; ++c) if (c < w) v[c] = __float_as_uint(__uint_as_float(v[c]) + __ldcg(src + c * 128));
-            }
-          }
-        };
-        gather(0, v0);
-        if (ns_mine > 1) gather(1, v1);
-      }
-      // ---- phase 2: staging buffers ready (residual slabs landed / previous tile's stores have read them) ----
-      if (RES) {
-        mbar_wait(&rbar[0], res_phase, 500 + grp * 2);
-        if (ns_mine > 1) mbar_wait(&rbar[1], res_phase, 501 + grp * 2);
-      } else {
-        if (elected && a.dbg_mode != 3) tma_store_wait_read<0>();   // issued a whole tile ago: normally no wait at all
-        epi_bar_sync(bar_id);
-      }
-      // ---- phase 3: per-element epilogue of each slab into its staging buffer ----
+      };
+      auto store_slab = [&](int i) {
+        const int sl = grp + 2 * i, w = sl < n64 ? 64 : 32, col0 = sl * 64;
+        unsigned char* stg = gstg + i * 16384;
+        if constexpr (GEGLU) tma_store_4d(&map_o32, stg, (n0 + col0) >> 1, x0, y0, b0);
+        else tma_store_4d(w == 64 ? &map_o64 : &map_o32, stg, n0 + col0, x0, y0, b0);
+      };
+      // per-element epilogue of one slab into its staging buffer
       auto slab_math = [&](int i, const uint32_t (&v)[64]) {
         const int sl = grp + 2 * i;
         const int w = sl < n64 ? 64 : 32;
@@ -634,19 +620,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
       };
-      slab_math(0, v0);
-      if (ns_mine > 1) slab_math(1, v1);
-      // ---- phase 4: one fence / barrier per tile, then both stores in one bulk group ----
-      fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
-      epi_bar_sync(bar_id);
-      if (elected && a.dbg_mode != 3) {
+      if constexpr (GEGLU) {
+        // GEGLU epilogues are bound by their own math (erf: two SFU ops and ~20 FP ops per output), not by the latency
+        // chain: one slab at a time keeps the two warp groups staggered against each other (both slabs at once measured
+        // 164 -> 224 us at 65536 x 2560 x 320)
         for (int i = 0; i < ns_mine; ++i) {
-          const int sl = grp + 2 * i, w = sl < n64 ? 64 : 32, col0 = sl * 64;
-          unsigned char* stg = gstg + i * 16384;
-          if constexpr (GEGLU) tma_store_4d(&map_o32, stg, (n0 + col0) >> 1, x0, y0, b0);
-          else tma_store_4d(w == 64 ? &map_o64 : &map_o32, stg, n0 + col0, x0, y0, b0);
+          if (!partial) {
+            ld_slab(i, v0);
+            tmem_ld_wait();
+            if (i == ns_mine - 1) arrive_empty();
+          } else {
+            gather(i, v0);
+          }
+          if (RES) {
+            mbar_wait(&rbar[i], res_phase, 500 + grp * 2 + i);
+          } else {
+            // buffer i was last read by the store issued two slabs ago: the most recent store may still be in flight
+            if (elected && a.dbg_mode != 3) { if (ns_mine == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+            epi_bar_sync(bar_id);
+          }
+          slab_math(i, v0);
+          fence_proxy_async();               // generic-proxy smem writes -> visible to the TMA engine
+          epi_bar_sync(bar_id);
+          if (elected && a.dbg_mode != 3) { store_slab(i); tma_store_commit(); }
         }
-        tma_store_commit();
+      } else {
+        // ---- BOTH slabs of this group leave TMEM in one round trip, the accumulator goes back to the MMA warp ----
+        // (measured, DESIGN 4.1b: the short-K layers were bound by the per-slab chain load -> wait -> barrier -> math ->
+        // fence -> barrier -> store run twice per tile while the accumulator stayed held for ~1.5 slab times)
+        if (!partial) {
+          ld_slab(0, v0);
+          if (ns_mine > 1) ld_slab(1, v1);
+          tmem_ld_wait();
+          arrive_empty();
+        } else {
+          gather(0, v0);
+          if (ns_mine > 1) gather(1, v1);
+        }
+        // staging buffers ready (residual slabs landed / the previous tile's stores have read them)
+        if (RES) {
+          mbar_wait(&rbar[0], res_phase, 500 + grp * 2);
+          if (ns_mine > 1) mbar_wait(&rbar[1], res_phase, 501 + grp * 2);
+        } else {
+          if (elected && a.dbg_mode != 3) tma_store_wait_read<0>();   // issued a whole tile ago: normally no wait at all
+          epi_bar_sync(bar_id);
+        }
+        slab_math(0, v0);
+        if (ns_mine > 1) slab_math(1, v1);
+        // one fence / barrier per tile, then both stores in one bulk group
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
+        epi_bar_sync(bar_id);
+        if (elected && a.dbg_mode != 3) {
+          for (int i = 0; i < ns_mine; ++i) store_slab(i);
+          tma_store_commit();
+        }
       }
       if (RES) res_phase ^= 1u;
       if (ew == 0 && lane == 0) PD_DBG(2, it, 1);
