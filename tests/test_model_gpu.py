@@ -224,6 +224,55 @@ def test_apply_model_config2_shape_vs_oracle_gpu(models, cfg, state_dict_cpu):
         assert err <= TOL[mode], (mode, err)
 
 
+def test_apply_model_config4_shape_vs_oracle_gpu(models, cfg, state_dict_cpu):
+    """A slice of BASELINE config 4 (768^2 -> 96x96 latent, 9216-token self-attention: the attention-bound stress
+    case), batch 1 (B_eff 2), bf16 mode: CUDA path vs the oracle run in fp32 on this GPU."""
+    from oracle import cldm_oracle as O
+    sd_gpu = {k: v.to(DEV) for k, v in state_dict_cpu.items()}
+    _, _, _, x_in, c_in = _cfg_inputs(cfg, 1, 768, 768)
+    t = torch.tensor([261, 261], dtype=torch.long, device=DEV)
+    ref = O.apply_model(sd_gpu, cfg, x_in, t, c_in)
+    del sd_gpu
+    eps = models["bf16"].apply_model(x_in, t, c_in)
+    err = rel_l2(eps, ref)
+    print(f"[parity] apply_model 768^2 bf16 vs oracle(gpu fp32): eps rel-L2 = {err:.3e}")
+    assert eps.shape == (2, 4, 96, 96) and err <= TOL["bf16"], err
+
+
+def test_full_size_batch_properties(models, cfg):
+    """Size-independent properties at BASELINE config 2's FULL size (B_eff 16, 64x64 latent, 512^2 hints):
+    (1) samples are independent — permuting the batch permutes eps; (2) [uncond, cond] halves with IDENTICAL
+    conditioning give identical eps, so classifier-free guidance at any scale returns it; (3) determinism: a second
+    call reproduces the first bit for bit.  fp32 mode: (1) and (2) hold BIT FOR BIT (no kernel mixes rows of different
+    images).  bf16 mode: (3) is exact, (1) / (2) hold to the bf16 noise floor only — a moved row lands in another tile,
+    the stream-K schedule sums it in a different fp32 order, a few bf16 roundings flip, and 60 layers later the
+    rounding noise of the two runs is decorrelated (scripts/perm_probe.py: a 1e-6 relative input perturbation moves
+    the bf16 eps by 6e-3 .. 8e-3, the fp32 eps by 3e-6) — i.e. the ~9e-3 distance to the fp32 reference IS that noise."""
+    _, _, _, x_in, c_in = _cfg_inputs(cfg, 8, 512, 512)
+    B = x_in.shape[0]
+    assert B == 16
+    g = torch.Generator(device="cpu").manual_seed(12)
+    x = torch.randn(x_in.shape, generator=g).to(DEV)
+    t = torch.full((B,), 421, dtype=torch.long, device=DEV)
+    perm = torch.randperm(B, generator=g).to(DEV)
+    c_perm = {k: [v[0][perm].contiguous()] for k, v in c_in.items()}
+    half = B // 2
+    x2 = torch.cat([x[:half], x[:half]])
+    c2 = {k: [torch.cat([v[0][:half], v[0][:half]])] for k, v in c_in.items()}
+    for mode in ("fp32", "bf16"):
+        m = models[mode]
+        eps = m.apply_model(x, t, c_in)
+        assert bool(torch.isfinite(eps).all())
+        assert torch.equal(eps, m.apply_model(x, t, c_in))                               # (3)
+        eps_p = m.apply_model(x[perm].contiguous(), t, c_perm)
+        e2 = m.apply_model(x2, t, c2)
+        e1, e2r = rel_l2(eps_p, eps[perm]), rel_l2(e2[:half], e2[half:])
+        print(f"[property] full-size {mode}: batch permutation rel-L2 = {e1:.3e}; identical CFG halves rel-L2 = {e2r:.3e}")
+        if mode == "fp32":
+            assert torch.equal(eps_p, eps[perm]) and torch.equal(e2[:half], e2[half:])   # (1), (2) bit for bit
+        else:
+            assert e1 <= 1e-2 and e2r <= 1e-2
+
 def test_create_model_and_full_checkpoint_dict(models, cfg, state_dict_cpu):
     """Notebook set-up lines (cldm/model.py:8-28): create_model(yaml) + load_state_dict(get_state_dict(ckpt)) must give
     the same eps as the fixture's model, with the Lightning envelope and foreign entries (VAE / CLIP / EMA) present.
