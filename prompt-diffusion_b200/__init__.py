@@ -15,6 +15,9 @@ def __getattr__(name):
     if name in ("ControlLDM", "ControlNet", "ControlledUnetModel", "DDIMSampler"):
         from . import cldm as _cldm
         return getattr(_cldm, name)
+    if name in ("PromptDiffusionPipeline", "DDIMScheduler", "UNet2DConditionShim"):
+        from . import pipeline_prompt_diffusion as _ppd
+        return getattr(_ppd, name)
     if name == "FrozenCLIPTextEncoder":
         from .clip_text import FrozenCLIPTextEncoder
         return FrozenCLIPTextEncoder

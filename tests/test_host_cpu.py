@@ -195,3 +195,33 @@ def test_create_model_refuses_cpu():
     from prompt_diffusion_b200.cldm.model import create_model
     with pytest.raises(RuntimeError):
         create_model(os.path.join(REPO, "tests", "golden", "cldm_v15_topology.yaml"), device="cpu")
+
+
+def test_ddim_scheduler_restatement_matches_reference_schedule(golden):
+    """The restated diffusers DDIMScheduler (SD1.5 config) must walk the reference's own DDIM schedule
+    (cldm/ddim_hacked.py make_schedule, golden sched_S*_eta*): timesteps 981 ... 1, alpha_t, alpha_prev (alpha_cumprod[0]
+    after the last step), sigma — and its step() must equal ddim_hacked.py:218-233 on random tensors."""
+    from prompt_diffusion_b200.pipeline_prompt_diffusion import DDIMScheduler
+    for S, eta in ((20, 0.0), (50, 0.0), (50, 0.5)):
+        tag = f"sched_S{S}_eta{eta}"
+        sch = DDIMScheduler()
+        sch.set_timesteps(S)
+        ts = sch.timesteps.numpy()
+        assert np.array_equal(ts[::-1], golden[tag + "_timesteps"])
+        g = torch.Generator().manual_seed(S)
+        x, e = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+        for i, t in enumerate(ts):
+            index = S - 1 - i
+            a_t, a_prev = float(golden[tag + "_alphas"][index]), float(golden[tag + "_alphas_prev"][index])
+            sigma, s1m = float(golden[tag + "_sigmas"][index]), float(golden[tag + "_sqrt_one_minus"][index])
+            assert abs(float(sch.alphas_cumprod[t]) - a_t) <= 2e-6 * a_t      # diffusers builds the betas in fp32, ldm in fp64
+            pred_x0 = (x - s1m * e) / a_t ** 0.5
+            ref = a_prev ** 0.5 * pred_x0 + (1.0 - a_prev - sigma ** 2) ** 0.5 * e          # noise term checked via sigma below
+            got = sch.step(e, int(t), x, eta=0.0)[0] if eta == 0.0 else None
+            if got is not None:
+                assert float((got - ref).abs().max()) <= 5e-5 * float(ref.abs().max())
+            else:
+                prev_t = int(t) - 1000 // S
+                ap = float(sch.alphas_cumprod[prev_t]) if prev_t >= 0 else float(sch.final_alpha_cumprod)
+                var = (1 - ap) / (1 - a_t) * (1 - a_t / ap)
+                assert abs(eta * var ** 0.5 - sigma) <= 1e-5 * max(sigma, 1e-6) + 1e-9 and abs(ap - a_prev) <= 2e-6 * a_prev
