@@ -63,9 +63,22 @@ int pd_prof_enable(int on);
 int pd_prof_read(double* total_ms, double* total_flops, uint64_t* launches);
 /* one CSV line per recorded launch (shape, tile choice, milliseconds, TFLOP/s) */
 int pd_prof_dump(const char* path_host);
-/* debugging aid: device buffer of 3*64*2 uint64 that receives CTA 0's per-role (TMA / MMA / epilogue) tile
- * start/end globaltimer stamps of subsequent tcgen05 launches; NULL switches it off */
+#ifdef PD_DEBUG
+/* PD_DEBUG builds only (scripts/build_variant.sh; never the shipped library): device buffer of 3*64*2 uint64 that
+ * receives CTA 0's per-role (TMA / MMA / epilogue) tile start/end globaltimer stamps; NULL switches it off */
 int pd_debug_timeline(void* dev_buf);
+/* PD_DEBUG builds only: timing experiments on the conv engine (results are WRONG when non-zero):
+ * 1 = issue no MMAs, 2 = issue no TMA loads, 3 = no TMA stores, 8 = no epilogue, 9 = 1 + 2 */
+int pd_debug_gemm_mode(int32_t mode);
+#endif
+/* tile order of the tcgen05 conv engine: 1 (default) = the N tiles of one M tile are adjacent in the schedule,
+ * 0 = all M tiles of one N tile first */
+int pd_debug_tile_order(int32_t n_fast);
+/* Launch variants (single-CTA / CTA-pair tiles, stream-K, tile width) are chosen per layer shape from a committed
+ * table (csrc/tune_table.inc), so results never depend on timing noise; PD_B200_AUTOTUNE=1 times the candidates of
+ * shapes missing from the table on first use (table regeneration only).  pd_tune_dump writes the table rows
+ * currently in effect (committed + tuned) in tune_table.inc syntax. */
+int pd_tune_dump(const char* path_host);
 /* tile-shape override of the tcgen05 conv engine: 0 auto, 1 single-CTA 128-row tiles, 2 CTA-pair 256-row tiles */
 int pd_debug_force_cta_group(int32_t cg);
 /* experiments: pin the N extent of the tile (multiple of 32 up to 256; 0 = heuristic) */
@@ -73,8 +86,6 @@ int pd_debug_force_bn(int32_t bn);
 /* together with a forced CTA group: 1 = stream-K schedule of the tcgen05 conv engine wherever it applies (the (tile, k-block)
  * space is cut evenly over the CTAs; partial tiles are summed in K order by the last CTA to arrive), 0 = data-parallel */
 int pd_debug_force_stream_k(int32_t on);
-/* timing experiments on the conv engine (results are WRONG when non-zero): 1 = issue no MMAs, 2 = issue no TMA loads */
-int pd_debug_gemm_mode(int32_t mode);
 /* 1 (default): GroupNorm is one cooperative launch; 0: statistics kernel + apply kernel */
 int pd_debug_group_norm_fused(int32_t on);
 /* same for the tcgen05 attention kernel: 6 phases x 32 tiles of uint64 stamps from block (0,0,0) */

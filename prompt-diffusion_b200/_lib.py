@@ -44,12 +44,12 @@ SIGNATURES = {
     "pd_prof_enable": (C.c_int, [C.c_int]),
     "pd_prof_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "pd_prof_dump": (C.c_int, [C.c_char_p]),
-    "pd_debug_timeline": (C.c_int, [C.c_void_p]),
+    "pd_debug_tile_order": (C.c_int, [C.c_int32]),
+    "pd_tune_dump": (C.c_int, [C.c_char_p]),
     "pd_debug_force_cta_group": (C.c_int, [C.c_int32]),
     "pd_debug_force_bn": (C.c_int, [C.c_int32]),
     "pd_debug_force_stream_k": (C.c_int, [C.c_int32]),
     "pd_layer_norm_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
-    "pd_debug_gemm_mode": (C.c_int, [C.c_int32]),
     "pd_debug_group_norm_fused": (C.c_int, [C.c_int32]),
     "pd_debug_attention_timeline": (C.c_int, [C.c_void_p]),
     "pd_conv2d": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
@@ -92,6 +92,13 @@ SIGNATURES = {
 }
 
 
+# exported by PD_DEBUG builds only (scripts/build_variant.sh, selected with PD_B200_LIB); bound when present
+DEBUG_SIGNATURES = {
+    "pd_debug_timeline": (C.c_int, [C.c_void_p]),
+    "pd_debug_gemm_mode": (C.c_int, [C.c_int32]),
+}
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -102,6 +109,11 @@ def _load():
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in DEBUG_SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype = res
+            fn.argtypes = args
     return lib
 
 

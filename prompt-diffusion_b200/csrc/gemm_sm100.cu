@@ -17,8 +17,12 @@
 //   zero-conv add / skip / guided hint) -> optional SiLU -> bf16 (or fp32) 16-byte stores
 //   with an arbitrary row pitch (writes land directly in channel-concat slots).
 #include <cstdlib>
+#include <cstring>
 #include <map>
+#include <mutex>
+#include <string>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include "tc_ptx.cuh"
@@ -53,6 +57,7 @@ struct TcArgs {
                                 // epilogue: 3 = no TMA stores, 8 = no epilogue work at all, 9 = no MMA and no TMA loads
                                 // (4..7, 10, 11 existed for the per-slab epilogue of commit "GEMM epilogue: 16-byte shared-space...")
   int epi_tma;                  // 1: bf16 output staged in smem and written by TMA
+  int n_fast;                   // tile order, see PD_TILE_COORDS
   int sk;                       // 1: stream-K schedule (the (tile, k-block) space is cut evenly over the workers)
   float* sk_ws;                 // stream-K partial accumulators [worker][2 slots][CG][256 cols][128 rows] fp32
   int* sk_cnt;                  // stream-K arrival counters [tile][CG], zero between launches (the reducer resets its own)
@@ -99,10 +104,27 @@ struct PieceIter {
   }
 };
 
+// Timeline stamps and the "switch a pipeline stage off" timing modes exist only in the PD_DEBUG build
+// (scripts/build_variant.sh -> libpd_b200_dbg.so); the shipped kernels carry none of these branches.
+#ifdef PD_DEBUG
 #define PD_DBG(role, tileidx, which)                                                        \
   do {                                                                                      \
     if (a.dbg != nullptr && blockIdx.x == 0 && (tileidx) < 64)                              \
       a.dbg[((role) * 64 + (tileidx)) * 2 + (which)] = gtimer();                            \
+  } while (0)
+#define PD_MODE_IS(m) (a.dbg_mode == (m))
+#else
+#define PD_DBG(role, tileidx, which) do { } while (0)
+#define PD_MODE_IS(m) false
+#endif
+
+// tile index -> (N tile, M (pair) tile).  n_fast: the N tiles of one M tile are adjacent in the schedule, so the CTAs
+// that share an A tile run at the same time (its second .. n-th read is an L2 hit / de-duplicated request);
+// otherwise all M tiles of one N tile come first (a CTA keeps its weight tile across consecutive tiles).
+#define PD_TILE_COORDS(tile_, nt_, pmt_)                                     \
+  do {                                                                       \
+    if (a.n_fast) { pmt_ = (tile_) / a.n_tiles; nt_ = (tile_) - pmt_ * a.n_tiles; } \
+    else { nt_ = (tile_) / pm_tiles; pmt_ = (tile_) - nt_ * pm_tiles; }      \
   } while (0)
 
 // ---- the kernel ---------------------------------------------------------------------------------
@@ -178,7 +200,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       PieceIter pit(SK, worker, nworkers, num_tiles, nkb);
       int tile, kb0, kb1, tix = 0;
       for (; pit.next(tile, kb0, kb1); ++tix) {
-        const int nt = tile / pm_tiles, mt = (tile - nt * pm_tiles) * CG + (int)cta_rank;
+        int nt, pmt;
+        PD_TILE_COORDS(tile, nt, pmt);
+        const int mt = pmt * CG + (int)cta_rank;
         const int txi = mt % a.tiles_x;
         const int tyi = (mt / a.tiles_x) % a.tiles_y;
         const int tbi = mt / (a.tiles_x * a.tiles_y);   // >= tiles_b for the phantom half of an odd last pair: TMA zero-fills
@@ -197,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (kb == kb1 - 1 && lane == 0) PD_DBG(0, tix, 1);
           unsigned char* sa = smem + stage * stage_bytes;
           unsigned char* sb = sa + TC_A_BYTES;
-          if (a.dbg_mode == 2 || a.dbg_mode == 9) {
+          if (PD_MODE_IS(2) || PD_MODE_IS(9)) {
             if (cta_rank == 0 && elect_one()) mbar_arrive(&full_bar[stage]);
             __syncwarp();
             if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -254,7 +278,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
-              if (a.dbg_mode == 1 || a.dbg_mode == 9) break;
+              if (PD_MODE_IS(1) || PD_MODE_IS(9)) break;
               // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the >>4 field
               const uint32_t accum = ((kb - kb0) | k) != 0 ? 1u : 0u;
               if (CG == 2) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, accum);
@@ -284,7 +308,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int nt = tile / pm_tiles, mt = (tile - nt * pm_tiles) * CG + (int)cta_rank;
+      int nt, pmt;
+      PD_TILE_COORDS(tile, nt, pmt);
+      const int mt = pmt * CG + (int)cta_rank;
       const int txi = mt % a.tiles_x;
       const int tyi = (mt / a.tiles_x) % a.tiles_y;
       const int tbi = mt / (a.tiles_x * a.tiles_y);
@@ -399,7 +425,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     for (; pit.next(tile, kb0, kb1); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-      const int nt = tile / pm_tiles, mt = (tile - nt * pm_tiles) * CG + (int)cta_rank;
+      int nt, pmt;
+      PD_TILE_COORDS(tile, nt, pmt);
+      const int mt = pmt * CG + (int)cta_rank;
       const int txi = mt % a.tiles_x;
       const int tyi = (mt / a.tiles_x) % a.tiles_y;
       const int tbi = mt / (a.tiles_x * a.tiles_y);
@@ -424,7 +452,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
             const int ntile = pit.peek_tile();
             if (ntile >= 0) {
-              const int nnt = ntile / pm_tiles, nmt = (ntile - nnt * pm_tiles) * CG + (int)cta_rank;
+              int nnt, npmt;
+              PD_TILE_COORDS(ntile, nnt, npmt);
+              const int nmt = npmt * CG + (int)cta_rank;
               const int nx0 = (nmt % a.tiles_x) * a.bw, ny0 = ((nmt / a.tiles_x) % a.tiles_y) * a.bh;
               const int nb0 = (nmt / (a.tiles_x * a.tiles_y)) * a.bn;
               for (int i = 0; i < ns_mine; ++i) {
@@ -489,7 +519,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (RES) res_phase ^= 1u;
         continue;
       }
-      if (a.dbg_mode == 8) {                 // timing experiment: hand the accumulator straight back, no epilogue work
+      if (PD_MODE_IS(8)) {                 // timing experiment: hand the accumulator straight back, no epilogue work
         tc_fence_before();
         __syncwarp();
         if (lane == 0 && ns_mine != 0 && !partial) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
@@ -636,13 +666,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             mbar_wait(&rbar[i], res_phase, 500 + grp * 2 + i);
           } else {
             // buffer i was last read by the store issued two slabs ago: the most recent store may still be in flight
-            if (elected && a.dbg_mode != 3) { if (ns_mine == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+            if (elected && !PD_MODE_IS(3)) { if (ns_mine == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
             epi_bar_sync(bar_id);
           }
           slab_math(i, v0);
           fence_proxy_async();               // generic-proxy smem writes -> visible to the TMA engine
           epi_bar_sync(bar_id);
-          if (elected && a.dbg_mode != 3) { store_slab(i); tma_store_commit(); }
+          if (elected && !PD_MODE_IS(3)) { store_slab(i); tma_store_commit(); }
         }
       } else {
         // ---- BOTH slabs of this group leave TMEM in one round trip, the accumulator goes back to the MMA warp ----
@@ -662,7 +692,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           mbar_wait(&rbar[0], res_phase, 500 + grp * 2);
           if (ns_mine > 1) mbar_wait(&rbar[1], res_phase, 501 + grp * 2);
         } else {
-          if (elected && a.dbg_mode != 3) tma_store_wait_read<0>();   // issued a whole tile ago: normally no wait at all
+          if (elected && !PD_MODE_IS(3)) tma_store_wait_read<0>();   // issued a whole tile ago: normally no wait at all
           epi_bar_sync(bar_id);
         }
         slab_math(0, v0);
@@ -670,7 +700,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         // one fence / barrier per tile, then both stores in one bulk group
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
         epi_bar_sync(bar_id);
-        if (elected && a.dbg_mode != 3) {
+        if (elected && !PD_MODE_IS(3)) {
           for (int i = 0; i < ns_mine; ++i) store_slab(i);
           tma_store_commit();
         }
@@ -695,12 +725,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 // captured graph): every launch is bracketed by two events on ITS stream and logged with its
 // algorithmic FLOPs (2*M*Cout*K of the layer, padding excluded).
 struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, ksize, stride, BN, m_tiles, n_tiles, stages, grid, cg, sk; };
+// Process-wide host state of the engine.  g_mu guards the containers (profile log, tune cache, tensor-map cache);
+// the plain ints are experiment switches set before any launch.
+static std::mutex g_mu;
 static bool g_prof_on = false;
+#ifdef PD_DEBUG
 static int g_dbg_mode = 0;
+static unsigned long long* g_dbg = nullptr;
+#endif
 static int g_force_bn = 0;   // experiments: pin the N extent of the tile (multiple of 32, <= 256)
 static int g_force_cg = 0;   // 0 auto, 1 single-CTA tiles only, 2 CTA pairs whenever the epilogue allows (tests / A-B timing)
-static unsigned long long* g_dbg = nullptr;
+static int g_n_fast = -1;    // tile order (PD_TILE_COORDS): -1 = read PD_B200_NFAST once (default 1)
 static std::vector<ProfRec> g_prof;
+constexpr int PD_MAX_DEVICES = 16;
+static inline int cur_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PD_MAX_DEVICES) { cudaGetLastError(); return -1; }
+  return dev;
+}
+// SM count of the CURRENT device (common.cuh's num_sms() caches the first device it saw)
+static inline int dev_sms(int dev) {
+  static int n[PD_MAX_DEVICES] = {0};
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 148; }
+    n[dev] = v;
+  }
+  return n[dev];
+}
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
@@ -715,8 +767,39 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are pure functions of (base, geometry, box, swizzle): the pool buffers of the model have static
+// addresses, so every launch after the first finds its 3..7 maps here instead of re-encoding them on the host
+// (the eager path, the diffusers loop and the callback path pay that on every step; graph replay never did).
+struct MapKey {
+  uint64_t v[14];
+  bool operator==(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 14; ++i) { h ^= k.v[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+struct MapVal { CUtensorMap m; };
+static std::unordered_map<MapKey, MapVal, MapKeyHash> g_maps;
+
 int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box, const uint32_t* estrides, const char* what, CUtensorMapSwizzle swz) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.v[0] = (uint64_t)(uintptr_t)base;
+  key.v[1] = (uint64_t)rank | ((uint64_t)swz << 8) | ((uint64_t)(cur_device() & 0xff) << 16);
+  for (int i = 0; i < rank; ++i) {
+    key.v[2 + i] = dims[i];
+    if (i < rank - 1) key.v[6 + i] = strides_bytes[i];
+    key.v[10 + i] = (uint64_t)box[i] | ((uint64_t)estrides[i] << 32);
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *map = it->second.m; return 0; }
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_error("conv_tc: cuTensorMapEncodeTiled entry point unavailable"); return PD_ERR_NO_DEVICE; }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
@@ -729,6 +812,12 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dim
               (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1],
               rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
     return PD_ERR_BAD_ARG;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_maps.size() > 16384) g_maps.clear();     // bounded: callers with ever-changing addresses just re-encode
+    MapVal mv; mv.m = *map;
+    g_maps.emplace(key, mv);
   }
   return 0;
 }
@@ -785,7 +874,7 @@ static int sk_scratch(float** ws, int** cnt) {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) { set_error("conv_tc: bad device for stream-K scratch"); return PD_ERR_NO_DEVICE; }
   if (g_ws[dev] == nullptr) {
     float* w = nullptr; int* c = nullptr;
-    const size_t wbytes = (size_t)num_sms() * 2 * SK_SLOT_FLOATS * sizeof(float);
+    const size_t wbytes = (size_t)dev_sms(dev) * 2 * SK_SLOT_FLOATS * sizeof(float);
     if (cudaMalloc(&w, wbytes) != cudaSuccess || cudaMalloc(&c, (size_t)SK_MAX_TILES * 2 * sizeof(int)) != cudaSuccess ||
         cudaMemset(c, 0, (size_t)SK_MAX_TILES * 2 * sizeof(int)) != cudaSuccess) {
       cudaGetLastError();
@@ -806,8 +895,20 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
   a.bias = p->bias; a.rowvec = p->rowvec; a.res = p->res; a.out = p->out;
   a.ldr = p->ldr; a.ldo = p->ldo; a.ldrv = p->ldrv; a.act = p->act; a.out_f32 = p->out_dtype == PD_F32;
   a.alpha = p->alpha;
+#ifdef PD_DEBUG
   a.dbg = g_dbg;
   a.dbg_mode = g_dbg_mode;
+#else
+  a.dbg = nullptr;
+  a.dbg_mode = 0;
+#endif
+  if (g_n_fast < 0) {
+    const char* e = getenv("PD_B200_NFAST");
+    g_n_fast = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  a.n_fast = g_n_fast;
+  const int dev = cur_device();
+  if (dev < 0) { set_error("conv_tc: no current CUDA device (or device index >= %d)", PD_MAX_DEVICES); return PD_ERR_NO_DEVICE; }
   a.ln_stats = reinterpret_cast<const float2*>(p->ln_stats); a.ln_colsum = p->ln_colsum;
   a.ksize = p->ksize; a.stride = p->stride; a.C = p->C; a.C2 = p->C2; a.Cout = p->Cout;
   a.cpt0 = p->C / TC_BK;
@@ -837,7 +938,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
   // Per 64-deep k-block a CTA issues 4 MMAs (2*BN tensor cycles) and pulls 128 x (128 + BN/CG) bytes through L2;
   // at ~39 B/clk/SM of L2 bandwidth (measured: 10.9 TB/s over 148 SMs) the second term dominates, which is why
   // the pair (half the B traffic per CTA) wins whenever there are enough tiles to fill the machine.
-  const int sms = num_sms();
+  const int sms = dev_sms(dev);
   a.epi_tma = p->out_dtype == PD_BF16 ? 1 : 0;
   int best_bn = 64, best_cg = 1; double best_cost = 1e30;
   const int cg_max = (a.epi_tma && force_cg != 1) ? 2 : 1;
@@ -934,8 +1035,9 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
    conv_tc_kernel<10, CGv_, SKv_>, conv_tc_kernel<11, CGv_, SKv_>}
   static KernelFn kernels[2][2][12] = {{PD_TC_ROW(1, 0), PD_TC_ROW(2, 0)}, {PD_TC_ROW(1, 1), PD_TC_ROW(2, 1)}};
 #undef PD_TC_ROW
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[PD_MAX_DEVICES] = {false};    // function attributes are per device (context)
+  std::unique_lock<std::mutex> init_lk(g_mu);
+  if (!attr_set[dev]) {
     kernels[0][0][8] = conv_tc_kernel<8, 1, 0>;      // fp32 output: legacy epilogue, single CTA, data-parallel only
     for (int k = 0; k < 2; ++k)
       for (int c = 0; c < 2; ++c)
@@ -944,22 +1046,23 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
           cudaError_t e = cudaFuncSetAttribute(kernels[k][c][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
           if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         }
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int epi = !a.epi_tma ? 8 : p->ln_stats != nullptr ? (p->act == PD_ACT_GEGLU ? 11 : 10) : p->act == PD_ACT_GEGLU ? 9
                   : ((p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0));
-  static const float* zero_bias = nullptr;   // the TMA epilogue always adds a bias vector
+  static const float* zero_bias[PD_MAX_DEVICES] = {nullptr};   // the TMA epilogue always adds a bias vector
   if (a.epi_tma && a.bias == nullptr) {
-    if (zero_bias == nullptr) {
+    if (zero_bias[dev] == nullptr) {
       float* zb = nullptr;
-      if (cudaMalloc(&zb, 16384 * sizeof(float)) != cudaSuccess || cudaMemset(zb, 0, 16384 * sizeof(float)) != cudaSuccess) {
+      if (cudaMalloc(&zb, 32768 * sizeof(float)) != cudaSuccess || cudaMemset(zb, 0, 32768 * sizeof(float)) != cudaSuccess) {
         set_error("conv_tc: cannot allocate the zero bias"); return PD_ERR_NO_DEVICE;
       }
-      zero_bias = zb;
+      zero_bias[dev] = zb;
     }
-    if (p->Cout > 16384) { set_error("conv_tc: bias-less launch with Cout > 16384"); return PD_ERR_UNSUPPORTED; }
-    a.bias = zero_bias;
+    if (p->Cout > 32768) { set_error("conv_tc: bias-less launch with Cout > 32768"); return PD_ERR_UNSUPPORTED; }
+    a.bias = zero_bias[dev];
   }
+  init_lk.unlock();
   int64_t tiles = (int64_t)((a.m_tiles + CGv - 1) / CGv) * a.n_tiles;
   const int64_t workers = sms / CGv;
   int grid = (int)(tiles < workers ? tiles : workers) * CGv;
@@ -992,43 +1095,73 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
   }
   if (g_prof_on) {
     cudaEventRecord(rec.e1, s);
+    std::lock_guard<std::mutex> lk(g_mu);
     g_prof.push_back(rec);
   }
   return check_launch("conv_tc");
 }
 
-// Launch-variant autotuning.  Single-CTA vs CTA-pair tiles trade L2 / shared-memory operand traffic against per-tile
+// Launch-variant selection.  Single-CTA vs CTA-pair tiles trade L2 / shared-memory operand traffic against per-tile
 // synchronisation cost, and stream-K trades wave quantisation against a partial-tile exchange through L2; which one
-// wins depends on (M, N, K) in ways a closed-form model gets wrong for the short-K and small-M layers.  So the first
-// idempotent call of each layer shape times the candidates (CUDA events on the caller's stream; that one call is
-// synchronous), the choice is cached, and the call is finished with the winner so that its output carries the same
-// bits as every later call.  Every variant is deterministic (stream-K sums its pieces in K order whatever the
-// arrival order); data-parallel variants are bit-identical to each other, stream-K differs from them by fp32
-// reassociation only.  Calls that accumulate in place, calls during stream capture and profiled calls never tune.
+// wins depends on (M, N, K) in ways a closed-form model gets wrong for the short-K and small-M layers.
+//
+// The choice must not depend on timing noise: stream-K associates the fp32 sums differently from the data-parallel
+// variants, so a variant picked by a stopwatch makes the bits of eps differ between boxes, ranks and runs.  Hence:
+//   1. a COMMITTED per-shape table (tune_table.inc, generated on a B200 by scripts/make_tune_table.py from
+//      pd_tune_dump output) decides every shape of the path;
+//   2. shapes outside the table run the deterministic cost-model default;
+//   3. PD_B200_AUTOTUNE=1 (opt-in, used only to REGENERATE the table) times the candidates on first use.
+// Every variant is itself deterministic (stream-K sums its pieces in K order whatever the arrival order).
 struct TuneKey {
   int M, N, K, ksize, stride, c2, epi;
   bool operator<(const TuneKey& o) const {
     return std::tie(M, N, K, ksize, stride, c2, epi) < std::tie(o.M, o.N, o.K, o.ksize, o.stride, o.c2, o.epi);
   }
 };
-static std::map<TuneKey, TcVariant> g_tune;
+struct TuneRow { TuneKey k; TcVariant v; };
+static const TuneRow k_tune_table[] = {
+#include "tune_table.inc"
+    {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0}}   // terminator
+};
+static std::map<TuneKey, TcVariant> g_tune;      // runtime cache: table rows + autotuned shapes (guarded by g_mu)
+static bool g_tune_loaded = false;
 static int g_autotune = -1;
 static int g_force_sk = 0;
+
+static void tune_load_locked() {
+  if (g_tune_loaded) return;
+  for (const TuneRow* r = k_tune_table; r->k.M != 0; ++r) g_tune[r->k] = r->v;
+  g_tune_loaded = true;
+}
 
 int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   if (g_autotune < 0) {
     const char* e = getenv("PD_B200_AUTOTUNE");
-    g_autotune = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_autotune = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  if (g_force_cg != 0 || !g_autotune || p->out_dtype != PD_BF16 || g_dbg_mode != 0)
+  bool dbg = false;
+#ifdef PD_DEBUG
+  dbg = g_dbg_mode != 0;
+#endif
+  if (g_force_cg != 0 || p->out_dtype != PD_BF16 || dbg)
     return conv2d_tc_impl(p, s, TcVariant{g_force_cg, g_force_cg != 0 && g_force_sk ? 2 : 0, 0});
   const int pad = p->ksize / 2;
   const int Ho = (p->H + 2 * pad - p->ksize) / p->stride + 1, Wo = (p->W + 2 * pad - p->ksize) / p->stride + 1;
   const TuneKey key{p->B * Ho * Wo, p->Cout, p->ksize * p->ksize * p->C + p->C2, p->ksize, p->stride, p->C2 > 0 ? 1 : 0,
                     (p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0) |
                         (p->act == PD_ACT_GEGLU ? 8 : 0) | (p->ln_stats != nullptr ? 16 : 0)};
-  auto it = g_tune.find(key);
-  if (it != g_tune.end()) return conv2d_tc_impl(p, s, it->second);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    tune_load_locked();
+    auto it = g_tune.find(key);
+    if (it != g_tune.end()) {
+      const TcVariant v = it->second;
+      // a tabled stream-K row whose scratch cannot be had falls back to its data-parallel sibling inside impl (sk = 2)
+      return conv2d_tc_impl(p, s, TcVariant{v.cg, v.sk ? 2 : 0, v.bn});
+    }
+  }
+  if (!g_autotune) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0});
+  // ---- opt-in timing autotune (table regeneration) ----
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
   const bool in_place = p->res == p->out || p->x == p->out || (p->x2 != nullptr && p->x2 == p->out);
@@ -1038,16 +1171,6 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   // stream-K with the model's tile width, and with 128-wide tiles: fewer pieces per tile (cheaper fix-up) against
   // more operand traffic per FLOP
   const TcVariant cands[6] = {{1, 0, 0}, {2, 0, 0}, {2, 1, 0}, {1, 1, 0}, {2, 1, 128}, {1, 1, 128}};
-  // PD_B200_AUTOTUNE_COLD=1 (experiment): every timed launch runs behind a 256 MB memset, i.e. with its operands
-  // evicted from L2, instead of three warm launches back to back.  Measured in situ (3 x 10 graph replays each, same box):
-  // 26.24 / 26.07 / 25.82 ms per denoise step against 25.92 / 25.78 / 25.83 with the warm timing -> not the default.
-  static int cold = -1;
-  static void* cold_buf = nullptr;
-  if (cold < 0) {
-    const char* e = getenv("PD_B200_AUTOTUNE_COLD");
-    cold = (e != nullptr && e[0] == '1') ? 1 : 0;
-    if (cold && cudaMalloc(&cold_buf, (size_t)256 << 20) != cudaSuccess) { cudaGetLastError(); cold = 0; }
-  }
   float best_ms = 1e30f; TcVariant best = cands[0]; int last_run = -1, best_idx = 0;
   for (int c = 0; c < 6; ++c) {
     if (cands[c].bn != 0 && (p->Cout < cands[c].bn || p->act == PD_ACT_GEGLU)) continue;
@@ -1055,20 +1178,8 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
     if (rc == PD_ERR_UNSUPPORTED && cands[c].sk) continue;  // stream-K does not apply to this shape
     if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
     float ms = 0.f;
-    if (cold) {
-      for (int i = 0; i < 3 && rc == 0; ++i) {
-        cudaMemsetAsync(cold_buf, i, (size_t)256 << 20, s);
-        cudaEventRecord(e0, s);
-        rc = conv2d_tc_impl(p, s, cands[c]);
-        cudaEventRecord(e1, s);
-        float t = 0.f;
-        if (cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&t, e0, e1) != cudaSuccess) { cudaGetLastError(); rc = (int)cudaErrorUnknown; }
-        ms += t;
-      }
-      if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); set_error("conv_tc autotune (cold) failed"); return rc; }
-    } else {
     cudaEventRecord(e0, s);
-    for (int i = 0; i < 3 && rc == 0; ++i) rc = conv2d_tc_impl(p, s, cands[c]);
+    for (int i = 0; i < 5 && rc == 0; ++i) rc = conv2d_tc_impl(p, s, cands[c]);
     cudaEventRecord(e1, s);
     if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
     if (cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess) {
@@ -1077,13 +1188,15 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
       set_error("conv_tc autotune: %s", cudaGetErrorString(e));
       return (int)(e != cudaSuccess ? e : cudaErrorUnknown);
     }
-    }
     last_run = c;
     // stream-K must win clearly: it is the variant whose sums are associated differently
     if (ms * (cands[c].sk ? 1.03f : 1.0f) < best_ms) { best_ms = ms; best = cands[c]; best_idx = c; }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  g_tune[key] = best;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_tune[key] = best;
+  }
   // the output holds the last candidate's result: finish with the winner so this call's bits match every later call
   if (last_run != best_idx) return conv2d_tc_impl(p, s, best);
   return 0;
@@ -1092,16 +1205,33 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
 }  // namespace pd
 
 extern "C" {
+#ifdef PD_DEBUG
 // debugging aid: device buffer of 3*64*2 uint64 receiving CTA 0's per-role tile timeline (NULL = off)
 int pd_debug_timeline(void* dev_buf) { pd::g_dbg = (unsigned long long*)dev_buf; return 0; }
-// tile-shape override of the tcgen05 engine: 0 auto, 1 single-CTA tiles, 2 CTA-pair (cta_group::2) tiles
+// timing experiments (results WRONG when non-zero): pipeline stages switched off, see TcArgs::dbg_mode
 int pd_debug_gemm_mode(int mode) { pd::g_dbg_mode = mode; return 0; }
+#endif
+// tile order of the tcgen05 engine: 1 = N tiles of an M tile adjacent (default), 0 = M tiles of an N tile adjacent
+int pd_debug_tile_order(int n_fast) { pd::g_n_fast = n_fast != 0; return 0; }
+// Writes the launch-variant cache (committed table rows + shapes tuned under PD_B200_AUTOTUNE=1) as tune_table.inc rows.
+int pd_tune_dump(const char* path) {
+  FILE* f = fopen(path, "w");
+  if (!f) { pd::set_error("pd_tune_dump: cannot open %s", path); return PD_ERR_BAD_ARG; }
+  std::lock_guard<std::mutex> lk(pd::g_mu);
+  pd::tune_load_locked();
+  for (auto& kv : pd::g_tune)
+    fprintf(f, "{{%d, %d, %d, %d, %d, %d, %d}, {%d, %d, %d}},\n", kv.first.M, kv.first.N, kv.first.K, kv.first.ksize,
+            kv.first.stride, kv.first.c2, kv.first.epi, kv.second.cg, kv.second.sk, kv.second.bn);
+  fclose(f);
+  return 0;
+}
 int pd_debug_force_bn(int bn) { pd::g_force_bn = (bn >= 32 && bn <= 256 && bn % 32 == 0) ? bn : 0; return 0; }
 int pd_debug_force_cta_group(int cg) { pd::g_force_cg = (cg == 1 || cg == 2) ? cg : 0; return 0; }
 // with a forced CTA group: 1 = stream-K schedule wherever it applies (falls back to data-parallel elsewhere)
 int pd_debug_force_stream_k(int on) { pd::g_force_sk = on != 0; return 0; }
 // enable (1) / disable (0) per-launch timing of the tcgen05 engine; enabling clears the log
 int pd_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(pd::g_mu);
   for (auto& r : pd::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   pd::g_prof.clear();
   pd::g_prof_on = on != 0;
@@ -1112,6 +1242,7 @@ int pd_prof_dump(const char* path) {
   FILE* f = fopen(path, "w");
   if (!f) { pd::set_error("pd_prof_dump: cannot open %s", path); return PD_ERR_BAD_ARG; }
   fprintf(f, "M,N,K,ksize,stride,BN,m_tiles,n_tiles,stages,grid,cg,sk,ms,tflops\n");
+  std::lock_guard<std::mutex> lk(pd::g_mu);
   for (auto& r : pd::g_prof) {
     float t = 0.f;
     cudaEventSynchronize(r.e1);
@@ -1125,6 +1256,7 @@ int pd_prof_dump(const char* path) {
 // synchronises the recorded events and returns totals since pd_prof_enable(1)
 int pd_prof_read(double* total_ms, double* total_flops, uint64_t* launches) {
   double ms = 0.0, fl = 0.0;
+  std::lock_guard<std::mutex> lk(pd::g_mu);
   for (auto& r : pd::g_prof) {
     cudaError_t e = cudaEventSynchronize(r.e1);
     float t = 0.f;
@@ -1138,7 +1270,3 @@ int pd_prof_read(double* total_ms, double* total_flops, uint64_t* launches) {
   return 0;
 }
 }
-
-namespace pd {
-
-}  // namespace pd

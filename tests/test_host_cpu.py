@@ -18,6 +18,7 @@ HEADER = os.path.join(REPO, "include", "pd_b200.h")
 def _declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"#ifdef PD_DEBUG.*?#endif", "", src, flags=re.S)     # PD_DEBUG-only hooks are not in the shipped library
     return sorted(set(re.findall(r"\b(pd_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -30,6 +31,8 @@ def test_library_exports_every_declared_symbol():
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert _lib.lib.pd_abi_version() == 1
     assert isinstance(_lib.last_error(), str)
+    # the shipped library carries no pipeline-sabotaging timing hooks
+    assert not hasattr(_lib.lib, "pd_debug_gemm_mode") and not hasattr(_lib.lib, "pd_debug_timeline")
 
 
 def test_conv_params_struct_matches_header():
