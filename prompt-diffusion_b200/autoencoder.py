@@ -170,6 +170,7 @@ class AutoencoderKLDecoder:
 
     # ---- public surface ----------------------------------------------------------------------------------------
     @torch.no_grad()
+    @ops.on_device
     def decode(self, z: torch.Tensor, scaled: bool = False) -> torch.Tensor:
         """z [B, embed_dim, h, w] -> image [B, out_ch, 8h, 8w] fp32 (autoencoder.py:88-91).
         ``scaled=True`` decodes ``z / scale_factor`` (what ``decode_first_stage`` passes in)."""

@@ -34,6 +34,9 @@ from ..synth import CTRL_PREFIX, UNET_PREFIX
 _MODES = {"bf16": torch.bfloat16, "fp32": torch.float32}
 
 
+_on_device = ops.on_device
+
+
 class _Pool:
     """Named, shape-keyed device buffers (static addresses -> CUDA-graph friendly)."""
 
@@ -68,6 +71,8 @@ class _Net:
             raise ValueError(f"mode must be one of {list(_MODES)}")
         self.cfg, self.mode, self.dt = cfg, mode, _MODES[mode]
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.pool = pool if pool is not None else _Pool(self.device)
         self.w: Optional[PackedNet] = None
         self.model_channels = cfg.model_channels
@@ -272,12 +277,22 @@ class ControlNet(_Net):
         return self
 
     # hint encoders (cldm.py:147-181, 306-308) — depend only on example_pair / query: cached
-    def guided_hint(self, pair_list: Sequence[torch.Tensor], query: torch.Tensor) -> torch.Tensor:
-        key = _tensor_key(list(pair_list) + [query])
+    def guided_hint(self, pair_list: Sequence[torch.Tensor], query: torch.Tensor, batch: Optional[int] = None) -> torch.Tensor:
+        """``batch`` = latent batch the hint is added to.  The hint batch may DIVIDE it (extension over the reference,
+        which needs equal batches): the encoded hint is then tiled, i.e. [uncond, cond] halves that share their
+        ``example_pair`` / ``query`` run the two conv stacks once."""
+        key = _tensor_key(list(pair_list) + [query]) + (batch,)
         if self._hint_cache is not None and self._hint_cache[0] == key:
             return self._hint_cache[2]
         pair = pair_list[0] if len(pair_list) == 1 else torch.cat(list(pair_list), 1)
         B, _, Hp, Wp = pair.shape
+        if query.shape[0] != B:
+            raise ValueError(f"example_pair batch {B} != query batch {query.shape[0]}")
+        reps = 1
+        if batch is not None and batch != B:
+            if batch % B != 0:
+                raise ValueError(f"hint batch {B} does not divide the latent batch {batch}")
+            reps = batch // B
         outs = []
         for which, (src, stack) in enumerate(((pair, self.w.hint_pair), (query, self.w.hint_query))):
             src = src.to(device=self.device, dtype=torch.float32).contiguous()
@@ -295,8 +310,13 @@ class ControlNet(_Net):
                 self.conv(pc, xin, o, B, H, W, act=PD_ACT_NONE if last else PD_ACT_SILU, res=res)
                 cur, H, W = full, Ho, Wo
             outs.append(cur)
-        self._hint_cache = (key, list(pair_list) + [query], outs[1])
-        return outs[1]          # example_pair_hint + query_hint
+        hint = outs[1]          # example_pair_hint + query_hint
+        if reps > 1:            # once per conditioning, outside the per-step work: plain device-to-device copies
+            tiled = self.buf("hint.tiled", reps * hint.shape[0], hint.shape[1])
+            tiled.view(reps, hint.shape[0], hint.shape[1]).copy_(hint.unsqueeze(0).expand(reps, -1, -1))
+            hint = tiled
+        self._hint_cache = (key, list(pair_list) + [query], hint)
+        return hint
 
     def _run(self, x_pm, t, pair_list, query, context_list, B, H, W, sink):
         """Shared body.  ``sink(i, h, Hh, Ww, pc)`` is called with every block output and its zero conv
@@ -306,7 +326,7 @@ class ControlNet(_Net):
         emb_all = self.embed(t)
         kv = self.context_kv(context_list)
         ctx_len = self._ctx_cache[3]
-        hint = self.guided_hint(pair_list, query)
+        hint = self.guided_hint(pair_list, query, B)
         if hint.shape[0] != B * H * W:
             raise ValueError(f"hint resolution {tuple(pair_list[0].shape[-2:])} is not 8x the latent {H}x{W}")
         cur, Hh, Ww = x_pm, H, W
@@ -325,6 +345,7 @@ class ControlNet(_Net):
         self.run_block(w.middle, cur, o, emb_all, kv, ctx_len, B, Hh, Ww, "ctrl.mid")
         sink(len(w.input_blocks), o, Hh, Ww, w.middle_out)
 
+    @_on_device
     def forward(self, x, timesteps, example_pair, query, context, **kwargs) -> List[torch.Tensor]:
         B, Cx, H, W = x.shape
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
@@ -404,6 +425,7 @@ class ControlledUnetModel(_Net):
         self.conv(w.out_conv, g, eps_full, B, st.H, st.W)
         return eps_full[:, :self.cfg.out_channels]
 
+    @_on_device
     def forward(self, x, timesteps=None, context=None, control=None, only_mid_control=False, **kwargs):
         B, Cx, H, W = x.shape
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
@@ -432,6 +454,8 @@ class ControlLDM:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("prompt_diffusion_b200.ControlLDM runs on CUDA only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         pool = _Pool(self.device)
         self.control_model = ControlNet(cfg, mode, self.device, pool)
         self.model = SimpleNamespace(diffusion_model=ControlledUnetModel(cfg, mode, self.device, pool))
@@ -439,6 +463,7 @@ class ControlLDM:
         self.only_mid_control = only_mid_control
         self.control_scales = [1.0] * 13
         self.supports_step_graph = True     # apply_model is capture-safe once its buffers and caches are warm
+        self.tiles_hint_batch = True        # example_pair / query batches that divide the latent batch are tiled
         self.parameterization = cfg.parameterization
         self.channels = cfg.in_channels
         self.scale_factor = cfg.scale_factor
@@ -460,6 +485,7 @@ class ControlLDM:
         self.alphas_cumprod_prev = f32(acp_prev)
         self.sqrt_one_minus_alphas_cumprod = f32(np.sqrt(1.0 - acp))
 
+    @_on_device
     def load_state_dict(self, sd: Mapping[str, torch.Tensor], strict: bool = True):
         """Reference-format checkpoint (``control_model.*`` + ``model.diffusion_model.*``; other entries such
         as first_stage_model / cond_stage_model / schedule buffers are ignored — out of scope)."""
@@ -477,6 +503,7 @@ class ControlLDM:
         return self
 
     @torch.no_grad()
+    @_on_device
     def get_learned_conditioning(self, c):
         """LatentDiffusion.get_learned_conditioning (ldm/models/diffusion/ddpm.py:554-565) for token-id input: the
         reference passes strings through ``cond_stage_model.encode`` (tokenizer + CLIP text tower); tokenisation is
@@ -488,6 +515,7 @@ class ControlLDM:
         return self.cond_stage_model.encode(c)
 
     @torch.no_grad()
+    @_on_device
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
         """LatentDiffusion.decode_first_stage (ldm/models/diffusion/ddpm.py:820-828): ``decode(z / scale_factor)`` on
         the B200 first-stage decoder; needs ``first_stage_model.*`` weights in the loaded checkpoint."""
@@ -504,6 +532,7 @@ class ControlLDM:
         return self
 
     @torch.no_grad()
+    @_on_device
     def apply_model(self, x_noisy, t, cond, *args, **kwargs):
         assert isinstance(cond, dict)
         assert cond["example_pair"] is not None
@@ -520,6 +549,7 @@ class ControlLDM:
         return eps if x_noisy.dtype == torch.float32 else eps.to(x_noisy.dtype)
 
     @torch.no_grad()
+    @_on_device
     def prepare_conditioning(self, cond) -> None:
         """Fill the step-invariant caches (both nets' context K/V projections, the two hint encoders) for
         ``cond``; a no-op when they already hold this conditioning.  A captured step graph reads those cache
@@ -527,7 +557,7 @@ class ControlLDM:
         ctx_list = list(cond["c_crossattn"])
         self.model.diffusion_model.context_kv(ctx_list)
         self.control_model.context_kv(ctx_list)
-        self.control_model.guided_hint(list(cond["example_pair"]), cond["query"][0])
+        self.control_model.guided_hint(list(cond["example_pair"]), cond["query"][0], ctx_list[0].shape[0])
 
     def _denoise_pm(self, x_pm, t_dev, ctx_list, pair_list, query, B, H, W):
         """UNet encoder -> ControlNet (zero-conv epilogues add scale*control onto the stored skips, in

@@ -27,14 +27,29 @@ def get_state_dict(d):
     return d.get("state_dict", d)
 
 
-def load_state_dict(ckpt_path: str, location: str = "cpu") -> Dict[str, torch.Tensor]:
-    """cldm/model.py:12-21 (same extension dispatch, same envelope handling, same log line)."""
+def load_state_dict(ckpt_path: str, location: str = "cpu", allow_pickle: bool = False) -> Dict[str, torch.Tensor]:
+    """cldm/model.py:12-21 (same extension dispatch, same envelope handling, same log line).
+
+    ``.safetensors`` is the preferred format.  ``.ckpt`` / ``.pth`` files are read with ``weights_only=True`` (tensors
+    and plain containers only); a checkpoint that needs full unpickling — which can execute arbitrary code from the
+    file — is loaded only on explicit opt-in (``allow_pickle=True`` or ``PD_B200_ALLOW_PICKLE=1``), with a warning."""
     _, extension = os.path.splitext(ckpt_path)
     if extension.lower() == ".safetensors":
         import safetensors.torch
         state_dict = safetensors.torch.load_file(ckpt_path, device=location)
     else:
-        state_dict = get_state_dict(torch.load(ckpt_path, map_location=torch.device(location), weights_only=False))
+        try:
+            raw = torch.load(ckpt_path, map_location=torch.device(location), weights_only=True)
+        except Exception as e:
+            if not (allow_pickle or os.environ.get("PD_B200_ALLOW_PICKLE") == "1"):
+                raise RuntimeError(
+                    f"{ckpt_path} cannot be read with weights_only=True ({type(e).__name__}: {e}). Full unpickling can "
+                    "run arbitrary code from the file: convert the checkpoint to .safetensors, or opt in with "
+                    "allow_pickle=True / PD_B200_ALLOW_PICKLE=1 if you trust its source.") from e
+            import warnings
+            warnings.warn(f"loading {ckpt_path} with full unpickling (weights_only=False): only do this for trusted files")
+            raw = torch.load(ckpt_path, map_location=torch.device(location), weights_only=False)
+        state_dict = get_state_dict(raw)
     state_dict = get_state_dict(state_dict)
     print(f"Loaded state_dict from [{ckpt_path}]")
     return state_dict

@@ -74,6 +74,7 @@ class FrozenCLIPTextEncoder:
         return self
 
     @torch.no_grad()
+    @ops.on_device
     def forward(self, tokens: torch.Tensor) -> torch.Tensor:
         """tokens int64 [B, L <= 77] (the tokenizer's ``input_ids``) -> last_hidden_state fp32 [B, L, width]."""
         if not self.loaded:

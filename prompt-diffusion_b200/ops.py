@@ -19,6 +19,22 @@ from ._lib import (PD_ACT_GEGLU, PD_ACT_NONE, PD_ACT_SILU, PD_BF16, PD_ENGINE_AU
 _DT = {torch.float32: PD_F32, torch.bfloat16: PD_BF16}
 
 
+def on_device(fn):
+    """Decorator for public entry points of the model classes (anything with ``self.device``): run with the model's
+    device current.  The C-ABI launches on the current device's current stream and keeps per-device state keyed by
+    ``cudaGetDevice()``, so a ``cuda:1`` model must not be driven while ``cuda:0`` is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        dev = torch.device(self.device)
+        if dev.type != "cuda" or dev.index is None or torch.cuda.current_device() == dev.index:
+            return fn(self, *a, **kw)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 def dt_code(t: torch.Tensor) -> int:
     try:
         return _DT[t.dtype]
@@ -43,9 +59,18 @@ def _ld(t: torch.Tensor) -> int:
 
 
 def _cuda(*ts):
+    """Every tensor must live on the CURRENT CUDA device: the library launches on that device's current stream and
+    keeps per-device state keyed by ``cudaGetDevice()``.  The model classes enter ``torch.cuda.device(self.device)``
+    around their public entry points; direct callers of these ops on a second GPU must do the same."""
+    cur = torch.cuda.current_device()
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise ValueError("prompt_diffusion_b200 ops need CUDA tensors (there is no CPU path)")
+        if t.device.index != cur:
+            raise ValueError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: wrap the call in "
+                             f"torch.cuda.device({t.device.index}) (the model classes do this themselves)")
 
 
 def conv2d(x, w, out, B, H, W, *, ksize=1, stride=1, upsample=False, bias=None, rowvec=None, res=None,

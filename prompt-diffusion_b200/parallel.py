@@ -51,11 +51,18 @@ def sample_sharded(sample_fn: Callable, batch_size: int, conditioning, unconditi
     """Run ``sample_fn(local_batch, cond, un_cond, x_T) -> latents`` on this rank's shard (optionally in
     chunks of ``chunk`` prompts) and all-gather the results in prompt order.
 
-    ``x_T`` (if given) is the FULL-batch noise so that the result is bit-identical to the single-GPU run."""
+    ``x_T`` (if given) is the FULL-batch noise, so every rank denoises exactly the rows the single-GPU run would.
+    In fp32 mode the gathered result equals the single-GPU run bit for bit (kernels are deterministic and per-sample);
+    in bf16 mode a prompt's result depends on its position inside the rank-local batch (tile boundaries change the fp32
+    summation order), so sharded and unsharded runs agree to bf16 rounding noise, not bit for bit."""
     if dist.is_available() and dist.is_initialized():
         world, rank = dist.get_world_size(group), dist.get_rank(group)
     else:
         world, rank = 1, 0
+    if batch_size < world:
+        # checked on EVERY rank before any work or collective: a rank without prompts must not leave the others
+        # waiting inside the all-gather
+        raise ValueError(f"batch {batch_size} < world size {world}: every rank needs at least one prompt")
     lo, hi = shard_bounds(batch_size, rank, world)
     outs = []
     step = (hi - lo) if not chunk else chunk
@@ -64,7 +71,4 @@ def sample_sharded(sample_fn: Callable, batch_size: int, conditioning, unconditi
         outs.append(sample_fn(b - a, shard_conditioning(conditioning, a, b),
                               shard_conditioning(unconditional_conditioning, a, b),
                               None if x_T is None else x_T[a:b]))
-    local = torch.cat(outs) if outs else None
-    if local is None:
-        raise ValueError(f"rank {rank} owns no prompts (batch {batch_size} < world {world})")
-    return all_gather_latents(local, batch_size, group)
+    return all_gather_latents(torch.cat(outs), batch_size, group)

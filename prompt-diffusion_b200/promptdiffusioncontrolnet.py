@@ -17,6 +17,7 @@ from typing import Any, Dict, List, Mapping, Optional, Tuple, Union
 
 import torch
 
+from . import ops
 from .cldm.cldm import ControlNet
 from .config import CLDM_V15, CLDMConfig
 
@@ -152,6 +153,7 @@ class PromptDiffusionControlNetModel:
         return self
 
     @torch.no_grad()
+    @ops.on_device
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
                 encoder_hidden_states: torch.Tensor, controlnet_cond: torch.Tensor,
                 controlnet_query_cond: torch.Tensor, conditioning_scale: float = 1.0,
