@@ -17,6 +17,10 @@
  *    ELEMENTS (lets a producer write straight into a channel-concat slot).
  *  - dtype codes: PD_F32 (fp32 mode: SIMT FFMA kernels, fp32 storage) and
  *    PD_BF16 (bf16 storage, fp32 accumulation; tcgen05/TMEM/TMA GEMMs).
+ *  - concurrency: launches that use library-owned scratch — the stream-K workspace of pd_conv2d (one per device)
+ *    and, for callers that do not pass their own, the cooperative GroupNorm scratch — must not overlap on two
+ *    streams of one device; serialise such users with an event, or give each its own `partial` scratch
+ *    (pd_group_norm) and run pd_conv2d from one stream per device.  Host-side caches are mutex-guarded.
  *  - return value: 0 on success, a negative PD_ERR_* / positive cudaError_t
  *    otherwise; pd_last_error() gives a human-readable message.  There is no
  *    CPU fallback anywhere behind this interface.
@@ -117,7 +121,7 @@ typedef struct pd_conv_params {
   int32_t B, H, W, C;  /* input geometry of x (H, W BEFORE the optional upsample) */
   int32_t C2;          /* channels of x2 (0 = no segment 1)                 */
   int32_t Cout;
-  int32_t ksize;       /* 1 or 3 (padding = ksize/2)                        */
+  int32_t ksize;       /* 1 or 3 (padding = ksize/2); 2 with pad_y / pad_x (tcgen05 engine) */
   int32_t stride;      /* 1 or 2                                            */
   int32_t upsample;    /* 1: x is read through a nearest x2 upsample (Upsample.forward) */
   int32_t ldx, ldx2, ldr, ldo, ldrv;
@@ -135,7 +139,32 @@ typedef struct pd_conv_params {
    * without ever writing the normalised tensor.  NULL = off. */
   const float* ln_stats;   /* [rows][2] fp32 (mean, rstd) from pd_layer_norm_stats */
   const float* ln_colsum;  /* [Cout] fp32: sum_k of the (rounded) scaled weights of row n */
+  /* ---- statistics handed from a GEMM's epilogue to the norm that follows it (tcgen05 engine, bf16 output; all
+   * zero = off).  A norm's statistics pass re-reads a tensor the producing GEMM held in registers a moment earlier;
+   * the epilogue emits (sum, sum of squares) partials of the values AS STORED (bf16-rounded) instead. ---- */
+  const float* ln_parts;   /* consumer side of a folded LayerNorm, alternative to ln_stats: the producer's ln_parts_out */
+  float* ln_parts_out;     /* producer side: 16-byte header {int32 parts} followed by float2 (sum, sumsq) [parts][ln_rows];
+                            * one partial per (N tile, epilogue warp group) of this launch and output row; needs
+                            * space for pd_conv2d_ln_parts_floats(rows) floats */
+  float* gn_stats_out;     /* producer side of GroupNorm (util.py:217-219 statistics): float2 (sum, sumsq) per
+                            * (64-pixel record, channel): [(image * gn_recs_per_image + gn_rec_off + record)][gn_ld],
+                            * this launch's channel 0 at the pointer.  Needs Ho*Wo % 64 == 0 and a pixel-box tile of
+                            * at least 64 pixels (pd_conv2d_gn_stats_supported); consumed by pd_group_norm_apply */
+  int64_t ln_rows;         /* row pitch of the ln_parts / ln_parts_out arrays (>= output rows) */
+  int64_t out_sx, out_sy, out_sb; /* output pixel strides in ELEMENTS (x, y, image); all 0 = dense (ldo, Wo*ldo, Ho*Wo*ldo).
+                            * Non-dense: ldo is ignored, res must be NULL.  Lets a launch write one phase of a 2x
+                            * upsampled tensor (see pad_y / pad_x) */
+  float ln_eps;            /* eps of the LayerNorm behind ln_parts */
+  int32_t gn_ld, gn_rec_off, gn_recs_per_image;
+  int32_t pad_y, pad_x;    /* ksize == 2 only: zero rows / columns before the first tap (0 or 1); Ho = H, Wo = W.
+                            * Upsample.forward (openaimodel.py:108-118: nearest x2 then conv3x3) == four such 2x2
+                            * convolutions of the LOW-resolution tensor, one per output phase (py, px), with the 3x3
+                            * taps that fall on the same source pixel pre-summed: 4/9 of the MACs, no 4x tensor */
 } pd_conv_params;
+/* floats needed behind ln_parts_out for `rows` output rows (header + 64 partial slots) */
+int64_t pd_conv2d_ln_parts_floats(int64_t rows);
+/* 1 when a launch with this output geometry can emit gn_stats_out */
+int pd_conv2d_gn_stats_supported(int32_t B, int32_t Ho, int32_t Wo, int32_t ksize, int32_t stride);
 int pd_conv2d(const pd_conv_params* p, void* stream);
 
 /* Re-lay a reference OIHW fp32 conv weight (or [out,in] linear weight with kh=kw=1)
@@ -156,6 +185,16 @@ int pd_group_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const floa
                   const float* beta, float* partial, int32_t B, int32_t HW, int32_t C,
                   int32_t groups, float eps, int32_t act, int32_t dtype, int32_t out_dtype,
                   void* stream);
+
+/* GroupNorm(+SiLU) of a bf16 tensor whose (sum, sum of squares) records were emitted by the epilogue of the GEMM(s)
+ * that produced it (pd_conv_params.gn_stats_out: float2 [B * recs_per_image][stats_ld], one record per 64 pixels):
+ * the records are folded per (image, group) in a fixed order, then x is streamed once.  Same arithmetic as
+ * pd_group_norm (fp32 statistics over the stored bf16 values, GroupNorm32 util.py:217-219).  `scratch` receives the
+ * B * 64 (mean, rstd) floats.  split != 0: out gets 2C columns, bf16(y) at column c and bf16(y - bf16(y)) at C + c. */
+int pd_group_norm_apply(const void* x, int32_t ldx, void* out, int32_t ldo, const float* gamma,
+                        const float* beta, const float* colstats, int32_t stats_ld,
+                        int32_t recs_per_image, float* scratch, int32_t B, int32_t HW, int32_t C,
+                        int32_t groups, float eps, int32_t act, int32_t split, void* stream);
 
 /* Row statistics of LayerNorm: stats[row] = (mean, 1/sqrt(var + eps)) in fp32, for the folded form of
  * LayerNorm -> Linear (pd_conv_params.ln_stats). */
@@ -228,6 +267,15 @@ int pd_nchw_to_nhwc(const float* x, void* out, int32_t ldo, int32_t B, int32_t C
                     int32_t W, int32_t out_dtype, int32_t accumulate, void* stream);
 int pd_nhwc_to_nchw(const void* x, int32_t ldx, float* out, int32_t B, int32_t C, int32_t H,
                     int32_t W, int32_t dtype, float scale, void* stream);
+/* Split-precision entry of the latent (bf16 mode): out[:, 0:C] = hi = bf16(x), out[:, C:2C] = bf16(x - hi),
+ * out[:, 2C:3C] = hi; with conv_in's weights packed [w_hi | w_hi | w_lo] per tap (input_blocks.0.0 of both nets,
+ * openaimodel.py:560-566 / cldm.py:183-189) the 4-channel latent is convolved at ~16 mantissa bits inside the
+ * 64-channel K padding the tcgen05 engine needs anyway. */
+int pd_nchw_to_nhwc_split(const float* x, void* out, int32_t ldo, int32_t B, int32_t C, int32_t H,
+                          int32_t W, void* stream);
+/* out[r, c] = x[r, c] + y[r, c], fp32, row-pitched (sums the hi / lo weight halves of the UNet `out` conv). */
+int pd_add2d(const float* x, int32_t ldx, const float* y, int32_t ldy, float* out, int32_t ldo,
+             int64_t rows, int32_t cols, void* stream);
 /* strided 2-D cast/copy: out[r, c] = (out_dtype) x[r, c], r < rows, c < cols */
 int pd_cast2d(const void* x, int32_t ldx, int32_t dtype, void* out, int32_t ldo,
               int32_t out_dtype, int64_t rows, int32_t cols, void* stream);

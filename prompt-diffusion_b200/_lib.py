@@ -32,6 +32,10 @@ class ConvParams(C.Structure):
         ("act", C.c_int32), ("dtype", C.c_int32), ("out_dtype", C.c_int32), ("engine", C.c_int32),
         ("alpha", C.c_float), ("w_blocked", C.c_int32),
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p),
+        ("ln_parts", C.c_void_p), ("ln_parts_out", C.c_void_p), ("gn_stats_out", C.c_void_p),
+        ("ln_rows", C.c_int64), ("out_sx", C.c_int64), ("out_sy", C.c_int64), ("out_sb", C.c_int64),
+        ("ln_eps", C.c_float), ("gn_ld", C.c_int32), ("gn_rec_off", C.c_int32), ("gn_recs_per_image", C.c_int32),
+        ("pad_y", C.c_int32), ("pad_x", C.c_int32),
     ]
 
 
@@ -53,11 +57,16 @@ SIGNATURES = {
     "pd_debug_group_norm_fused": (C.c_int, [C.c_int32]),
     "pd_debug_attention_timeline": (C.c_int, [C.c_void_p]),
     "pd_conv2d": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
+    "pd_conv2d_ln_parts_floats": (C.c_int64, [C.c_int64]),
+    "pd_conv2d_gn_stats_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "pd_repack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p]),
     "pd_group_norm_scratch_floats": (C.c_int64, [C.c_int32]),
     "pd_group_norm": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "pd_group_norm_apply": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
     "pd_layer_norm": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "pd_attention_causal": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
@@ -84,6 +93,10 @@ SIGNATURES = {
                                   C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "pd_nhwc_to_nchw": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "pd_nchw_to_nhwc_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p]),
+    "pd_add2d": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
+                           C.c_void_p]),
     "pd_cast2d": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64,
                             C.c_int32, C.c_void_p]),
     "pd_upsample2x": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

@@ -118,7 +118,11 @@ class AutoencoderKLDecoder:
         return ops.conv2d(x, pc.w, out, B, H, W, ksize=pc.ksize, stride=pc.stride, bias=pc.bias, **kw)
 
     def _gn(self, n: PNorm, x, out, B, HW, act):
-        return ops.group_norm(x, out, n.gamma, n.beta, B, HW, eps=1e-6, act=act)
+        # this decoder's OWN barrier / partial-sum scratch: a decode on a side stream must not share the cooperative
+        # GroupNorm kernel's barrier words with a sampler running on the same device
+        from ._lib import lib
+        scr = self.buf("gn.coop", 1, int(lib.pd_group_norm_scratch_floats(B)), torch.float32, zero=True)
+        return ops.group_norm(x, out, n.gamma, n.beta, B, HW, eps=1e-6, act=act, scratch=scr.view(-1))
 
     def _res_block(self, r: _VRes, x, out, B, H, W):
         """ResnetBlock.forward with temb=None (model.py:123-145)."""

@@ -25,7 +25,7 @@ from typing import Dict, List, Mapping, Optional, Sequence
 import numpy as np
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from .._lib import PD_ACT_GEGLU, PD_ACT_NONE, PD_ACT_SILU
 from ..config import CLDM_V15, CLDMConfig
 from ..packing import PConv, PRes, PST, PackedNet, pad_channels
@@ -43,6 +43,7 @@ class _Pool:
     def __init__(self, device):
         self.device = device
         self.bufs: Dict[tuple, torch.Tensor] = {}
+        self.fresh: Dict[tuple, Dict[int, int]] = {}
 
     def get(self, name: str, rows: int, cols: int, dtype: torch.dtype, zero: bool = False) -> torch.Tensor:
         key = (name, rows, cols, dtype)
@@ -54,6 +55,46 @@ class _Pool:
 
     def nbytes(self) -> int:
         return sum(b.numel() * b.element_size() for b in self.bufs.values())
+
+    # ---- GroupNorm statistics handed over by GEMM epilogues (pd_conv_params.gn_stats_out) -------------------------
+    # One fp32 workspace per activation buffer: float2 (sum, sumsq) [B * HW / 64 records][row pitch of the buffer], so
+    # the producers of the two column slots of a decoder concat buffer write side by side.  ``fresh`` remembers which
+    # channel ranges currently hold statistics of what is stored (any writer that does not emit them invalidates).
+    def gn_ws(self, view: torch.Tensor, B: int, HW: int):
+        pitch = view.stride(0)
+        key = ("gnws", view.untyped_storage().data_ptr(), pitch, B, HW)
+        ws = self.bufs.get(key)
+        if ws is None:
+            ws = torch.zeros(((B * HW // 64) * pitch * 2,), dtype=torch.float32, device=self.device)
+            self.bufs[key] = ws
+            self.fresh[key] = {}
+        return key, ws, pitch
+
+    def gn_mark(self, key, chan: int, width: int):
+        f = self.fresh[key]
+        for c0 in [c for c, w in f.items() if c < chan + width and chan < c + w and c != chan]:
+            del f[c0]
+        f[chan] = width
+
+    def gn_invalidate(self, view: torch.Tensor):
+        sp, pitch = view.untyped_storage().data_ptr(), view.stride(0)
+        chan, width = view.storage_offset() % pitch, view.shape[1]
+        for key, f in self.fresh.items():
+            if key[1] == sp:
+                for c0 in [c for c, w in f.items() if c < chan + width and chan < c + w]:
+                    del f[c0]
+
+    def gn_covered(self, key, chan: int, width: int) -> bool:
+        f = self.fresh.get(key)
+        if not f:
+            return False
+        c = chan
+        while c < chan + width:
+            w = f.get(c)
+            if w is None:
+                return False
+            c += w
+        return c == chan + width
 
 
 def _tensor_key(ts: Sequence[torch.Tensor]):
@@ -107,8 +148,59 @@ class _Net:
             raise ValueError(f"latent has {cx} channels, the model expects {pc.cin}")
         return self.buf(name, rows, pc.cin_pad, zero=True)
 
-    def conv(self, pc: PConv, x, out, B, H, W, **kw):
-        return ops.conv2d(x, pc.w, out, B, H, W, ksize=pc.ksize, stride=pc.stride, bias=pc.bias, **kw)
+    def load_latent(self, name, x):
+        """NCHW fp32 latent -> the pixel-major buffer conv_in reads (split hi / lo / hi columns in bf16 mode)."""
+        B, Cx, H, W = x.shape
+        x_pm = self.latent_buffer(name, B * H * W, Cx)
+        if self.w.input_blocks[0][0].split == "in":
+            ops.nchw_to_nhwc_split(x, x_pm)
+        else:
+            ops.nchw_to_nhwc(x, x_pm)
+        return x_pm
+
+    def conv(self, pc: PConv, x, out, B, H, W, stats=None, **kw):
+        """``stats=(B_real, HW_real)``: the output feeds a GroupNorm — have the epilogue emit its column statistics
+        (tcgen05 engine, geometry permitting); otherwise whatever statistics the output range held are invalidated."""
+        ks, st = pc.ksize, pc.stride
+        if stats is not None:
+            Ho, Wo = (H, W) if ks == 2 else ((H + 2 * (ks // 2) - ks) // st + 1, (W + 2 * (ks // 2) - ks) // st + 1)
+            sB, sHW = stats
+            ok = (self.dt == torch.bfloat16 and out.dtype == torch.bfloat16 and x.shape[1] % 64 == 0 and out.shape[1] % 8 == 0
+                  and sHW % 64 == 0 and kw.get("act", PD_ACT_NONE) != PD_ACT_GEGLU
+                  and ops.gn_stats_supported(B, Ho, Wo, ks, st))
+            if ok:
+                key, ws, pitch = self.pool.gn_ws(out, sB, sHW)
+                chan = out.storage_offset() % pitch
+                kw.update(gn_stats_out=ws[2 * chan:], gn_ld=pitch, gn_recs_per_image=sHW // 64)
+                kw.setdefault("gn_rec_off", 0)
+                self.pool.gn_mark(key, chan, out.shape[1])
+            else:
+                kw.pop("gn_rec_off", None)
+                self.pool.gn_invalidate(out)
+        return ops.conv2d(x, pc.w, out, B, H, W, ksize=ks, stride=st, bias=pc.bias, **kw)
+
+    def gn(self, x, out, norm, B, HW, eps, act, split=False):
+        """GroupNorm32 / Normalize (+SiLU).  When every producer of ``x`` emitted statistics from its epilogue the
+        tensor is streamed once (pd_group_norm_apply); otherwise the two-phase cooperative kernel re-reads it."""
+        if self.dt == torch.bfloat16 and HW % 64 == 0:
+            pitch = x.stride(0)
+            key = ("gnws", x.untyped_storage().data_ptr(), pitch, B, HW)
+            chan = x.storage_offset() % pitch
+            if self.pool.gn_covered(key, chan, x.shape[1]):
+                ws = self.pool.bufs[key]
+                scr = self.pool.get("gn.meanrstd", 1, B * 64, torch.float32)
+                return ops.group_norm_apply(x, out, norm.gamma, norm.beta, ws[2 * chan:], pitch, HW // 64, scr.view(-1), B, HW,
+                                            eps=eps, act=act, split=split)
+        if split:
+            raise RuntimeError("split-precision GroupNorm output needs producer statistics")
+        scr = self.pool.get("gn.coop", 1, int(_lib.lib.pd_group_norm_scratch_floats(B)), torch.float32, zero=True)
+        return ops.group_norm(x, out, norm.gamma, norm.beta, B, HW, eps=eps, act=act, scratch=scr.view(-1))
+
+    def gn_ready(self, x, B, HW) -> bool:
+        if self.dt != torch.bfloat16 or HW % 64 != 0:
+            return False
+        key = ("gnws", x.untyped_storage().data_ptr(), x.stride(0), B, HW)
+        return self.pool.gn_covered(key, x.storage_offset() % x.stride(0), x.shape[1])
 
     # ---- timestep embedding (cldm.py:26-27,303-304; openaimodel.py:526-531; ResBlock emb_layers) ----
     def embed(self, t: torch.Tensor) -> torch.Tensor:
@@ -153,55 +245,55 @@ class _Net:
         (+ skip, fused as residual or as a second K segment)."""
         M = B * H * W
         g1 = self.buf("t_gn", M, r.cin)
-        ops.group_norm(x, g1, r.gn1.gamma, r.gn1.beta, B, H * W, eps=1e-5, act=PD_ACT_SILU)
+        self.gn(x, g1, r.gn1, B, H * W, 1e-5, PD_ACT_SILU)
         h1 = self.buf("t_h1", M, r.cout)
-        self.conv(r.conv1, g1, h1, B, H, W, rowvec=emb_all[:, r.emb_off:r.emb_off + r.cout])
+        self.conv(r.conv1, g1, h1, B, H, W, rowvec=emb_all[:, r.emb_off:r.emb_off + r.cout], stats=(B, H * W))
         g2 = self.buf("t_gn", M, r.cout)
-        ops.group_norm(h1, g2, r.gn2.gamma, r.gn2.beta, B, H * W, eps=1e-5, act=PD_ACT_SILU)
+        self.gn(h1, g2, r.gn2, B, H * W, 1e-5, PD_ACT_SILU)
         if r.has_skip:
-            self.conv(r.conv2, g2, out, B, H, W, x2=x)
+            self.conv(r.conv2, g2, out, B, H, W, x2=x, stats=(B, H * W))
         else:
-            self.conv(r.conv2, g2, out, B, H, W, res=x)
+            self.conv(r.conv2, g2, out, B, H, W, res=x, stats=(B, H * W))
         return out
 
     def spatial_transformer(self, s: PST, x, out, ctx_kv, ctx_len, B, H, W):
         """SpatialTransformer.forward + BasicTransformerBlock._forward (attention.py:271-275,321-340)."""
         M, Cc, N = B * H * W, s.ch, H * W
         g = self.buf("t_gn", M, Cc)
-        ops.group_norm(x, g, s.gn.gamma, s.gn.beta, B, N, eps=1e-6, act=PD_ACT_NONE)
+        self.gn(x, g, s.gn, B, N, 1e-6, PD_ACT_NONE)
         a = self.buf("t_a", M, Cc)
-        self.conv(s.proj_in, g, a, 1, 1, M)
         fold = s.ln_folded
+        # Folded LayerNorms take their row statistics from the epilogue of the GEMM that PRODUCES the stream
+        # (ln_parts_out -> ln_parts): no statistics pass over the tensor at all.
+        lnp = [self.buf(f"t_lnp{i}", 1, ops.ln_parts_floats(M), dtype=torch.float32).view(-1) for i in (0, 1)] if fold else None
+        lnk = (lambda i: dict(ln_parts_out=lnp[i], ln_rows=M)) if fold else (lambda i: {})
+        self.conv(s.proj_in, g, a, 1, 1, M, **lnk(0))
         ln = None if fold else self.buf("t_ln", M, Cc)
-        st = self.buf("t_lnstats", M, 2, dtype=torch.float32) if fold else None
-        # attn1 (self).  Folded form: row statistics only, the GEMM reads the raw stream (packing.Packer.folded)
+        # attn1 (self).  Folded form: the GEMM reads the raw stream (packing.Packer.folded)
         qkv = self.buf("t_qkv", M, 3 * Cc)
         if fold:
-            ops.layer_norm_stats(a, st)
-            ops.linear(a, s.wqkv.w, qkv, bias=s.wqkv.bias, ln_stats=st, ln_colsum=s.wqkv.colsum)
+            ops.linear(a, s.wqkv.w, qkv, bias=s.wqkv.bias, ln_parts=lnp[0], ln_rows=M, ln_colsum=s.wqkv.colsum)
         else:
             ops.layer_norm(a, ln, s.ln1.gamma, s.ln1.beta)
             ops.linear(ln, s.wqkv.w, qkv)
         att = self.buf("t_att", M, Cc)
         ops.attention(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], att, B, s.heads, N, N, s.d)
         b = self.buf("t_b", M, Cc)
-        ops.linear(att, s.out1.w, b, bias=s.out1.bias, res=a)
+        ops.linear(att, s.out1.w, b, bias=s.out1.bias, res=a, **lnk(1))
         # attn2 (cross, 77 keys)
         q2 = self.buf("t_q", M, Cc)
         if fold:
-            ops.layer_norm_stats(b, st)
-            ops.linear(b, s.wq2.w, q2, bias=s.wq2.bias, ln_stats=st, ln_colsum=s.wq2.colsum)
+            ops.linear(b, s.wq2.w, q2, bias=s.wq2.bias, ln_parts=lnp[1], ln_rows=M, ln_colsum=s.wq2.colsum)
         else:
             ops.layer_norm(b, ln, s.ln2.gamma, s.ln2.beta)
             ops.linear(ln, s.wq2.w, q2)
         kv = ctx_kv[s.key]
         ops.attention(q2, kv[:, :Cc], kv[:, Cc:], att, B, s.heads, N, ctx_len, s.d)
-        ops.linear(att, s.out2.w, a, bias=s.out2.bias, res=b)
+        ops.linear(att, s.out2.w, a, bias=s.out2.bias, res=b, **lnk(0))
         # feed-forward (GEGLU)
         gg = self.buf("t_gg", M, 4 * Cc)
         if fold:
-            ops.layer_norm_stats(a, st)
-            ops.linear(a, s.ff1_geglu.w, gg, bias=s.ff1_geglu.bias, act=PD_ACT_GEGLU, ln_stats=st,
+            ops.linear(a, s.ff1_geglu.w, gg, bias=s.ff1_geglu.bias, act=PD_ACT_GEGLU, ln_parts=lnp[0], ln_rows=M,
                        ln_colsum=s.ff1_geglu.colsum)
         elif s.ff1_geglu is not None:      # bf16: x * gelu(gate) in the GEMM epilogue, the [M, 8C] tensor never exists
             ops.layer_norm(a, ln, s.ln3.gamma, s.ln3.beta)
@@ -212,18 +304,32 @@ class _Net:
             ops.linear(ln, s.ff1.w, ff, bias=s.ff1.bias)
             ops.geglu(ff, gg)
         ops.linear(gg, s.ff2.w, b, bias=s.ff2.bias, res=a)
-        self.conv(s.proj_out, b, out, 1, 1, M, res=x)
+        self.conv(s.proj_out, b, out, 1, 1, M, res=x, stats=(B, N))
         return out
 
     def down(self, pc: PConv, x, out, B, H, W):
-        return self.conv(pc, x, out, B, H, W)
+        return self.conv(pc, x, out, B, H, W, stats=(B, (H // 2) * (W // 2)))
 
     def up(self, pc: PConv, x, out, B, H, W):
-        """Upsample.forward (openaimodel.py:108-118): nearest x2 then conv3x3."""
+        """Upsample.forward (openaimodel.py:108-118): nearest x2 then conv3x3.  bf16 mode: four 2x2 phase convolutions
+        of the LOW-resolution tensor (packing.Packer.up_phases), each writing its quarter of the output pixels through
+        a strided tensor map — 4/9 of the MACs and the 4x tensor is never materialised."""
+        if pc.phases is not None:
+            ld = out.stride(0)
+            sup = self.dt == torch.bfloat16 and (H * W) % 64 == 0 and ops.gn_stats_supported(B, H, W, 2, 1)
+            for py, px, ph in pc.phases:
+                first = (py * 2 * W + px)
+                kw = {}
+                if sup:
+                    kw = dict(stats=(B, 4 * H * W), gn_rec_off=(2 * py + px) * (H * W // 64))
+                self.conv(ph, x, out[first:], B, H, W, pad=(1 - py, 1 - px), out_strides=(2 * ld, 4 * W * ld, 4 * H * W * ld), **kw)
+            if not sup:
+                self.pool.gn_invalidate(out)
+            return out
         if self.dt == torch.bfloat16:
             u = self.buf("t_up", B * 4 * H * W, x.shape[1])
             ops.upsample2x(x, u, B, H, W)
-            return self.conv(pc, u, out, B, 2 * H, 2 * W)
+            return self.conv(pc, u, out, B, 2 * H, 2 * W, stats=(B, 4 * H * W))
         return self.conv(pc, x, out, B, H, W, upsample=True)
 
     def run_block(self, layers, x, out, emb_all, ctx_kv, ctx_len, B, H, W, name):
@@ -245,7 +351,7 @@ class _Net:
                 cur = self.up(l, cur, out, B, H, W)
                 H, W = 2 * H, 2 * W
             else:
-                cur = self.conv(l, cur, out, B, H, W)    # input_blocks.0.0
+                cur = self.conv(l, cur, out, B, H, W, stats=(B, H * W))    # input_blocks.0.0
         return cur, H, W
 
 
@@ -336,7 +442,7 @@ class ControlNet(_Net):
             o = self.buf(f"ctrl.h{i}", B * Ho * Wo, cout)
             if i == 0:
                 # h = conv(x) ; h += guided_hint (cldm.py:314-317) -> residual in the conv epilogue
-                self.conv(blk[0], cur, o, B, Hh, Ww, res=hint)
+                self.conv(blk[0], cur, o, B, Hh, Ww, res=hint, stats=(B, Hh * Ww))
             else:
                 self.run_block(blk, cur, o, emb_all, kv, ctx_len, B, Hh, Ww, f"ctrl.b{i}")
             cur, Hh, Ww = o, Ho, Wo
@@ -349,8 +455,7 @@ class ControlNet(_Net):
     def forward(self, x, timesteps, example_pair, query, context, **kwargs) -> List[torch.Tensor]:
         B, Cx, H, W = x.shape
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
-        x_pm = self.latent_buffer("ctrl.x", B * H * W, Cx)
-        ops.nchw_to_nhwc(x, x_pm)
+        x_pm = self.load_latent("ctrl.x", x)
         outs: List[torch.Tensor] = []
 
         def sink(i, h, Hh, Ww, pc):
@@ -419,26 +524,39 @@ class ControlledUnetModel(_Net):
                 o = self.buf("unet.hfinal", B * Ho * Wo, blk[0].cout)
             self.run_block(blk, full, o, st.emb_all, st.kv, st.ctx_len, B, Hj, Wj, f"unet.out{j}")
         M = B * st.H * st.W
-        g = self.buf("t_gn", M, self.cfg.model_channels)
-        ops.group_norm(o, g, w.out_norm.gamma, w.out_norm.beta, B, st.H * st.W, eps=1e-5, act=PD_ACT_SILU)
-        eps_full = self.buf("unet.eps", M, w.out_conv.cout_pad, torch.float32)
-        self.conv(w.out_conv, g, eps_full, B, st.H, st.W)
-        return eps_full[:, :self.cfg.out_channels]
+        mc, oc = self.cfg.model_channels, self.cfg.out_channels
+        if w.out_conv.split == "out" and self.gn_ready(o, B, st.H * st.W):
+            # split precision: GroupNorm+SiLU writes (hi | lo) bf16 columns, the conv's rows [0, oc) carry w_hi against
+            # both halves and rows [oc, 2 oc) carry w_lo against the hi half; their sum is eps at ~16 mantissa bits
+            g = self.buf("t_gn2", M, 2 * mc)
+            self.gn(o, g, w.out_norm, B, st.H * st.W, 1e-5, PD_ACT_SILU, split=True)
+            eps_full = self.buf("unet.eps", M, w.out_conv.cout_pad, torch.float32)
+            self.conv(w.out_conv, g, eps_full, B, st.H, st.W)
+            ops.add2d(eps_full[:, :oc], eps_full[:, oc:2 * oc], eps_full[:, :oc])
+            return eps_full[:, :oc]
+        pc = w.out_conv if w.out_conv.split is None else w.out_conv_plain
+        g = self.buf("t_gn", M, mc)
+        self.gn(o, g, w.out_norm, B, st.H * st.W, 1e-5, PD_ACT_SILU)
+        eps_full = self.buf("unet.eps", M, pc.cout_pad, torch.float32)
+        self.conv(pc, g, eps_full, B, st.H, st.W)
+        return eps_full[:, :oc]
 
     @_on_device
     def forward(self, x, timesteps=None, context=None, control=None, only_mid_control=False, **kwargs):
         B, Cx, H, W = x.shape
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
-        x_pm = self.latent_buffer("unet.x", B * H * W, Cx)
-        ops.nchw_to_nhwc(x, x_pm)
+        x_pm = self.load_latent("unet.x", x)
         st = self.encode(x_pm, _to_dev_i64(timesteps, self.device), [context], B, H, W)
         if control is not None:
             # h += control.pop() ; cat([h, hs.pop() + control.pop()]) — the caller's list is consumed
+            # externally supplied NCHW controls are added by a layout kernel that emits no GroupNorm statistics
             ops.nchw_to_nhwc(control.pop().to(self.device, torch.float32).contiguous(), st.cats[0][1], accumulate=True)
+            self.pool.gn_invalidate(st.cats[0][1])
             if not only_mid_control:
                 for j in range(len(self.w.output_blocks)):
                     ops.nchw_to_nhwc(control.pop().to(self.device, torch.float32).contiguous(), st.cats[j][2],
                                      accumulate=True)
+                    self.pool.gn_invalidate(st.cats[j][2])
         eps_pm = self.decode(st)
         return ops.nhwc_to_nchw(eps_pm, B, self.cfg.out_channels, H, W)
 
@@ -541,8 +659,7 @@ class ControlLDM:
         ctx_list = list(cond["c_crossattn"])
         B, Cx, H, W = x_noisy.shape
         x = x_noisy.to(device=self.device, dtype=torch.float32).contiguous()
-        x_pm = unet.latent_buffer("ldm.x", B * H * W, Cx)
-        ops.nchw_to_nhwc(x, x_pm)
+        x_pm = unet.load_latent("ldm.x", x)
         t_dev = _to_dev_i64(t, self.device)
         eps_pm = self._denoise_pm(x_pm, t_dev, ctx_list, list(cond["example_pair"]), cond["query"][0], B, H, W)
         eps = ops.nhwc_to_nchw(eps_pm, B, self.cfg.out_channels, H, W)
@@ -576,7 +693,7 @@ class ControlLDM:
                 return
             else:                                           # hs[i] + control[i], consumed by output block 11-i
                 slot = st.cats[nblk - 1 - i][2]
-            ctrl.conv(pc, h, slot, 1, 1, B * Hh * Ww, res=slot, alpha=scales[i])
+            ctrl.conv(pc, h, slot, 1, 1, B * Hh * Ww, res=slot, alpha=scales[i], stats=(B, Hh * Ww))
 
         ctrl._run(x_pm, t_dev, pair_list, query, ctx_list, B, H, W, sink)
         return unet.decode(st)

@@ -240,7 +240,11 @@ int pd_conv2d(const pd_conv_params* p, void* stream) {
   PD_REQUIRE(p != nullptr, "pd_conv2d: null params");
   PD_REQUIRE(p->x && p->w && p->out, "pd_conv2d: null tensor");
   PD_REQUIRE(p->B > 0 && p->H > 0 && p->W > 0 && p->C > 0 && p->Cout > 0, "pd_conv2d: bad geometry");
-  PD_REQUIRE(p->ksize == 1 || p->ksize == 3, "pd_conv2d: ksize must be 1 or 3 (got %d)", p->ksize);
+  PD_REQUIRE(p->ksize == 1 || p->ksize == 3 || p->ksize == 2, "pd_conv2d: ksize must be 1, 3 or 2 (got %d)", p->ksize);
+  const bool tc_only = p->ksize == 2 || p->ln_parts != nullptr || p->ln_parts_out != nullptr || p->gn_stats_out != nullptr ||
+                       p->out_sx != 0 || p->out_sy != 0 || p->out_sb != 0;
+  PD_REQUIRE(p->ksize != 2 || (p->stride == 1 && !p->upsample && (p->pad_y == 0 || p->pad_y == 1) && (p->pad_x == 0 || p->pad_x == 1)),
+             "pd_conv2d: ksize 2 needs stride 1, no upsample flag and pad_y / pad_x in {0, 1}");
   PD_REQUIRE(p->stride == 1 || p->stride == 2, "pd_conv2d: stride must be 1 or 2 (got %d)", p->stride);
   PD_REQUIRE(!(p->upsample && p->stride != 1), "pd_conv2d: upsample with stride 2 is not a path op");
   PD_REQUIRE(p->C2 >= 0 && (p->C2 == 0 || p->x2 != nullptr), "pd_conv2d: C2 > 0 needs x2");
@@ -266,6 +270,17 @@ int pd_conv2d(const pd_conv_params* p, void* stream) {
   if (p->w_blocked && p->engine == PD_ENGINE_SIMT) {
     set_error("pd_conv2d: k-block-major weights (w_blocked) are read by the tcgen05 engine only");
     return PD_ERR_UNSUPPORTED;
+  }
+  if (tc_only) {
+    // phase convolutions, strided output and the statistics hand-off exist on the tcgen05 engine only: never a silent
+    // fall-back to a kernel that would ignore them
+    const char* why_tc = "";
+    if (p->engine == PD_ENGINE_SIMT || !conv2d_tc_supported(p, &why_tc)) {
+      set_error("pd_conv2d: ksize 2 / strided output / ln_parts / gn_stats_out need the tcgen05 engine%s%s",
+                p->engine == PD_ENGINE_SIMT ? "" : ": ", why_tc);
+      return PD_ERR_UNSUPPORTED;
+    }
+    return conv2d_tc(p, s);
   }
   if (p->engine == PD_ENGINE_SIMT) return conv2d_simt(p, s);
   const char* why = "";

@@ -69,6 +69,34 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__
   }
 }
 
+// NCHW fp32 -> pixel-major bf16 in split precision: columns [0,C) = hi = bf16(x), [C,2C) = lo = bf16(x - hi),
+// [2C,3C) = hi again.  Against weights laid out [w_hi | w_hi | w_lo] the tensor cores then form
+// x_hi w_hi + x_lo w_hi + x_hi w_lo = x w up to 2^-16 relative: the 4-channel latent enters conv_in (both nets)
+// at fp32-like precision for free — its K dimension is zero-padded to 64 channels per tap anyway.
+__global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, bf16* __restrict__ out, int ldo, int B, int C, int HW) {
+  int64_t total = (int64_t)B * HW * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t pix = i / C;
+    int64_t b = pix / HW, p = pix % HW;
+    const float v = x[(b * C + c) * (int64_t)HW + p];
+    const bf16 hi = __float2bfloat16_rn(v);
+    const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    bf16* o = out + pix * ldo + c;
+    o[0] = hi; o[C] = lo; o[2 * C] = hi;
+  }
+}
+
+__global__ void add2d_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ y, int ldy, float* __restrict__ out,
+                             int ldo, int64_t rows, int cols) {
+  int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols;
+    int c = (int)(i % cols);
+    out[r * ldo + c] = x[r * ldx + c] + y[r * ldy + c];
+  }
+}
+
 // pixel-major -> NCHW fp32 through a 32x33 smem transpose tile (coalesced both sides).
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int ldx, float* __restrict__ out, int C,
@@ -306,6 +334,21 @@ int pd_nchw_to_nhwc(const float* x, void* out, int32_t ldo, int32_t B, int32_t C
   else
     PD_REQUIRE(false, "pd_nchw_to_nhwc: bad dtype %d", out_dtype);
   return check_launch("pd_nchw_to_nhwc");
+}
+
+int pd_nchw_to_nhwc_split(const float* x, void* out, int32_t ldo, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
+  PD_REQUIRE(x && out && B > 0 && C > 0 && H > 0 && W > 0 && ldo >= 3 * C, "pd_nchw_to_nhwc_split: bad args (ldo >= 3C)");
+  cudaStream_t s = (cudaStream_t)stream;
+  nchw_to_nhwc_split_kernel<<<grid_for((int64_t)B * C * H * W, 256), 256, 0, s>>>(x, (bf16*)out, ldo, B, C, H * W);
+  return check_launch("pd_nchw_to_nhwc_split");
+}
+
+int pd_add2d(const float* x, int32_t ldx, const float* y, int32_t ldy, float* out, int32_t ldo, int64_t rows, int32_t cols,
+             void* stream) {
+  PD_REQUIRE(x && y && out && rows > 0 && cols > 0 && ldx >= cols && ldy >= cols && ldo >= cols, "pd_add2d: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  add2d_kernel<<<grid_for(rows * cols, 256), 256, 0, s>>>(x, ldx, y, ldy, out, ldo, rows, cols);
+  return check_launch("pd_add2d");
 }
 
 int pd_nhwc_to_nchw(const void* x, int32_t ldx, float* out, int32_t B, int32_t C, int32_t H, int32_t W,

@@ -63,9 +63,21 @@ struct TcArgs {
   int* sk_cnt;                  // stream-K arrival counters [tile][CG], zero between launches (the reducer resets its own)
   const float2* ln_stats;       // folded LayerNorm: (mean, rstd) per GEMM row
   const float* ln_colsum;       // folded LayerNorm: column sums of the gamma-scaled weights
+  const float* ln_parts_in;     // folded LayerNorm, statistics from the PRODUCER's epilogue instead of ln_stats: 16-byte
+                                // header {int parts} then float2 (sum, sumsq) [parts][ln_rows]
+  float ln_inv_c, ln_eps;       // 1 / (LayerNorm width), eps
+  // statistics of THIS launch's output, emitted by the epilogue so that the next norm does not re-read the tensor:
+  float* ln_parts_out;          // LayerNorm row partials, same layout as ln_parts_in (part = n_tile * 2 + epilogue group)
+  long long ln_rows;            // row pitch of the partial arrays (in and out)
+  float* gn_out;                // GroupNorm column partials: float2 (sum, sumsq) [(image * gn_rpi + gn_rec_off + rec)][gn_ld],
+                                // one record per 64 output pixels; this launch's columns start at the pointer
+  int gn_ld, gn_rec_off, gn_rpi;
+  int pad_x, pad_y;             // zero-padding before the first tap (ksize / 2 for the centred 1x1 / 3x3 kernels)
+  int flat;                     // 1x1 stride-1 layer flattened to one long pixel row
   uint32_t idesc;
 };
 
+constexpr int PD_LN_MAX_PARTS = 32;          // LayerNorm row partials a producer may write (2 per N tile)
 constexpr int SK_SLOT_FLOATS = 256 * 128;   // one CTA's half of a partial tile: up to 256 columns x 128 rows
 
 // Work decomposition shared by the three roles of a CTA.  Data-parallel: whole tiles, strided over the workers.
@@ -196,7 +208,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ================= TMA producer (both CTAs of a pair); warp-uniform loop, one elected lane issues =================
     {
       int stage = 0; uint32_t phase = 0;
-      const int pad = a.ksize >> 1;
       PieceIter pit(SK, worker, nworkers, num_tiles, nkb);
       int tile, kb0, kb1, tix = 0;
       for (; pit.next(tile, kb0, kb1); ++tix) {
@@ -230,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           int ac0, ax, ay, wk;
           const CUtensorMap* am;
           if (kb < a.nk0) {
-            am = &map_a0; ac0 = cb * TC_BK; ax = x0 * a.stride + dx - pad; ay = y0 * a.stride + dy - pad; wk = wk0;
+            am = &map_a0; ac0 = cb * TC_BK; ax = x0 * a.stride + dx - a.pad_x; ay = y0 * a.stride + dy - a.pad_y; wk = wk0;
             wk0 += TC_BK;                                  // weights are tap-major, channel-minor: K advances linearly
             if (++cb == a.cpt0) { cb = 0; if (++dx == a.ksize) { dx = 0; ++dy; } }
           } else {
@@ -419,6 +430,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int ns_mine = (nslabs > grp ? 1 : 0) + (nslabs > grp + 2 ? 1 : 0);
     const float alpha = a.alpha;
     const long long sk_units = (long long)num_tiles * nkb;
+    if (!LNF && a.ln_parts_out != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0)
+      *reinterpret_cast<int*>(a.ln_parts_out) = a.n_tiles * 2;       // header: partial count of this launch
     int it = 0;
     PieceIter pit(SK, worker, nworkers, num_tiles, nkb);
     int tile, kb0, kb1;
@@ -442,6 +455,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       // no MMA time to hide an HBM round trip behind).
       auto load_res = [&]() {
         if constexpr (RES) {
+          // with column statistics on, the other warps of the group may still be reading the staging buffers of the
+          // previous tile: nobody refills them before everybody is done
+          if (a.gn_out != nullptr) epi_bar_sync(bar_id);
           if (elected) {
             tma_store_wait_read<0>();
             for (int i = 0; i < ns_mine; ++i) {
@@ -516,6 +532,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           __syncwarp();
           if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
         }
+        if (!LNF && a.ln_parts_out != nullptr && row_ok)      // reached by whole tiles and by the stream-K reducer
+          reinterpret_cast<float2*>(a.ln_parts_out + 4)[(long long)(nt * 2 + grp) * a.ln_rows + m] = make_float2(0.f, 0.f);
         if (RES) res_phase ^= 1u;
         continue;
       }
@@ -529,7 +547,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const float* rvp = nullptr;
       if (RV) rvp = a.rowvec + (row_ok ? (m / a.hw_real) : 0) * a.ldrv;
       float ln_mu = 0.f, ln_rs = 0.f;
-      if (LNF && row_ok) { const float2 st = __ldg(a.ln_stats + m); ln_mu = st.x; ln_rs = st.y; }
+      if (LNF && row_ok) {
+        if (a.ln_parts_in != nullptr) {
+          // (sum, sumsq) partials written by the producing GEMM's epilogue (one per N tile and epilogue group), folded
+          // in a fixed order; mean / variance over the bf16-ROUNDED values the tensor cores read
+          const int parts = __ldg(reinterpret_cast<const int*>(a.ln_parts_in));
+          const float2* pp = reinterpret_cast<const float2*>(a.ln_parts_in + 4) + m;
+          float su = 0.f, sq = 0.f;
+          for (int i = 0; i < parts; ++i) { const float2 v = __ldg(pp + (long long)i * a.ln_rows); su += v.x; sq += v.y; }
+          ln_mu = su * a.ln_inv_c;
+          ln_rs = rsqrtf(fmaxf(sq * a.ln_inv_c - ln_mu * ln_mu, 0.f) + a.ln_eps);
+        } else {
+          const float2 st = __ldg(a.ln_stats + m); ln_mu = st.x; ln_rs = st.y;
+        }
+      }
+      float lnp_s = 0.f, lnp_q = 0.f;      // LayerNorm partial of this thread's row over this group's slabs
       uint32_t v0[64], v1[64];
       // stream-K reducer: pieces of this tile in K order (worker p's piece sits in its slot 0 when the tile is where
       // p's range starts)
@@ -645,8 +677,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
               }
-              sts_bf16x8(cell, pack8(f));
+              const bf16x8 pk = pack8(f);
+              sts_bf16x8(cell, pk);
+              if (!LNF && a.ln_parts_out != nullptr && n0 + col0 + g * 8 < a.Cout) {
+                float rf[8];
+                unpack8(pk, rf);                       // statistics of the values as STORED (bf16-rounded)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { lnp_s += rf[e]; lnp_q = fmaf(rf[e], rf[e], lnp_q); }
+              }
             }
+          }
+        }
+      };
+      // GroupNorm column statistics of slab i, read back from the staging buffer (bf16 as stored) after the group
+      // barrier: warp w of the group owns 16 columns, a lane one column PAIR and one of four row phases; rows are
+      // visited so that the four phases of an instruction sit in distinct swizzle positions (no bank conflicts).
+      // One record per 64 rows (the two halves of a tile may belong to different images).
+      auto col_stats = [&](int i) {
+        const int sl = grp + 2 * i;
+        const int w = sl < n64 ? 64 : 32;
+        const int wq = ew & 3;
+        if (wq * 16 >= w) return;
+        const int c = wq * 16 + 2 * (lane & 7), q = lane >> 3;
+        const int ch = n0 + sl * 64 + c;
+        const uint32_t stg_s = s_u32(gstg + i * 16384);
+        const int chunk = c >> 3, inb = (c & 7) * 2;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int rr = half * 64 + ii * 8 + 2 * q + j;
+              const int off = w == 64 ? rr * 128 + ((chunk ^ (rr & 7)) << 4) + inb : rr * 64 + ((chunk ^ ((rr >> 1) & 3)) << 4) + inb;
+              uint32_t u;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(stg_s + (uint32_t)off));
+              const float v0 = __uint_as_float(u << 16), v1 = __uint_as_float(u & 0xffff0000u);
+              s0 += v0; q0 = fmaf(v0, v0, q0); s1 += v1; q1 = fmaf(v1, v1, q1);
+            }
+          }
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+          }
+          // record of this half tile: image and 64-pixel chunk of its first row
+          const int r0h = half * 64;
+          const int hx = x0 + r0h % a.bw, hy = y0 + (r0h / a.bw) % a.bh, hb = b0 + r0h / (a.bw * a.bh);
+          if (q == 0 && ch < a.Cout && hx < a.Wo && hy < a.Ho && hb < a.B) {
+            // 64-pixel chunks are numbered along the launch's own pixel order; any numbering works as long as every
+            // pixel of an image lands in exactly one record of that image
+            const long long pix = ((long long)hb * a.Ho + hy) * a.Wo + hx;      // first pixel of the half tile
+            const int img = (int)(pix / a.hw_real);
+            int rec;
+            if (a.flat) rec = (int)((pix - (long long)img * a.hw_real) >> 6);                       // flattened 1x1 GEMM
+            else if (a.bn == 1) rec = ((hy / a.bh) * a.tiles_x + hx / a.bw) * 2 + half;             // pixel-box tiles
+            else rec = (hy / a.bh) * a.tiles_x + hx / a.bw;                                         // box spans two images
+            float4* dst = reinterpret_cast<float4*>(a.gn_out + (((long long)img * a.gn_rpi + a.gn_rec_off + rec) * a.gn_ld + ch) * 2);
+            *dst = make_float4(s0, q0, s1, q1);
           }
         }
       };
@@ -704,6 +793,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int i = 0; i < ns_mine; ++i) store_slab(i);
           tma_store_commit();
         }
+        if (a.gn_out != nullptr) {
+          col_stats(0);
+          if (ns_mine > 1) col_stats(1);
+        }
+        if (!LNF && a.ln_parts_out != nullptr && row_ok)
+          reinterpret_cast<float2*>(a.ln_parts_out + 4)[(long long)(nt * 2 + grp) * a.ln_rows + m] = make_float2(lnp_s, lnp_q);
       }
       if (RES) res_phase ^= 1u;
       if (ew == 0 && lane == 0) PD_DBG(2, it, 1);
@@ -848,10 +943,32 @@ bool conv2d_tc_supported(const pd_conv_params* p, const char** why) {
   if (p->act == PD_ACT_GEGLU && (p->out_dtype != PD_BF16 || p->Cout % 64 != 0 || p->res != nullptr || p->rowvec != nullptr ||
                                  p->alpha != 1.0f))
     PD_NO("GEGLU epilogue needs bf16 output, Cout % 64 == 0, no residual / row vector / alpha");
-  if ((p->ln_stats != nullptr) != (p->ln_colsum != nullptr)) PD_NO("ln_stats and ln_colsum go together");
-  if (p->ln_stats && (p->out_dtype != PD_BF16 || p->ksize != 1 || p->stride != 1 || p->C2 != 0 || p->res != nullptr ||
+  if (p->ln_stats != nullptr && p->ln_parts != nullptr) PD_NO("ln_stats and ln_parts are alternatives");
+  const void* ln_in = p->ln_stats != nullptr ? (const void*)p->ln_stats : (const void*)p->ln_parts;
+  if ((ln_in != nullptr) != (p->ln_colsum != nullptr)) PD_NO("ln_stats / ln_parts and ln_colsum go together");
+  if (p->ln_parts && (p->ln_rows < (int64_t)p->B * p->H * p->W || (uintptr_t)p->ln_parts % 16 != 0)) PD_NO("ln_parts: bad ln_rows / alignment");
+  if (p->ln_parts_out && (p->ln_rows <= 0 || (uintptr_t)p->ln_parts_out % 16 != 0 || p->out_dtype != PD_BF16 ||
+                          p->act == PD_ACT_GEGLU || ln_in != nullptr))
+    PD_NO("ln_parts_out needs a bf16, non-GEGLU, non-folded launch with ln_rows set");
+  if (p->gn_stats_out) {
+    const int pad_ = p->ksize / 2;
+    const int Ho_ = p->ksize == 2 ? p->H : (p->H + 2 * pad_ - p->ksize) / p->stride + 1;
+    const int Wo_ = p->ksize == 2 ? p->W : (p->W + 2 * pad_ - p->ksize) / p->stride + 1;
+    if (!pd_conv2d_gn_stats_supported(p->B, Ho_, Wo_, p->ksize, p->stride)) PD_NO("gn_stats_out: output geometry has no 64-pixel records");
+    if (p->out_dtype != PD_BF16 || p->act == PD_ACT_GEGLU || ln_in != nullptr || (uintptr_t)p->gn_stats_out % 16 != 0 ||
+        p->gn_ld < p->Cout || p->gn_ld % 2 != 0 || p->gn_recs_per_image <= 0 || p->gn_rec_off < 0)
+      PD_NO("gn_stats_out needs a bf16, non-GEGLU, non-folded launch, 16-byte aligned records, even gn_ld >= Cout");
+  }
+  if (p->ksize == 2 && (p->stride != 1 || p->C2 != 0)) PD_NO("ksize 2 needs stride 1 and no second K segment");
+  if ((p->out_sx | p->out_sy | p->out_sb) != 0) {
+    if (p->out_sx <= 0 || p->out_sy <= 0 || p->out_sb <= 0 || p->res != nullptr || p->out_dtype != PD_BF16 ||
+        (p->out_sx * 2) % 16 != 0 || (p->out_sy * 2) % 16 != 0 || (p->out_sb * 2) % 16 != 0 || p->out_sx < p->Cout)
+      PD_NO("strided output needs positive 16-byte-aligned strides, bf16 output and no residual");
+    if (p->ksize == 1) PD_NO("strided output is for spatial kernels (1x1 layers are flattened)");
+  }
+  if (ln_in && (p->out_dtype != PD_BF16 || p->ksize != 1 || p->stride != 1 || p->C2 != 0 || p->res != nullptr ||
                       p->rowvec != nullptr || p->alpha != 1.0f || p->bias == nullptr ||
-                      (p->act != PD_ACT_NONE && p->act != PD_ACT_GEGLU) || (uintptr_t)p->ln_stats % 8 != 0 ||
+                      (p->act != PD_ACT_NONE && p->act != PD_ACT_GEGLU) || (uintptr_t)ln_in % 8 != 0 ||
                       (uintptr_t)p->ln_colsum % 16 != 0))
     PD_NO("folded LayerNorm needs a bf16 1x1 layer with bias, act NONE/GEGLU, no residual / row vector / alpha");
   if (p->stride == 2 && p->ksize != 3) PD_NO("stride 2 only with 3x3");
@@ -890,8 +1007,14 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
   const int force_cg = var.cg;
   TcArgs a;
   const int pad = p->ksize / 2;
-  const int Ho = (p->H + 2 * pad - p->ksize) / p->stride + 1;
-  const int Wo = (p->W + 2 * pad - p->ksize) / p->stride + 1;
+  const int Ho = p->ksize == 2 ? p->H : (p->H + 2 * pad - p->ksize) / p->stride + 1;
+  const int Wo = p->ksize == 2 ? p->W : (p->W + 2 * pad - p->ksize) / p->stride + 1;
+  a.pad_x = p->ksize == 2 ? p->pad_x : pad;
+  a.pad_y = p->ksize == 2 ? p->pad_y : pad;
+  a.ln_parts_in = p->ln_parts; a.ln_eps = p->ln_eps; a.ln_inv_c = 1.0f / (float)p->C;
+  a.ln_parts_out = p->ln_parts_out; a.ln_rows = (long long)p->ln_rows;
+  a.gn_out = p->gn_stats_out; a.gn_ld = p->gn_ld; a.gn_rec_off = p->gn_rec_off; a.gn_rpi = p->gn_recs_per_image;
+  a.flat = (p->ksize == 1 && p->stride == 1) ? 1 : 0;
   a.bias = p->bias; a.rowvec = p->rowvec; a.res = p->res; a.out = p->out;
   a.ldr = p->ldr; a.ldo = p->ldo; a.ldrv = p->ldrv; a.act = p->act; a.out_f32 = p->out_dtype == PD_F32;
   a.alpha = p->alpha;
@@ -949,6 +1072,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
       if (g_force_bn != 0 && bn != g_force_bn) continue;
       if (var.bn != 0 && bn != var.bn) continue;
       int n_tiles = (p->Cout + bn - 1) / bn;
+      if (p->ln_parts_out != nullptr && 2 * n_tiles > PD_LN_MAX_PARTS) continue;   // partial slots behind ln_parts_out
       int64_t tiles = (int64_t)((a.m_tiles + cg - 1) / cg) * n_tiles;
       int64_t workers = sms / cg;
       int64_t waves = (tiles + workers - 1) / workers;
@@ -958,6 +1082,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
       if (cost < best_cost - 1e-9) { best_cost = cost; best_bn = bn; best_cg = cg; }
     }
   }
+  if (best_cost >= 1e30) { set_error("conv_tc: no tile width satisfies the launch constraints (BN override %d)", var.bn); return PD_ERR_UNSUPPORTED; }
   const int CGv = best_cg;
   a.BN = best_bn;
   a.n_tiles = (p->Cout + a.BN - 1) / a.BN;
@@ -1014,6 +1139,9 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
       if (base == nullptr) continue;
       const uint64_t ld = which == 0 ? (uint64_t)p->ldo : (uint64_t)p->ldr;
       uint64_t strides[3] = {ld * 2, (uint64_t)gW * ld * 2, (uint64_t)gH * gW * ld * 2};
+      if (which == 0 && p->out_sx != 0) {       // one phase of a 2x upsampled tensor: a plain strided 4-D tensor
+        strides[0] = (uint64_t)p->out_sx * 2; strides[1] = (uint64_t)p->out_sy * 2; strides[2] = (uint64_t)p->out_sb * 2;
+      }
       uint32_t box64[4] = {64, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn};
       uint32_t box32[4] = {32, (uint32_t)a.bw, (uint32_t)a.bh, (uint32_t)a.bn};
       int rc = encode_map(which == 0 ? &map_o64 : &map_r64, base, 4, dims, strides, box64, es, which == 0 ? "O64" : "R64",
@@ -1048,7 +1176,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
         }
     attr_set[dev] = true;
   }
-  const int epi = !a.epi_tma ? 8 : p->ln_stats != nullptr ? (p->act == PD_ACT_GEGLU ? 11 : 10) : p->act == PD_ACT_GEGLU ? 9
+  const int epi = !a.epi_tma ? 8 : (p->ln_stats != nullptr || p->ln_parts != nullptr) ? (p->act == PD_ACT_GEGLU ? 11 : 10) : p->act == PD_ACT_GEGLU ? 9
                   : ((p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0));
   static const float* zero_bias[PD_MAX_DEVICES] = {nullptr};   // the TMA epilogue always adds a bias vector
   if (a.epi_tma && a.bias == nullptr) {
@@ -1146,10 +1274,11 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   if (g_force_cg != 0 || p->out_dtype != PD_BF16 || dbg)
     return conv2d_tc_impl(p, s, TcVariant{g_force_cg, g_force_cg != 0 && g_force_sk ? 2 : 0, 0});
   const int pad = p->ksize / 2;
-  const int Ho = (p->H + 2 * pad - p->ksize) / p->stride + 1, Wo = (p->W + 2 * pad - p->ksize) / p->stride + 1;
+  const int Ho = p->ksize == 2 ? p->H : (p->H + 2 * pad - p->ksize) / p->stride + 1;
+  const int Wo = p->ksize == 2 ? p->W : (p->W + 2 * pad - p->ksize) / p->stride + 1;
   const TuneKey key{p->B * Ho * Wo, p->Cout, p->ksize * p->ksize * p->C + p->C2, p->ksize, p->stride, p->C2 > 0 ? 1 : 0,
                     (p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0) |
-                        (p->act == PD_ACT_GEGLU ? 8 : 0) | (p->ln_stats != nullptr ? 16 : 0)};
+                        (p->act == PD_ACT_GEGLU ? 8 : 0) | ((p->ln_stats != nullptr || p->ln_parts != nullptr) ? 16 : 0)};
   {
     std::lock_guard<std::mutex> lk(g_mu);
     tune_load_locked();
@@ -1211,6 +1340,13 @@ int pd_debug_timeline(void* dev_buf) { pd::g_dbg = (unsigned long long*)dev_buf;
 // timing experiments (results WRONG when non-zero): pipeline stages switched off, see TcArgs::dbg_mode
 int pd_debug_gemm_mode(int mode) { pd::g_dbg_mode = mode; return 0; }
 #endif
+int64_t pd_conv2d_ln_parts_floats(int64_t rows) { return 4 + (int64_t)pd::PD_LN_MAX_PARTS * 2 * rows; }
+int pd_conv2d_gn_stats_supported(int32_t B, int32_t Ho, int32_t Wo, int32_t ksize, int32_t stride) {
+  if (B <= 0 || Ho <= 0 || Wo <= 0 || ((int64_t)Ho * Wo) % 64 != 0) return 0;
+  if (ksize == 1 && stride == 1) return 1;                       // flattened: 128 consecutive pixels per tile
+  const int bw = pd::pow2_divisor(Wo, 128), bh = pd::pow2_divisor(Ho, 128 / bw);
+  return bw * bh >= 64 ? 1 : 0;                                  // a tile holds whole 64-pixel records of one image each
+}
 // tile order of the tcgen05 engine: 1 = N tiles of an M tile adjacent (default), 0 = M tiles of an N tile adjacent
 int pd_debug_tile_order(int n_fast) { pd::g_n_fast = n_fast != 0; return 0; }
 // Writes the launch-variant cache (committed table rows + shapes tuned under PD_B200_AUTOTUNE=1) as tune_table.inc rows.

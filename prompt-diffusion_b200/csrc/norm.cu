@@ -376,6 +376,112 @@ gn_fused_kernel(const T* __restrict__ x, int ldx, TO* __restrict__ out, int ldo,
   }
 }
 
+
+// ---- GroupNorm from producer statistics ------------------------------------------------------------------------
+// The GEMM that produced x already emitted (sum, sum of squares) per (64-pixel record, channel) from its epilogue
+// (pd_conv_params.gn_stats_out), so the tensor is streamed ONCE here: a tiny finalize kernel folds the records of
+// every (image, group) in a fixed order (double accumulation -> deterministic), then the apply kernel normalises.
+__global__ void __launch_bounds__(128)
+gn_finalize_kernel(const float* __restrict__ colstats, int ld, int rpi, int C, int groups, int HW, float eps,
+                   float* __restrict__ stats) {
+  __shared__ double sh_s[128], sh_q[128];
+  griddep_wait();
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / groups;
+  const int items = rpi * cpg;
+  const float2* base = reinterpret_cast<const float2*>(colstats) + (int64_t)b * rpi * ld + g * cpg;
+  double su = 0.0, sq = 0.0;
+  for (int i = threadIdx.x; i < items; i += 128) {
+    const int rec = i / cpg, c = i - rec * cpg;
+    const float2 v = __ldg(base + (int64_t)rec * ld + c);
+    su += (double)v.x; sq += (double)v.y;
+  }
+  sh_s[threadIdx.x] = su; sh_q[threadIdx.x] = sq;
+  __syncthreads();
+#pragma unroll
+  for (int o = 64; o > 0; o >>= 1) {                 // fixed tree: the result does not depend on scheduling
+    if (threadIdx.x < o) { sh_s[threadIdx.x] += sh_s[threadIdx.x + o]; sh_q[threadIdx.x] += sh_q[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = (double)HW * (double)cpg;
+    const double mean = sh_s[0] / n;
+    double var = sh_q[0] / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((int64_t)b * GN_GROUPS_MAX + g) * 2] = (float)mean;
+    stats[((int64_t)b * GN_GROUPS_MAX + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+// y = act(x * a + bt), a = rstd * gamma, bt = beta - mean * a; bf16 in, bf16 out, four rows in flight per thread.
+// SPLIT: y is written as a (hi, lo) pair of bf16 tensors, hi = bf16(y) at column c and lo = bf16(y - hi) at column
+// C + c: a consumer GEMM over the 2C columns sees y to ~16 mantissa bits (used in front of the UNet's `out` conv,
+// whose operand rounding alone is a quarter of the bf16-mode eps error).
+template <bool SPLIT>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_stream_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int ldo, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, const float* __restrict__ stats, int HW, int C, int groups, int act,
+                       int row_blocks) {
+  constexpr int V = 8;
+  __shared__ float s_g[2 * GN_GROUPS_MAX];
+  const int b = blockIdx.y;
+  const int cpg = C / groups;
+  const GnGrid g = gn_grid(C, V);
+  const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
+  griddep_wait();
+  if (threadIdx.x < 2 * groups) s_g[threadIdx.x] = stats[(int64_t)b * GN_GROUPS_MAX * 2 + threadIdx.x];
+  __syncthreads();
+  if (ty >= g.ty_n) return;
+  const int rows_per = (HW + row_blocks - 1) / row_blocks;
+  const int r0 = blockIdx.x * rows_per;
+  const int r1 = min(HW, r0 + rows_per);
+  for (int ps = 0; ps < g.passes; ++ps) {
+    const int j = tx + ps * g.tx_n;
+    if (j >= g.vpr) break;
+    const int c0 = j * V;
+    float a[V], bt[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int gi = (c0 + k) / cpg;
+      a[k] = s_g[2 * gi + 1] * gamma[c0 + k];
+      bt[k] = fmaf(-s_g[2 * gi], a[k], beta[c0 + k]);
+    }
+    const bf16* xc = x + (int64_t)b * HW * ldx + c0;
+    bf16* oc = out + (int64_t)b * HW * ldo + c0;
+    auto emit = [&](int r, float (&f)[V]) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float y = fmaf(f[k], a[k], bt[k]);
+        if (act == PD_ACT_SILU) y = silu_f(y);
+        f[k] = y;
+      }
+      const bf16x8 hi = pack8(f);
+      *reinterpret_cast<bf16x8*>(oc + (int64_t)r * ldo) = hi;
+      if (SPLIT) {
+        float h[V];
+        unpack8(hi, h);
+#pragma unroll
+        for (int k = 0; k < V; ++k) h[k] = f[k] - h[k];
+        *reinterpret_cast<bf16x8*>(oc + (int64_t)r * ldo + C) = pack8(h);
+      }
+    };
+    int r = r0 + ty;
+    for (; r + 3 * g.ty_n < r1; r += 4 * g.ty_n) {
+      float f0[V], f1[V], f2[V], f3[V];
+      unpack8(*reinterpret_cast<const bf16x8*>(xc + (int64_t)r * ldx), f0);
+      unpack8(*reinterpret_cast<const bf16x8*>(xc + (int64_t)(r + g.ty_n) * ldx), f1);
+      unpack8(*reinterpret_cast<const bf16x8*>(xc + (int64_t)(r + 2 * g.ty_n) * ldx), f2);
+      unpack8(*reinterpret_cast<const bf16x8*>(xc + (int64_t)(r + 3 * g.ty_n) * ldx), f3);
+      emit(r, f0); emit(r + g.ty_n, f1); emit(r + 2 * g.ty_n, f2); emit(r + 3 * g.ty_n, f3);
+    }
+    for (; r < r1; r += g.ty_n) {
+      float f0[V];
+      unpack8(*reinterpret_cast<const bf16x8*>(xc + (int64_t)r * ldx), f0);
+      emit(r, f0);
+    }
+  }
+}
+
 // ---- LayerNorm -------------------------------------------------------------------------
 // One warp per row; NV = vectors per lane (compile-time), so the row sits in registers and the
 // loads of a row are all issued before the first use.  C in {320, 640, 1280} -> NV in {2, 3, 5} (bf16).
@@ -687,6 +793,41 @@ int pd_group_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const floa
   if (dtype == PD_F32 && out_dtype == PD_BF16)
     return gn_launch<float, bf16>(x, ldx, out, ldo, gamma, beta, partial, B, HW, C, groups, eps, act, s);
   PD_REQUIRE(false, "pd_group_norm: unsupported dtypes %d -> %d", dtype, out_dtype);
+}
+
+int pd_group_norm_apply(const void* x, int32_t ldx, void* out, int32_t ldo, const float* gamma, const float* beta,
+                        const float* colstats, int32_t stats_ld, int32_t recs_per_image, float* scratch, int32_t B,
+                        int32_t HW, int32_t C, int32_t groups, float eps, int32_t act, int32_t split, void* stream) {
+  PD_REQUIRE(x && out && gamma && beta && colstats && scratch, "pd_group_norm_apply: null pointer");
+  PD_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0 && groups <= GN_GROUPS_MAX && C % groups == 0 && B <= 65535,
+             "pd_group_norm_apply: bad geometry B=%d HW=%d C=%d groups=%d", B, HW, C, groups);
+  PD_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && ldx >= C && ldo >= (split ? 2 * C : C) &&
+                 ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0,
+             "pd_group_norm_apply: bf16 tensors with 16-byte aligned rows (C, pitches multiples of 8; ldo >= 2C when split)");
+  PD_REQUIRE(HW % 64 == 0 && recs_per_image == HW / 64 && stats_ld >= C && ((uintptr_t)colstats % 8) == 0,
+             "pd_group_norm_apply: one statistics record per 64 pixels (HW=%d, records=%d)", HW, recs_per_image);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = launch_pdl(gn_finalize_kernel, dim3((unsigned)groups, (unsigned)B), dim3(128), 0, s, 1, colstats,
+                             (int)stats_ld, (int)recs_per_image, (int)C, (int)groups, (int)HW, eps, scratch);
+  if (e != cudaSuccess) { set_error("pd_group_norm_apply: finalize launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+  int rc = check_launch("gn_finalize");
+  if (rc) return rc;
+  // ~4 CTAs of 512 threads per SM over (row_blocks, B); at least one pass of the thread grid per CTA
+  const GnGrid gg = gn_grid(C, 8);
+  int row_blocks = (num_sms() * 4 + B - 1) / B;
+  int max_rb = (HW + 4 * gg.ty_n - 1) / (4 * gg.ty_n);
+  if (row_blocks > max_rb) row_blocks = max_rb;
+  if (row_blocks < 1) row_blocks = 1;
+  if (split)
+    e = launch_pdl(gn_apply_stream_kernel<true>, dim3((unsigned)row_blocks, (unsigned)B), dim3(GN_THREADS), 0, s, 1,
+                   (const bf16*)x, (int)ldx, (bf16*)out, (int)ldo, gamma, beta, (const float*)scratch, (int)HW, (int)C,
+                   (int)groups, (int)act, row_blocks);
+  else
+    e = launch_pdl(gn_apply_stream_kernel<false>, dim3((unsigned)row_blocks, (unsigned)B), dim3(GN_THREADS), 0, s, 1,
+                   (const bf16*)x, (int)ldx, (bf16*)out, (int)ldo, gamma, beta, (const float*)scratch, (int)HW, (int)C,
+                   (int)groups, (int)act, row_blocks);
+  if (e != cudaSuccess) { set_error("pd_group_norm_apply: apply launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+  return check_launch("gn_apply_stream");
 }
 
 int pd_layer_norm(const void* x, int32_t ldx, void* out, int32_t ldo, const float* gamma, const float* beta,

@@ -74,11 +74,17 @@ def _cuda(*ts):
 
 
 def conv2d(x, w, out, B, H, W, *, ksize=1, stride=1, upsample=False, bias=None, rowvec=None, res=None,
-           x2=None, act=PD_ACT_NONE, alpha=1.0, engine=PD_ENGINE_AUTO, ln_stats=None, ln_colsum=None):
+           x2=None, act=PD_ACT_NONE, alpha=1.0, engine=PD_ENGINE_AUTO, ln_stats=None, ln_colsum=None,
+           ln_parts=None, ln_parts_out=None, ln_rows=0, ln_eps=1e-5, gn_stats_out=None, gn_ld=0, gn_rec_off=0,
+           gn_recs_per_image=0, pad=None, out_strides=None):
     """out[B*Ho*Wo, Cout] = act(alpha*(conv(x) [+ x2 @ Wskip] + bias) + rowvec[b] + res).
     ``act=PD_ACT_GEGLU``: w / bias hold 2F rows (see ``geglu_interleave``), out has F columns.
-    ``ln_stats`` / ``ln_colsum``: LayerNorm folded into the layer (see ``fold_layer_norm``)."""
-    _cuda(x, w, out, bias, rowvec, res, x2, ln_stats, ln_colsum)
+    ``ln_stats`` / ``ln_colsum``: LayerNorm folded into the layer (see ``fold_layer_norm``); ``ln_parts`` instead of
+    ``ln_stats`` takes the row partials a producing launch wrote through ``ln_parts_out``.
+    ``gn_stats_out`` (fp32 view at this launch's first channel) receives GroupNorm column records, see
+    pd_conv_params.  ``ksize=2`` with ``pad=(py, px)`` and ``out_strides=(sx, sy, sb)`` is one phase of
+    Upsample's nearest-x2 + conv3x3 (``out`` then points at the phase's first pixel)."""
+    _cuda(x, w, out, bias, rowvec, res, x2, ln_stats, ln_colsum, ln_parts, ln_parts_out, gn_stats_out)
     p = ConvParams()
     p.x, p.x2, p.w, p.bias, p.rowvec, p.res, p.out = _p(x), _p(x2), _p(w), _p(bias), _p(rowvec), _p(res), _p(out)
     p.B, p.H, p.W, p.C = B, H, W, x.shape[1]
@@ -94,6 +100,15 @@ def conv2d(x, w, out, B, H, W, *, ksize=1, stride=1, upsample=False, bias=None, 
     p.act, p.dtype, p.out_dtype, p.engine, p.alpha = act, dt_code(x), dt_code(out), engine, float(alpha)
     p.w_blocked = int(bool(getattr(w, "_pd_blocked", False)))
     p.ln_stats, p.ln_colsum = _p(ln_stats), _p(ln_colsum)
+    p.ln_parts, p.ln_parts_out, p.ln_rows, p.ln_eps = _p(ln_parts), _p(ln_parts_out), int(ln_rows), float(ln_eps)
+    p.gn_stats_out, p.gn_ld, p.gn_rec_off, p.gn_recs_per_image = _p(gn_stats_out), int(gn_ld), int(gn_rec_off), int(gn_recs_per_image)
+    if pad is not None:
+        p.pad_y, p.pad_x = int(pad[0]), int(pad[1])
+    if out_strides is not None:
+        p.out_sx, p.out_sy, p.out_sb = (int(v) for v in out_strides)
+    for t in (ln_parts, ln_parts_out, gn_stats_out):
+        if t is not None and t.dtype != torch.float32:
+            raise TypeError("ln_parts / ln_parts_out / gn_stats_out are fp32 buffers")
     if ln_stats is not None and (ln_stats.dtype != torch.float32 or ln_stats.shape != (x.shape[0], 2) or
                                  not ln_stats.is_contiguous() or ln_colsum is None or ln_colsum.dtype != torch.float32 or
                                  ln_colsum.numel() != p.Cout):
@@ -155,16 +170,52 @@ def repack_conv_weight(w_oihw: torch.Tensor, out: torch.Tensor, cin_pad: Optiona
 _gn_scratch = {}
 
 
-def group_norm(x, out, gamma, beta, B, HW, *, groups=32, eps=1e-5, act=PD_ACT_NONE):
+def group_norm(x, out, gamma, beta, B, HW, *, groups=32, eps=1e-5, act=PD_ACT_NONE, scratch=None):
+    """``scratch`` (zero-filled once, pd_group_norm_scratch_floats(B) floats) holds the cooperative kernel's barrier words:
+    pass one per model / stream when several may run GroupNorm concurrently on one device (the model classes pass
+    their pool's); the default is one per (device, B), which is only safe for single-stream use."""
     _cuda(x, out, gamma, beta)
     key = (x.device.index, B)
-    scratch = _gn_scratch.get(key)
+    if scratch is None:
+        scratch = _gn_scratch.get(key)
     if scratch is None:
         scratch = torch.zeros(int(lib.pd_group_norm_scratch_floats(B)), dtype=torch.float32, device=x.device)
         _gn_scratch[key] = scratch
     check(lib.pd_group_norm(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), gamma.data_ptr(), beta.data_ptr(),
                             scratch.data_ptr(), B, HW, x.shape[1], groups, float(eps), act, dt_code(x),
                             dt_code(out), _stream()), "pd_group_norm")
+    return out
+
+
+def ln_parts_floats(rows: int) -> int:
+    """Size (floats) of a LayerNorm row-partial buffer behind ``conv2d(..., ln_parts_out=)`` for ``rows`` rows."""
+    return int(lib.pd_conv2d_ln_parts_floats(int(rows)))
+
+
+_gn_sup = {}
+
+
+def gn_stats_supported(B, Ho, Wo, ksize, stride) -> bool:
+    key = (B, Ho, Wo, ksize, stride)
+    v = _gn_sup.get(key)
+    if v is None:
+        v = bool(lib.pd_conv2d_gn_stats_supported(B, Ho, Wo, ksize, stride))
+        _gn_sup[key] = v
+    return v
+
+
+def group_norm_apply(x, out, gamma, beta, colstats, stats_ld, recs_per_image, scratch, B, HW, *, groups=32, eps=1e-5,
+                     act=PD_ACT_NONE, split=False):
+    """GroupNorm(+SiLU) from the (sum, sumsq) records the producing GEMM epilogues emitted: x is streamed once.
+    ``split``: out has 2C columns (bf16(y) | bf16(y - bf16(y)))."""
+    _cuda(x, out, gamma, beta, colstats, scratch)
+    if x.dtype != torch.bfloat16 or out.dtype != torch.bfloat16 or colstats.dtype != torch.float32 or scratch.dtype != torch.float32:
+        raise TypeError("group_norm_apply: bf16 tensors, fp32 statistics")
+    if scratch.numel() < B * 64:
+        raise ValueError("group_norm_apply: scratch needs B * 64 floats")
+    check(lib.pd_group_norm_apply(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), gamma.data_ptr(), beta.data_ptr(),
+                                  colstats.data_ptr(), int(stats_ld), int(recs_per_image), scratch.data_ptr(), B, HW,
+                                  x.shape[1], groups, float(eps), act, int(bool(split)), _stream()), "pd_group_norm_apply")
     return out
 
 
@@ -291,6 +342,26 @@ def nchw_to_nhwc(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False):
     B, Cc, H, W = x.shape
     check(lib.pd_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), _ld(out), B, Cc, H, W, dt_code(out),
                               int(accumulate), _stream()), "pd_nchw_to_nhwc")
+    return out
+
+
+def nchw_to_nhwc_split(x: torch.Tensor, out: torch.Tensor):
+    """x fp32 [B,C,H,W] -> bf16 out[:, 0:C] = hi, [C:2C] = lo, [2C:3C] = hi (see pd_nchw_to_nhwc_split)."""
+    _cuda(x, out)
+    if x.dtype != torch.float32 or not x.is_contiguous() or out.dtype != torch.bfloat16:
+        raise TypeError("nchw_to_nhwc_split wants a contiguous fp32 NCHW tensor and a bf16 output")
+    B, Cc, H, W = x.shape
+    check(lib.pd_nchw_to_nhwc_split(x.data_ptr(), out.data_ptr(), _ld(out), B, Cc, H, W, _stream()),
+          "pd_nchw_to_nhwc_split")
+    return out
+
+
+def add2d(x, y, out):
+    _cuda(x, y, out)
+    if not (x.dtype == y.dtype == out.dtype == torch.float32):
+        raise TypeError("add2d is fp32")
+    check(lib.pd_add2d(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), out.data_ptr(), _ld(out), x.shape[0], x.shape[1],
+                       _stream()), "pd_add2d")
     return out
 
 

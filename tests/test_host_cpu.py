@@ -43,11 +43,12 @@ def test_conv_params_struct_matches_header():
     names = []
     for line in body.split(";"):
         line = line.strip()
-        m = re.match(r"(const\s+)?(void|float|int32_t)\s*\*?\s*(.+)$", line.replace("typedef struct pd_conv_params {", "").strip())
+        m = re.match(r"(const\s+)?(void|float|int32_t|int64_t)\s*\*?\s*(.+)$", line.replace("typedef struct pd_conv_params {", "").strip())
         if m:
             names += [n.strip(" *") for n in m.group(3).split(",")]
     assert names == [f[0] for f in ConvParams._fields_]
-    assert ctypes.sizeof(ConvParams) == 7 * 8 + 20 * 4 + 2 * 8  # 7 pointers, 19 int32 + float, 2 pointers
+    # 7 pointers, 19 int32 + float, 2 pointers | round 2: 3 pointers, 4 int64, float + 5 int32 (+4 bytes tail padding)
+    assert ctypes.sizeof(ConvParams) == 7 * 8 + 20 * 4 + 2 * 8 + 3 * 8 + 4 * 8 + 6 * 4
 
 
 def test_schedule_matches_reference_golden(golden):

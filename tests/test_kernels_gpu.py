@@ -480,3 +480,201 @@ def test_cfg_ddim_step_bit_exact():
         r_xp = full(a_prev).sqrt() * r_p0 + (1. - full(a_prev) - full(sigma) ** 2).sqrt() * e + full(sigma) * nz * temp
         assert torch.equal(p0, r_p0)
         assert torch.equal(xp, r_xp)
+
+
+# ---- round 2: statistics handed from GEMM epilogues to the norms, phase-decomposed Upsample, split-precision entry ----
+GN_STATS_CASES = [
+    dict(B=2, H=32, W=32, C=320, Cout=320, ksize=3, mode="rowvec"),              # ResBlock conv1 -> gn2 (pixel-box tiles)
+    dict(B=3, H=8, W=8, C=1280, Cout=1280, ksize=3, mode="res"),                 # 8x8 level, odd batch: box spans 2 images
+    dict(B=2, H=16, W=16, C=640, Cout=640, ksize=1, mode="slot"),                # zero conv adding into a concat slot
+    dict(B=2, H=16, W=16, C=128, Cout=192, ksize=3, stride=2, mode="plain"),     # Downsample, partial last N tile
+    dict(B=1, H=64, W=64, C=64, Cout=320, ksize=3, mode="res"),                  # batch 1 with pixel-box tiles
+    dict(B=2, H=24, W=24, C=64, Cout=64, ksize=3, mode="plain"),                 # 768^2 family: 8x8 boxes, 9 records / image
+]
+
+
+def _gn_stats_run(B, H, W, C, Cout, ksize, mode, stride=1, slot_extra=64):
+    """conv2d with gn_stats_out; returns (out view, ws [B, rpi, ld, 2], ld, channel offset, Ho*Wo)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(B * H * W, C, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, ksize * ksize * C, device=DEV, generator=g) / math.sqrt(C * ksize * ksize)).to(torch.bfloat16)
+    bias = torch.randn(Cout, device=DEV, generator=g)
+    Ho, Wo = (H + 2 * (ksize // 2) - ksize) // stride + 1, (W + 2 * (ksize // 2) - ksize) // stride + 1
+    M, HW = B * Ho * Wo, Ho * Wo
+    off = slot_extra if mode == "slot" else 0
+    ld = Cout + off
+    full = torch.randn(M, ld, device=DEV, generator=g).to(torch.bfloat16)
+    out = full[:, off:]
+    ws = torch.zeros(B * (HW // 64) * ld * 2, device=DEV)
+    kw = dict(gn_stats_out=ws[2 * off:], gn_ld=ld, gn_recs_per_image=HW // 64)
+    if mode == "rowvec":
+        kw["rowvec"] = torch.randn(B, Cout, device=DEV, generator=g)
+    elif mode == "res":
+        kw["res"] = torch.randn(M, Cout, device=DEV, generator=g).to(torch.bfloat16)
+    elif mode == "slot":
+        kw.update(res=out, alpha=0.5)
+    if ksize == 1:
+        ops.conv2d(x, w, out, 1, 1, B * H * W, ksize=1, bias=bias, **kw)          # flattened, as the model calls 1x1 layers
+    else:
+        ops.conv2d(x, w, out, B, H, W, ksize=ksize, stride=stride, bias=bias, **kw)
+    torch.cuda.synchronize()
+    return out, ws.view(B, HW // 64, ld, 2), ld, off, HW
+
+
+@pytest.mark.parametrize("variant", ["auto", "cg1", "cg2", "cg2+sk"])
+@pytest.mark.parametrize("case", GN_STATS_CASES)
+def test_conv_epilogue_gn_statistics(case, variant):
+    """The (sum, sumsq) records the epilogue writes must add up, per (image, channel), to the sums over the bf16
+    tensor the launch stored (GroupNorm32 statistics, util.py:217-219) — for every tile shape and schedule."""
+    from prompt_diffusion_b200 import _lib
+    if variant != "auto":
+        _lib.lib.pd_debug_force_cta_group(2 if "cg2" in variant else 1)
+        _lib.lib.pd_debug_force_stream_k(1 if "sk" in variant else 0)
+    try:
+        out, ws, ld, off, HW = _gn_stats_run(**case)
+    finally:
+        _lib.lib.pd_debug_force_cta_group(0)
+        _lib.lib.pd_debug_force_stream_k(0)
+    B, Cout = case["B"], case["Cout"]
+    o = out.float().reshape(B, HW, Cout).double()
+    got = ws[:, :, off:off + Cout, :].double().sum(1)                             # [B, Cout, 2]
+    assert torch.allclose(got[..., 0], o.sum(1), rtol=1e-5, atol=2e-3)
+    assert torch.allclose(got[..., 1], (o * o).sum(1), rtol=2e-5, atol=1e-3)
+    if off:
+        assert float(ws[:, :, :off].abs().max()) == 0.0, "records written outside the launch's channel slot"
+
+
+@pytest.mark.parametrize("act", [0, 1])
+@pytest.mark.parametrize("case", GN_STATS_CASES[:4])
+def test_group_norm_from_epilogue_statistics(case, act):
+    """pd_group_norm_apply (records -> finalize -> one streaming pass) against the cooperative two-phase kernel on the
+    same tensor, and against torch's fp32 group_norm; the split (hi | lo) output recovers y to ~16 bits."""
+    ops = _ops()
+    out, ws, ld, off, HW = _gn_stats_run(**case)
+    B, Cout = case["B"], case["Cout"]
+    if Cout % 32:
+        pytest.skip("GroupNorm32 needs C % 32 == 0")
+    g = torch.Generator(device=DEV).manual_seed(3)
+    gamma = 1.0 + 0.2 * torch.randn(Cout, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(Cout, device=DEV, generator=g)
+    scr = torch.empty(B * 64, device=DEV)
+    y_new = torch.empty(B * HW, Cout, device=DEV, dtype=torch.bfloat16)
+    ops.group_norm_apply(out, y_new, gamma, beta, ws.view(-1)[2 * off:], ld, HW // 64, scr, B, HW, eps=1e-5, act=act)
+    y_old = torch.empty_like(y_new)
+    ops.group_norm(out, y_old, gamma, beta, B, HW, eps=1e-5, act=act)
+    ref = F.group_norm(out.float().reshape(B, HW, Cout).permute(0, 2, 1), 32, gamma, beta, 1e-5)
+    ref = (F.silu(ref) if act else ref).permute(0, 2, 1).reshape(B * HW, Cout)
+    assert rel_l2(y_new.float(), ref) < 6e-3
+    assert rel_l2(y_new.float(), y_old.float()) < 3e-3                            # same arithmetic up to fp32 summation order
+    y_split = torch.empty(B * HW, 2 * Cout, device=DEV, dtype=torch.bfloat16)
+    ops.group_norm_apply(out, y_split, gamma, beta, ws.view(-1)[2 * off:], ld, HW // 64, scr, B, HW, eps=1e-5, act=act, split=True)
+    assert torch.equal(y_split[:, :Cout], y_new)
+    assert rel_l2(y_split[:, :Cout].float() + y_split[:, Cout:].float(), ref) < (6e-4 if act else 5e-5)   # silu: tanh.approx
+
+
+@pytest.mark.parametrize("variant", ["auto", "cg2+sk"])
+@pytest.mark.parametrize("M,C", [(4096, 320), (1024, 640), (640, 1280)])
+def test_folded_layer_norm_from_producer_epilogue(M, C, variant):
+    """BasicTransformerBlock's stream (attention.py:271-275): the GEMM that PRODUCES x writes per-row (sum, sumsq)
+    partials from its epilogue; the folded LayerNorm -> Linear that consumes x reads them (ln_parts) instead of a
+    statistics pass.  Checked against the ln_stats route and against torch's LayerNorm -> Linear."""
+    from prompt_diffusion_b200 import _lib
+    from prompt_diffusion_b200._lib import PD_ENGINE_TC
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(9)
+    a0 = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
+    w0 = (torch.randn(C, C, device=DEV, generator=g) / C ** 0.5).to(torch.bfloat16)
+    b0 = torch.randn(C, device=DEV, generator=g) + 2.0                           # rows with a real common offset
+    res = torch.randn(M, C, device=DEV, generator=g).to(torch.bfloat16)
+    x = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    parts = torch.full((ops.ln_parts_floats(M),), float("nan"), device=DEV)
+    if variant != "auto":
+        _lib.lib.pd_debug_force_cta_group(2)
+        _lib.lib.pd_debug_force_stream_k(1)
+    try:
+        ops.linear(a0, w0, x, bias=b0, res=res, engine=PD_ENGINE_TC, ln_parts_out=parts, ln_rows=M)
+    finally:
+        _lib.lib.pd_debug_force_cta_group(0)
+        _lib.lib.pd_debug_force_stream_k(0)
+    torch.cuda.synchronize()
+    nparts = int(parts[:1].view(torch.int32).item())
+    assert 2 <= nparts <= 32
+    pv = parts[4:4 + nparts * M * 2].view(nparts, M, 2).double().sum(0)
+    xf = x.float().double()
+    assert torch.allclose(pv[:, 0], xf.sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(pv[:, 1], (xf * xf).sum(1), rtol=2e-5, atol=1e-3)
+    gamma = 1.0 + 0.3 * torch.randn(C, device=DEV, generator=g)
+    beta = 0.2 * torch.randn(C, device=DEV, generator=g)
+    N = 2 * C
+    w = torch.randn(N, C, device=DEV, generator=g) / C ** 0.5
+    b = torch.randn(N, device=DEV, generator=g)
+    ws, bf, cs = ops.fold_layer_norm(w, b, gamma, beta, torch.bfloat16)
+    y1 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.linear(x, ws.contiguous(), y1, bias=bf.contiguous(), engine=PD_ENGINE_TC, ln_parts=parts, ln_rows=M,
+               ln_colsum=cs.contiguous())
+    stats = torch.empty(M, 2, device=DEV)
+    ops.layer_norm_stats(x, stats)
+    y2 = torch.empty_like(y1)
+    ops.linear(x, ws.contiguous(), y2, bias=bf.contiguous(), engine=PD_ENGINE_TC, ln_stats=stats, ln_colsum=cs.contiguous())
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.t() + b
+    assert rel_l2(y1.float(), ref) < 6e-3
+    assert rel_l2(y1.float(), y2.float()) < 3e-3
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout", [(2, 8, 8, 128, 128), (1, 16, 16, 64, 192), (3, 8, 8, 1280, 1280), (2, 32, 32, 64, 64)])
+def test_upsample_as_four_phase_convs(B, H, W, C, Cout):
+    """Upsample.forward (openaimodel.py:108-118: F.interpolate(x, 2, 'nearest') then conv3x3) == four 2x2 phase
+    convolutions of the low-resolution tensor with pre-summed taps, written through strided tensor maps — against
+    torch's interpolate + conv2d on the same bf16-rounded input with the fp32 weights (error: one bf16 rounding of the
+    summed taps and of the output), with the GroupNorm records of the assembled output checked as well."""
+    from prompt_diffusion_b200.packing import Packer
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x = torch.randn(B, C, H, W, device=DEV, generator=g)
+    w = torch.randn(Cout, C, 3, 3, device=DEV, generator=g) / math.sqrt(9 * C)
+    bias = torch.randn(Cout, device=DEV, generator=g)
+    phases = Packer({"u.weight": w, "u.bias": bias}, "", torch.bfloat16, DEV).up_phases("u")
+    xq = x.to(torch.bfloat16)
+    ref = F.conv2d(F.interpolate(xq.float(), scale_factor=2, mode="nearest"), w, bias, padding=1)
+    ld = Cout + 64
+    full = torch.full((B * 4 * H * W, ld), 7.0, device=DEV, dtype=torch.bfloat16)
+    out = full[:, 64:]
+    HW = 4 * H * W
+    ws = torch.zeros(B * (HW // 64) * ld * 2, device=DEV)
+    sup = ops.gn_stats_supported(B, H, W, 2, 1) and (H * W) % 64 == 0
+    for py, px, ph in phases:
+        kw = dict(gn_stats_out=ws[2 * 64:], gn_ld=ld, gn_recs_per_image=HW // 64, gn_rec_off=(2 * py + px) * (H * W // 64)) if sup else {}
+        ops.conv2d(_pm(xq.float()).to(torch.bfloat16), ph.w, out[py * 2 * W + px:], B, H, W, ksize=2, bias=ph.bias,
+                   pad=(1 - py, 1 - px), out_strides=(2 * ld, 4 * W * ld, 4 * H * W * ld), **kw)
+    torch.cuda.synchronize()
+    assert bool((full[:, :64] == 7.0).all())
+    assert rel_l2(out.float(), _pm(ref)) < 6e-3
+    if sup:
+        o = out.float().reshape(B, HW, Cout).double()
+        got = ws.view(B, HW // 64, ld, 2)[:, :, 64:, :].double().sum(1)
+        assert torch.allclose(got[..., 0], o.sum(1), rtol=1e-5, atol=2e-3)
+        assert torch.allclose(got[..., 1], (o * o).sum(1), rtol=2e-5, atol=1e-3)
+
+
+def test_split_precision_latent_entry():
+    """conv_in (4 -> 320) with the latent as [hi | lo | hi] bf16 columns against [w_hi | w_hi | w_lo] weights: the
+    result matches the fp32 convolution of the UNROUNDED latent to ~1e-5, where plain bf16 operands give ~4e-3."""
+    from prompt_diffusion_b200._lib import PD_ENGINE_TC
+    from prompt_diffusion_b200.packing import Packer
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(6)
+    x = torch.randn(2, 4, 16, 16, device=DEV, generator=g)
+    w = torch.randn(320, 4, 3, 3, device=DEV, generator=g) / 6.0
+    bias = torch.randn(320, device=DEV, generator=g)
+    pc = Packer({"c.weight": w, "c.bias": bias}, "", torch.bfloat16, DEV).split_in_conv("c")
+    x_pm = torch.zeros(2 * 256, 64, device=DEV, dtype=torch.bfloat16)
+    ops.nchw_to_nhwc_split(x, x_pm)
+    assert torch.equal(x_pm[:, 0:4], x_pm[:, 8:12]) and float(x_pm[:, 12:].abs().max()) == 0.0
+    assert rel_l2(x_pm[:, 0:4].float() + x_pm[:, 4:8].float(), _pm(x)) < 2e-5
+    out = torch.empty(512, 320, device=DEV)
+    ops.conv2d(x_pm, pc.w, out, 2, 16, 16, ksize=3, bias=pc.bias, engine=PD_ENGINE_TC)
+    ref = _pm(F.conv2d(x, w, bias, padding=1))
+    plain = _pm(F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, padding=1))
+    e_split, e_plain = rel_l2(out, ref), rel_l2(plain, ref)
+    assert e_split < 5e-5 and e_plain > 20 * e_split, (e_split, e_plain)
