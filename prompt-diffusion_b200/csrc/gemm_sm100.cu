@@ -819,7 +819,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 // Optional per-launch CUDA-event timing of this engine (bench.py's roofline leg; never on in a
 // captured graph): every launch is bracketed by two events on ITS stream and logged with its
 // algorithmic FLOPs (2*M*Cout*K of the layer, padding excluded).
-struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, ksize, stride, BN, m_tiles, n_tiles, stages, grid, cg, sk; };
+struct ProfRec { cudaEvent_t e0, e1; double flops; int M, N, K, ksize, stride, BN, m_tiles, n_tiles, stages, grid, cg, sk, B, H, W, C, C2, act; };
 // Process-wide host state of the engine.  g_mu guards the containers (profile log, tune cache, tensor-map cache);
 // the plain ints are experiment switches set before any launch.
 static std::mutex g_mu;
@@ -1214,6 +1214,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
     rec.M = p->B * Ho * Wo; rec.N = p->Cout; rec.K = p->ksize * p->ksize * p->C + p->C2; rec.ksize = p->ksize;
     rec.stride = p->stride; rec.BN = a.BN; rec.m_tiles = a.m_tiles; rec.n_tiles = a.n_tiles; rec.stages = a.stages;
     rec.grid = grid; rec.cg = CGv; rec.sk = a.sk;
+    rec.B = p->B; rec.H = p->H; rec.W = p->W; rec.C = p->C; rec.C2 = p->C2; rec.act = p->act;
     cudaEventRecord(rec.e0, s);
   }
   {
@@ -1276,9 +1277,9 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   const int pad = p->ksize / 2;
   const int Ho = p->ksize == 2 ? p->H : (p->H + 2 * pad - p->ksize) / p->stride + 1;
   const int Wo = p->ksize == 2 ? p->W : (p->W + 2 * pad - p->ksize) / p->stride + 1;
-  const TuneKey key{p->B * Ho * Wo, p->Cout, p->ksize * p->ksize * p->C + p->C2, p->ksize, p->stride, p->C2 > 0 ? 1 : 0,
-                    (p->res != nullptr ? 1 : 0) | (p->rowvec != nullptr ? 2 : 0) | (p->act == PD_ACT_SILU ? 4 : 0) |
-                        (p->act == PD_ACT_GEGLU ? 8 : 0) | ((p->ln_stats != nullptr || p->ln_parts != nullptr) ? 16 : 0)};
+  // the table is keyed by the GEMM shape; of the epilogue only GEGLU matters (it constrains the tile width)
+  const TuneKey key{p->B * Ho * Wo, p->Cout, p->ksize * p->ksize * p->C + p->C2, p->ksize, p->stride, 0,
+                    p->act == PD_ACT_GEGLU ? 8 : 0};
   {
     std::lock_guard<std::mutex> lk(g_mu);
     tune_load_locked();
@@ -1377,14 +1378,14 @@ int pd_prof_enable(int on) {
 int pd_prof_dump(const char* path) {
   FILE* f = fopen(path, "w");
   if (!f) { pd::set_error("pd_prof_dump: cannot open %s", path); return PD_ERR_BAD_ARG; }
-  fprintf(f, "M,N,K,ksize,stride,BN,m_tiles,n_tiles,stages,grid,cg,sk,ms,tflops\n");
+  fprintf(f, "M,N,K,ksize,stride,BN,m_tiles,n_tiles,stages,grid,cg,sk,ms,tflops,B,H,W,C,C2,act\n");
   std::lock_guard<std::mutex> lk(pd::g_mu);
   for (auto& r : pd::g_prof) {
     float t = 0.f;
     cudaEventSynchronize(r.e1);
     cudaEventElapsedTime(&t, r.e0, r.e1);
-    fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.5f,%.1f\n", r.M, r.N, r.K, r.ksize, r.stride, r.BN, r.m_tiles,
-            r.n_tiles, r.stages, r.grid, r.cg, r.sk, t, r.flops / (t * 1e-3) / 1e12);
+    fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.5f,%.1f,%d,%d,%d,%d,%d,%d\n", r.M, r.N, r.K, r.ksize, r.stride, r.BN, r.m_tiles,
+            r.n_tiles, r.stages, r.grid, r.cg, r.sk, t, r.flops / (t * 1e-3) / 1e12, r.B, r.H, r.W, r.C, r.C2, r.act);
   }
   fclose(f);
   return 0;

@@ -2,12 +2,13 @@
 GEMM engine).
 
 On a B200 (gpurun):   PD_B200_AUTOTUNE=1 python scripts/make_tune_table.py --dump gpurun_out/tune_dump.inc
-    runs one apply_model of every workload shape the tests / bench use (and a VAE decode) with the opt-in timing
-    autotune on, then writes the chosen variants with pd_tune_dump.
+    records the GEMM shapes of one apply_model per workload (pd_prof), then launches every unique shape once on
+    synthetic operands with the opt-in timing autotune on and writes the winners with pd_tune_dump.
 Here (no GPU):        python scripts/make_tune_table.py --install gpurun_out/tune_dump.inc
     copies the dump into csrc/tune_table.inc (sorted, with a header); rebuild afterwards.
 """
 import argparse
+import csv
 import os
 import sys
 
@@ -18,50 +19,61 @@ TABLE = os.path.join(REPO, "prompt-diffusion_b200", "csrc", "tune_table.inc")
 ap = argparse.ArgumentParser()
 ap.add_argument("--dump")
 ap.add_argument("--install")
-ap.add_argument("--keep-default", action="store_true", help="also keep rows equal to the cost-model default")
+ap.add_argument("--workloads", default="8x512,16x768,1x512,1x768,1x256")
 a = ap.parse_args()
 
 if a.install:
     rows = sorted(set(l.strip() for l in open(a.install) if l.strip().startswith("{{")),
                   key=lambda l: [int(x) for x in l.replace("{", "").replace("}", "").split(",") if x.strip()])
     with open(TABLE, "w") as f:
-        f.write("// {{M, N, K, ksize, stride, has_x2, epilogue flags}, {cta_group, stream_k, BN override}} — generated on a B200 by\n"
-                "// scripts/make_tune_table.py (PD_B200_AUTOTUNE=1 timing of every layer shape of configs 1/2/4, the test slices\n"
-                "// and the first-stage decoder); committed so that the launch variant never depends on timing noise.\n")
+        f.write("// {{M, N, K, ksize, stride, 0, 8 if GEGLU epilogue}, {cta_group, stream_k, BN override}} — generated on a B200 by\n"
+                "// scripts/make_tune_table.py (PD_B200_AUTOTUNE=1 timing of every GEMM shape of the listed workloads); committed so\n"
+                "// that the launch variant, and with it the fp32 summation order, never depends on timing noise.\n")
         for r in rows:
             f.write(r + "\n")
     print(f"installed {len(rows)} rows into {TABLE}")
     sys.exit(0)
 
 import torch  # noqa: E402
-from prompt_diffusion_b200 import CLDM_V15 as cfg, ControlLDM, _lib  # noqa: E402
+from prompt_diffusion_b200 import CLDM_V15 as cfg, ControlLDM, _lib, ops  # noqa: E402
+from prompt_diffusion_b200._lib import PD_ACT_GEGLU  # noqa: E402
 from prompt_diffusion_b200.synth import make_conds, synthetic_inputs, synthetic_state_dict  # noqa: E402
 
 assert os.environ.get("PD_B200_AUTOTUNE") == "1", "run with PD_B200_AUTOTUNE=1"
 torch.set_grad_enabled(False)
 dev = "cuda:0"
-sd = synthetic_state_dict(cfg, seed=0)
-model = ControlLDM(cfg, mode="bf16", device=dev).load_state_dict(sd)
-for b, size in ((8, 512), (1, 512), (2, 512), (16, 768), (1, 768), (1, 256), (2, 64), (1, 128), (2, 128), (1, 64)):
+model = ControlLDM(cfg, mode="bf16", device=dev).load_state_dict(synthetic_state_dict(cfg, seed=0))
+shapes = {}
+tmp = a.dump + ".shapes.csv"
+for wl in a.workloads.split(","):
+    b, size = (int(v) for v in wl.split("x"))
     inp = {k: v.to(dev) for k, v in synthetic_inputs(cfg, b, size, size, seed=2).items()}
     cond, un = make_conds(inp)
     x_in = torch.cat([inp["x_T"]] * 2)
     c_in = {k: [torch.cat([un[k][0], cond[k][0]])] for k in cond}
     t = torch.full((2 * b,), 501, device=dev, dtype=torch.long)
+    model.apply_model(x_in, t, c_in)                    # warm: caches, buffers (profiled calls never tune)
+    _lib.lib.pd_prof_enable(1)
     model.apply_model(x_in, t, c_in)
-    if size in (128, 64, 256):                       # unguided shapes of the tests (B_eff = b)
-        model.apply_model(inp["x_T"], t[:b], cond)
     torch.cuda.synchronize()
-    print("tuned", b, size, flush=True)
-try:
-    from prompt_diffusion_b200.autoencoder import AutoencoderKLDecoder
-    from prompt_diffusion_b200.synth import synthetic_vae_state_dict
-    vae = AutoencoderKLDecoder("bf16", dev).load_state_dict(synthetic_vae_state_dict(seed=0))
-    for b, hw in ((8, 64), (1, 32), (2, 16)):
-        vae.decode(torch.randn(b, 4, hw, hw, device=dev))
-        torch.cuda.synchronize()
-        print("tuned vae", b, hw, flush=True)
-except Exception as e:                                   # the decoder is a neighbour of the path, not the path
-    print("vae tuning skipped:", e)
+    _lib.lib.pd_prof_dump(tmp.encode())
+    _lib.lib.pd_prof_enable(0)
+    for r in csv.DictReader(open(tmp)):
+        key = tuple(int(r[k]) for k in ("B", "H", "W", "C", "C2", "N", "ksize", "stride", "act"))
+        shapes[key] = shapes.get(key, 0) + 1
+    print("recorded", wl, len(shapes), "unique shapes so far", flush=True)
+del model
+torch.cuda.empty_cache()
+g = torch.Generator(device=dev).manual_seed(0)
+for (B, H, W, C, C2, N, ks, st, act) in sorted(shapes):
+    Ho, Wo = (H, W) if ks == 2 else ((H + 2 * (ks // 2) - ks) // st + 1, (W + 2 * (ks // 2) - ks) // st + 1)
+    x = torch.randn(B * H * W, C, device=dev, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, ks * ks * C + C2, device=dev, generator=g) * 0.02).to(torch.bfloat16)
+    x2 = torch.randn(B * Ho * Wo, C2, device=dev, generator=g).to(torch.bfloat16) if C2 else None
+    out = torch.empty(B * Ho * Wo, N // 2 if act == PD_ACT_GEGLU else N, device=dev, dtype=torch.bfloat16)
+    bias = torch.zeros(N, device=dev)
+    kw = dict(pad=(1, 1)) if ks == 2 else {}
+    ops.conv2d(x, w, out, B, H, W, ksize=ks, stride=st, bias=bias, x2=x2, act=act if act == PD_ACT_GEGLU else 0, **kw)
+    torch.cuda.synchronize()
 _lib.check(_lib.lib.pd_tune_dump(a.dump.encode()), "pd_tune_dump")
-print("dumped", a.dump)
+print("tuned", len(shapes), "shapes; dumped", a.dump)
