@@ -33,6 +33,14 @@ from ..synth import CTRL_PREFIX, UNET_PREFIX
 
 _MODES = {"bf16": torch.bfloat16, "fp32": torch.float32}
 
+# Statistics hand-off from GEMM epilogues to the norms (bf16 mode).  Emitting them costs epilogue issue slots: free
+# behind a long main loop (3x3 convs, K >= ~1000), not free on the short-K 1x1 layers whose epilogue IS the critical
+# path.  GN_STATS_MIN_K: only launches whose K extent reaches it emit GroupNorm records (their consumers stream once;
+# other GroupNorm inputs take the two-phase kernel).  LN_PARTS: LayerNorm row partials from the producing GEMM
+# (False: separate pd_layer_norm_stats pass).  Values measured on B200 at config 2, see DESIGN.md.
+GN_STATS_MIN_K = 0
+LN_PARTS = True
+
 
 _on_device = ops.on_device
 
@@ -165,8 +173,10 @@ class _Net:
         if stats is not None:
             Ho, Wo = (H, W) if ks == 2 else ((H + 2 * (ks // 2) - ks) // st + 1, (W + 2 * (ks // 2) - ks) // st + 1)
             sB, sHW = stats
+            x2 = kw.get("x2")
+            ktot = ks * ks * x.shape[1] + (0 if x2 is None else x2.shape[1])
             ok = (self.dt == torch.bfloat16 and out.dtype == torch.bfloat16 and x.shape[1] % 64 == 0 and out.shape[1] % 8 == 0
-                  and sHW % 64 == 0 and kw.get("act", PD_ACT_NONE) != PD_ACT_GEGLU
+                  and sHW % 64 == 0 and kw.get("act", PD_ACT_NONE) != PD_ACT_GEGLU and ktot >= GN_STATS_MIN_K
                   and ops.gn_stats_supported(B, Ho, Wo, ks, st))
             if ok:
                 key, ws, pitch = self.pool.gn_ws(out, sB, sHW)
@@ -265,14 +275,22 @@ class _Net:
         fold = s.ln_folded
         # Folded LayerNorms take their row statistics from the epilogue of the GEMM that PRODUCES the stream
         # (ln_parts_out -> ln_parts): no statistics pass over the tensor at all.
-        lnp = [self.buf(f"t_lnp{i}", 1, ops.ln_parts_floats(M), dtype=torch.float32).view(-1) for i in (0, 1)] if fold else None
-        lnk = (lambda i: dict(ln_parts_out=lnp[i], ln_rows=M)) if fold else (lambda i: {})
+        parts = fold and LN_PARTS
+        lnp = [self.buf(f"t_lnp{i}", 1, ops.ln_parts_floats(M), dtype=torch.float32).view(-1) for i in (0, 1)] if parts else None
+        st = self.buf("t_lnstats", M, 2, dtype=torch.float32) if (fold and not parts) else None
+        lnk = (lambda i: dict(ln_parts_out=lnp[i], ln_rows=M)) if parts else (lambda i: {})
+
+        def ln_in(t, i):            # statistics of the folded LayerNorm over the raw stream ``t``
+            if parts:
+                return dict(ln_parts=lnp[i], ln_rows=M)
+            ops.layer_norm_stats(t, st)
+            return dict(ln_stats=st)
         self.conv(s.proj_in, g, a, 1, 1, M, **lnk(0))
         ln = None if fold else self.buf("t_ln", M, Cc)
         # attn1 (self).  Folded form: the GEMM reads the raw stream (packing.Packer.folded)
         qkv = self.buf("t_qkv", M, 3 * Cc)
         if fold:
-            ops.linear(a, s.wqkv.w, qkv, bias=s.wqkv.bias, ln_parts=lnp[0], ln_rows=M, ln_colsum=s.wqkv.colsum)
+            ops.linear(a, s.wqkv.w, qkv, bias=s.wqkv.bias, ln_colsum=s.wqkv.colsum, **ln_in(a, 0))
         else:
             ops.layer_norm(a, ln, s.ln1.gamma, s.ln1.beta)
             ops.linear(ln, s.wqkv.w, qkv)
@@ -283,7 +301,7 @@ class _Net:
         # attn2 (cross, 77 keys)
         q2 = self.buf("t_q", M, Cc)
         if fold:
-            ops.linear(b, s.wq2.w, q2, bias=s.wq2.bias, ln_parts=lnp[1], ln_rows=M, ln_colsum=s.wq2.colsum)
+            ops.linear(b, s.wq2.w, q2, bias=s.wq2.bias, ln_colsum=s.wq2.colsum, **ln_in(b, 1))
         else:
             ops.layer_norm(b, ln, s.ln2.gamma, s.ln2.beta)
             ops.linear(ln, s.wq2.w, q2)
@@ -293,8 +311,8 @@ class _Net:
         # feed-forward (GEGLU)
         gg = self.buf("t_gg", M, 4 * Cc)
         if fold:
-            ops.linear(a, s.ff1_geglu.w, gg, bias=s.ff1_geglu.bias, act=PD_ACT_GEGLU, ln_parts=lnp[0], ln_rows=M,
-                       ln_colsum=s.ff1_geglu.colsum)
+            ops.linear(a, s.ff1_geglu.w, gg, bias=s.ff1_geglu.bias, act=PD_ACT_GEGLU, ln_colsum=s.ff1_geglu.colsum,
+                       **ln_in(a, 0))
         elif s.ff1_geglu is not None:      # bf16: x * gelu(gate) in the GEMM epilogue, the [M, 8C] tensor never exists
             ops.layer_norm(a, ln, s.ln3.gamma, s.ln3.beta)
             ops.linear(ln, s.ff1_geglu.w, gg, bias=s.ff1_geglu.bias, act=PD_ACT_GEGLU)

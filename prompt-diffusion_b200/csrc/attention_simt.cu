@@ -206,6 +206,13 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
   if (auto_short < 0) { const char* e = getenv("PD_B200_ATTN_SHORT"); auto_short = (e && e[0] == '0') ? 0 : 1; }
   if (engine == 4 || (engine == 0 && short_ok && auto_short))
     return attention_short(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
+  // engine 5 = the four-group / 64-key-tile tcgen05 kernel (d <= 64); auto picks it for the long sequences it is built for
+  if (engine == 5 && !(tc_ok && d <= 64)) {
+    set_error("pd_attention: the four-group tcgen05 engine needs what engine 3 needs and d <= 64");
+    return PD_ERR_UNSUPPORTED;
+  }
+  if (engine == 5 || (engine == 0 && tc_ok && attention_tc4_supported(d, Nq, Nk)))
+    return attention_tc4(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   if (engine == 3 || (engine == 0 && tc_ok)) return attention_tc(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   if (engine == 2 && !mma_ok) {
     set_error("pd_attention: tensor-core engine needs bf16, d in {32,40,48,64,80,128,160}, 16B-aligned q/k/v");

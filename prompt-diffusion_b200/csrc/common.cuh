@@ -68,6 +68,30 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, z));
 }
 
+// GELU for the bf16 GEGLU epilogue: x * Phi(x) with Phi(x) = 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4))), coefficients
+// fitted (minimax-weighted least squares over |x| <= 6) to the exact erf form: max |error| 1.0e-4, plus tanh.approx's
+// 2^-11 relative error (<= 2.5e-4 |x|) — both well under the bf16 rounding of the product that follows (2^-9 relative).
+// Five FMA-pipe ops and ONE SFU op per value against ~16 + 2 for gelu_erf_fast: the GEGLU GEMM epilogue
+// (attention.py:54-56) is issue-bound on exactly this arithmetic (8 epilogue warps for 128 x 256 accumulators).
+__device__ __forceinline__ float gelu_tanh_fit(float x) {
+  const float x2 = x * x;
+  const float u = x * fmaf(fmaf(-3.93428114e-04f, x2, 3.73541892e-02f), x2, 7.96888895e-01f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
+}
+#ifndef PD_GEGLU_EXACT_ERF
+#define PD_GEGLU_EXACT_ERF 0
+#endif
+__device__ __forceinline__ float gelu_epilogue(float x) {
+#if PD_GEGLU_EXACT_ERF
+  return gelu_erf_fast(x);
+#else
+  return gelu_tanh_fit(x);
+#endif
+}
+
 // 8 x bf16 <-> 8 floats through one 16-byte access
 struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
@@ -124,6 +148,10 @@ bool attention_tc_supported(int dtype, int d, int ldq, int ldk, int ldv, int ldo
                             const void* v, const void* out);
 int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
                  int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
+
+bool attention_tc4_supported(int d, int Nq, int Nk);            // attention_tc4.cu: four query groups, 64-key tiles
+int attention_tc4(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
+                  int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
 
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
 // Hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may be

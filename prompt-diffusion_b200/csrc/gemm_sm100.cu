@@ -432,6 +432,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const long long sk_units = (long long)num_tiles * nkb;
     if (!LNF && a.ln_parts_out != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0)
       *reinterpret_cast<int*>(a.ln_parts_out) = a.n_tiles * 2;       // header: partial count of this launch
+    int ln_nparts = 0;
+    if (LNF && a.ln_parts_in != nullptr) ln_nparts = __ldg(reinterpret_cast<const int*>(a.ln_parts_in));
     int it = 0;
     PieceIter pit(SK, worker, nworkers, num_tiles, nkb);
     int tile, kb0, kb1;
@@ -449,6 +451,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const bool row_ok = x < a.Wo && y < a.Ho && b < a.B;
       const int64_t m = ((int64_t)b * a.Ho + y) * a.Wo + x;
       const int n0 = nt * a.BN;
+      // folded LayerNorm: this row's (mean, rstd).  Fetched BEFORE the accumulator wait so that the loads fly while the
+      // MMAs of the tile run; with producer partials, four loads in flight at a time, folded in a fixed order over the
+      // bf16-ROUNDED values the tensor cores read.
+      float ln_mu = 0.f, ln_rs = 0.f;
+      if (LNF && row_ok) {
+        if (a.ln_parts_in != nullptr) {
+          const float2* pp = reinterpret_cast<const float2*>(a.ln_parts_in + 4) + m;
+          float su = 0.f, sq = 0.f;
+          for (int i0 = 0; i0 < ln_nparts; i0 += 4) {
+            float2 pv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              pv[u] = (i0 + u < ln_nparts) ? __ldg(pp + (long long)(i0 + u) * a.ln_rows) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { su += pv[u].x; sq += pv[u].y; }
+          }
+          ln_mu = su * a.ln_inv_c;
+          ln_rs = rsqrtf(fmaxf(sq * a.ln_inv_c - ln_mu * ln_mu, 0.f) + a.ln_eps);
+        } else {
+          const float2 st = __ldg(a.ln_stats + m); ln_mu = st.x; ln_rs = st.y;
+        }
+      }
       // residual slabs are fetched by TMA INTO the staging buffers (the sum is formed in place): both buffers must
       // have been drained by their stores.  Issued before the accumulator wait so that the MMAs of the tile hide the
       // latency; the slabs of the worker's NEXT tile are pulled into L2 at the same time (the short-K layers have
@@ -546,22 +570,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       const float* rvp = nullptr;
       if (RV) rvp = a.rowvec + (row_ok ? (m / a.hw_real) : 0) * a.ldrv;
-      float ln_mu = 0.f, ln_rs = 0.f;
-      if (LNF && row_ok) {
-        if (a.ln_parts_in != nullptr) {
-          // (sum, sumsq) partials written by the producing GEMM's epilogue (one per N tile and epilogue group), folded
-          // in a fixed order; mean / variance over the bf16-ROUNDED values the tensor cores read
-          const int parts = __ldg(reinterpret_cast<const int*>(a.ln_parts_in));
-          const float2* pp = reinterpret_cast<const float2*>(a.ln_parts_in + 4) + m;
-          float su = 0.f, sq = 0.f;
-          for (int i = 0; i < parts; ++i) { const float2 v = __ldg(pp + (long long)i * a.ln_rows); su += v.x; sq += v.y; }
-          ln_mu = su * a.ln_inv_c;
-          ln_rs = rsqrtf(fmaxf(sq * a.ln_inv_c - ln_mu * ln_mu, 0.f) + a.ln_eps);
-        } else {
-          const float2 st = __ldg(a.ln_stats + m); ln_mu = st.x; ln_rs = st.y;
-        }
-      }
-      float lnp_s = 0.f, lnp_q = 0.f;      // LayerNorm partial of this thread's row over this group's slabs
+      float lnp_s = 0.f, lnp_q = 0.f, lnp_s2 = 0.f, lnp_q2 = 0.f;      // LayerNorm partial of this thread's row over this group's slabs (even | odd columns)
       uint32_t v0[64], v1[64];
       // stream-K reducer: pieces of this tile in K order (worker p's piece sits in its slot 0 when the tile is where
       // p's range starts)
@@ -625,12 +634,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               for (int e = 0; e < 8; ++e) {
                 const float val = (__uint_as_float(v[g * 8 + e]) - ln_mu * sx[e]) * ln_rs + bx[e];
                 const float gate = (__uint_as_float(v[32 + g * 8 + e]) - ln_mu * sg[e]) * ln_rs + bg[e];
-                f[e] = val * gelu_erf_fast(gate);
+                f[e] = val * gelu_epilogue(gate);
               }
             } else {
 #pragma unroll
               for (int e = 0; e < 8; ++e)
-                f[e] = (__uint_as_float(v[g * 8 + e]) + bx[e]) * gelu_erf_fast(__uint_as_float(v[32 + g * 8 + e]) + bg[e]);
+                f[e] = (__uint_as_float(v[g * 8 + e]) + bx[e]) * gelu_epilogue(__uint_as_float(v[32 + g * 8 + e]) + bg[e]);
             }
             const int off = r * 64 + ((g ^ ((r >> 1) & 3)) << 4);     // SWIZZLE_64B rows of the 32-column output box
             sts_bf16x8(stg_s + (uint32_t)off, pack8(f));
@@ -683,7 +692,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 float rf[8];
                 unpack8(pk, rf);                       // statistics of the values as STORED (bf16-rounded)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { lnp_s += rf[e]; lnp_q = fmaf(rf[e], rf[e], lnp_q); }
+                for (int e = 0; e < 8; e += 2) {       // packed fp32x2: half the issue slots
+                  fadd2(lnp_s, lnp_s2, lnp_s, lnp_s2, rf[e], rf[e + 1]);
+                  ffma2(lnp_q, lnp_q2, rf[e], rf[e + 1], rf[e], rf[e + 1], lnp_q, lnp_q2);
+                }
               }
             }
           }
@@ -714,7 +726,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               uint32_t u;
               asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(stg_s + (uint32_t)off));
               const float v0 = __uint_as_float(u << 16), v1 = __uint_as_float(u & 0xffff0000u);
-              s0 += v0; q0 = fmaf(v0, v0, q0); s1 += v1; q1 = fmaf(v1, v1, q1);
+              fadd2(s0, s1, s0, s1, v0, v1);
+              ffma2(q0, q1, v0, v1, v0, v1, q0, q1);
             }
           }
 #pragma unroll
@@ -798,7 +811,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (ns_mine > 1) col_stats(1);
         }
         if (!LNF && a.ln_parts_out != nullptr && row_ok)
-          reinterpret_cast<float2*>(a.ln_parts_out + 4)[(long long)(nt * 2 + grp) * a.ln_rows + m] = make_float2(lnp_s, lnp_q);
+          reinterpret_cast<float2*>(a.ln_parts_out + 4)[(long long)(nt * 2 + grp) * a.ln_rows + m] = make_float2(lnp_s + lnp_s2, lnp_q + lnp_q2);
       }
       if (RES) res_phase ^= 1u;
       if (ew == 0 && lane == 0) PD_DBG(2, it, 1);
@@ -1280,16 +1293,16 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   // the table is keyed by the GEMM shape; of the epilogue only GEGLU matters (it constrains the tile width)
   const TuneKey key{p->B * Ho * Wo, p->Cout, p->ksize * p->ksize * p->C + p->C2, p->ksize, p->stride, 0,
                     p->act == PD_ACT_GEGLU ? 8 : 0};
+  bool tabled = false;
+  TcVariant tv{0, 0, 0};
   {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(g_mu);          // released before the launch: conv2d_tc_impl takes g_mu itself
     tune_load_locked();
     auto it = g_tune.find(key);
-    if (it != g_tune.end()) {
-      const TcVariant v = it->second;
-      // a tabled stream-K row whose scratch cannot be had falls back to its data-parallel sibling inside impl (sk = 2)
-      return conv2d_tc_impl(p, s, TcVariant{v.cg, v.sk ? 2 : 0, v.bn});
-    }
+    if (it != g_tune.end()) { tabled = true; tv = it->second; }
   }
+  // a tabled stream-K row whose scratch cannot be had falls back to its data-parallel sibling inside impl (sk = 2)
+  if (tabled) return conv2d_tc_impl(p, s, TcVariant{tv.cg, tv.sk ? 2 : 0, tv.bn});
   if (!g_autotune) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0});
   // ---- opt-in timing autotune (table regeneration) ----
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;

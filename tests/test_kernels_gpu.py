@@ -399,6 +399,38 @@ def test_attention_tcgen05(B, heads, Nq, Nk, d):
     assert err < 1e-2, err
 
 
+TC4_ATTN_CASES = [(1, 8, 1024, 1024, 40), (1, 8, 4096, 4096, 40), (2, 4, 1100, 700, 40), (1, 2, 2304, 2304, 40),
+                  (1, 4, 1536, 513, 64), (2, 3, 1024, 1000, 16), (1, 2, 520, 65, 48), (1, 1, 100, 64, 40)]
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", TC4_ATTN_CASES)
+def test_attention_tcgen05_four_groups(B, heads, Nq, Nk, d):
+    """The four-query-group / 64-key-tile tcgen05 kernel (engine 5: what auto picks for the 4096 / 9216-token
+    self-attention) vs torch fp32 on the same bf16 operands — full tiles, ragged query and key counts (partial last
+    CTA, partial last key tile), a single key tile; and bit-identical results when auto selects it."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(7)
+    Cc = heads * d
+    if Nq == Nk:
+        qkv = torch.randn(B * Nq, 3 * Cc, device=DEV, generator=g).to(torch.bfloat16)
+        q, k, v = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
+    else:
+        q = torch.randn(B * Nq, Cc, device=DEV, generator=g).to(torch.bfloat16)
+        kv = torch.randn(B * Nk, 2 * Cc, device=DEV, generator=g).to(torch.bfloat16)
+        k, v = kv[:, :Cc], kv[:, Cc:]
+    out = torch.full((B * Nq, Cc + 8), 3.0, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q, k, v, out[:, :Cc], B, heads, Nq, Nk, d, engine=5)
+    torch.cuda.synchronize()
+    assert bool((out[:, Cc:] == 3.0).all()), "wrote past the head columns"
+    ref = _attn_ref(q.reshape(B, Nq, Cc), k.reshape(B, Nk, Cc), v.reshape(B, Nk, Cc), heads, d ** -0.5)
+    err = rel_l2(out[:, :Cc].float().reshape(B, Nq, Cc), ref)
+    assert err < 1e-2, err
+    if Nq >= 1024 and Nk >= 512:
+        auto = torch.empty(B * Nq, Cc, dtype=torch.bfloat16, device=DEV)
+        ops.attention(q, k, v, auto, B, heads, Nq, Nk, d)
+        assert torch.equal(auto, out[:, :Cc])
+
+
 SHORT_ATTN_CASES = [(2, 8, 100, 77, 40), (1, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 2, 640, 1, 40),
                     (1, 4, 130, 128, 64), (2, 3, 257, 81, 16), (1, 8, 333, 16, 80), (1, 5, 64, 100, 48)]
 
