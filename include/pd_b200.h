@@ -230,7 +230,7 @@ int pd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const v
 /* same, with an explicit engine: 0 auto, 1 SIMT (fp32 math, any dtype), 2 warp-level mma.sync (bf16),
  * 3 tcgen05/TMEM/TMA (bf16, head dim <= 128), 4 single-pass short-key kernel (bf16, Nk <= 128, head dim <= 80: the
  * 77-token cross-attention; what auto picks for it), 5 four-query-group / 64-key-tile tcgen05 kernel (bf16, head dim <= 64;
- * what auto picks for Nq >= 1024, Nk >= 512: the 4096 / 9216-token self-attention) */
+ * measured slower than engine 3 on B200, kept as an explicit engine / PD_B200_ATTN4=1 only) */
 int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
                     int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
                     int32_t Nk, int32_t d, float scale, int32_t dtype, int32_t engine, void* stream);

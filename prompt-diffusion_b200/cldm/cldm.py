@@ -33,13 +33,17 @@ from ..synth import CTRL_PREFIX, UNET_PREFIX
 
 _MODES = {"bf16": torch.bfloat16, "fp32": torch.float32}
 
-# Statistics hand-off from GEMM epilogues to the norms (bf16 mode).  Emitting them costs epilogue issue slots: free
-# behind a long main loop (3x3 convs, K >= ~1000), not free on the short-K 1x1 layers whose epilogue IS the critical
-# path.  GN_STATS_MIN_K: only launches whose K extent reaches it emit GroupNorm records (their consumers stream once;
-# other GroupNorm inputs take the two-phase kernel).  LN_PARTS: LayerNorm row partials from the producing GEMM
-# (False: separate pd_layer_norm_stats pass).  Values measured on B200 at config 2, see DESIGN.md.
-GN_STATS_MIN_K = 0
-LN_PARTS = True
+# Statistics hand-off from GEMM epilogues to the norms (bf16 mode): the epilogue of the producing GEMM emits GroupNorm
+# column records / LayerNorm row partials so that the norm does not re-read the tensor (pd_conv_params.gn_stats_out /
+# ln_parts_out).  Built, parity-tested — and measured to LOSE at config 2 (scripts/stats_ab.py, CUDA-graph replay of one
+# denoising step on B200, profiles/r02_stats_ab.txt): 24.52 ms with both off, 24.89 with LayerNorm partials, 24.89 with
+# GroupNorm records from the K >= 1024 launches only, 25.28 with everything on.  The GEMM engine's epilogue and
+# shared-memory bandwidth are the critical resources of exactly the launches that would emit, and the
+# cooperative GroupNorm's second read is mostly an L2 hit inside the graph, so the hand-off costs more than the pass it
+# removes.  Defaults are therefore OFF; the one exception is the tensor in front of the UNet's `out` conv, whose
+# split-precision GroupNorm output needs the records (one launch per step).
+GN_STATS_MIN_K = 1 << 30     # K extent from which a launch emits GroupNorm records
+LN_PARTS = False             # LayerNorm row partials from the producing GEMM (False: pd_layer_norm_stats pass)
 
 
 _on_device = ops.on_device
@@ -176,7 +180,8 @@ class _Net:
             x2 = kw.get("x2")
             ktot = ks * ks * x.shape[1] + (0 if x2 is None else x2.shape[1])
             ok = (self.dt == torch.bfloat16 and out.dtype == torch.bfloat16 and x.shape[1] % 64 == 0 and out.shape[1] % 8 == 0
-                  and sHW % 64 == 0 and kw.get("act", PD_ACT_NONE) != PD_ACT_GEGLU and ktot >= GN_STATS_MIN_K
+                  and sHW % 64 == 0 and kw.get("act", PD_ACT_NONE) != PD_ACT_GEGLU
+                  and (ktot >= GN_STATS_MIN_K or getattr(out, "_pd_force_stats", False))
                   and ops.gn_stats_supported(B, Ho, Wo, ks, st))
             if ok:
                 key, ws, pitch = self.pool.gn_ws(out, sB, sHW)
@@ -540,6 +545,7 @@ class ControlledUnetModel(_Net):
                 o = st.cats[j + 1][1]
             else:
                 o = self.buf("unet.hfinal", B * Ho * Wo, blk[0].cout)
+                o._pd_force_stats = True       # feeds the split-precision GroupNorm in front of the `out` conv
             self.run_block(blk, full, o, st.emb_all, st.kv, st.ctx_len, B, Hj, Wj, f"unet.out{j}")
         M = B * st.H * st.W
         mc, oc = self.cfg.model_channels, self.cfg.out_channels

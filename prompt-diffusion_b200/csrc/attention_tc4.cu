@@ -276,11 +276,15 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 }
 
 // d <= 64 with enough queries and keys to amortise a 512-query CTA: the long self-attention of the first level
-static int g_tc4_on = -1;     // -1: read PD_B200_ATTN4 once (default on)
+// Measured on B200 (scripts/attn_bench.py, profiles/r02_attn_bench.txt): B16 h8 N4096 d40 takes 1135 us here against
+// 764 us on the two-group kernel (9216 tokens: 11.3 ms vs 7.3 ms) — the aliased P/S columns serialise every group's
+// softmax -> P V -> Q K^T round trip and a 64-key tile pays the per-tile waits twice as often, which costs more than the
+// four warps per sub-partition gain.  Auto therefore does NOT select it (PD_B200_ATTN4=1 or engine 5 do).
+static int g_tc4_on = -1;     // -1: read PD_B200_ATTN4 once (default off)
 bool attention_tc4_supported(int d, int Nq, int Nk) {
   if (g_tc4_on < 0) {
     const char* e = getenv("PD_B200_ATTN4");
-    g_tc4_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_tc4_on = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   return g_tc4_on && d <= 64 && Nq >= 1024 && Nk >= 512;
 }

@@ -405,9 +405,9 @@ TC4_ATTN_CASES = [(1, 8, 1024, 1024, 40), (1, 8, 4096, 4096, 40), (2, 4, 1100, 7
 
 @pytest.mark.parametrize("B,heads,Nq,Nk,d", TC4_ATTN_CASES)
 def test_attention_tcgen05_four_groups(B, heads, Nq, Nk, d):
-    """The four-query-group / 64-key-tile tcgen05 kernel (engine 5: what auto picks for the 4096 / 9216-token
-    self-attention) vs torch fp32 on the same bf16 operands — full tiles, ragged query and key counts (partial last
-    CTA, partial last key tile), a single key tile; and bit-identical results when auto selects it."""
+    """The four-query-group / 64-key-tile tcgen05 kernel (engine 5; an experiment that measured slower than the
+    two-group kernel, so auto does not pick it) vs torch fp32 on the same bf16 operands — full tiles, ragged query and
+    key counts (partial last CTA, partial last key tile), a single key tile."""
     ops = _ops()
     g = torch.Generator(device=DEV).manual_seed(7)
     Cc = heads * d
@@ -425,10 +425,6 @@ def test_attention_tcgen05_four_groups(B, heads, Nq, Nk, d):
     ref = _attn_ref(q.reshape(B, Nq, Cc), k.reshape(B, Nk, Cc), v.reshape(B, Nk, Cc), heads, d ** -0.5)
     err = rel_l2(out[:, :Cc].float().reshape(B, Nq, Cc), ref)
     assert err < 1e-2, err
-    if Nq >= 1024 and Nk >= 512:
-        auto = torch.empty(B * Nq, Cc, dtype=torch.bfloat16, device=DEV)
-        ops.attention(q, k, v, auto, B, heads, Nq, Nk, d)
-        assert torch.equal(auto, out[:, :Cc])
 
 
 SHORT_ATTN_CASES = [(2, 8, 100, 77, 40), (1, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 2, 640, 1, 40),
