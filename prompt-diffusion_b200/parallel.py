@@ -19,12 +19,21 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def shard_conditioning(cond: Optional[Dict[str, list]], lo: int, hi: int):
+def shard_conditioning(cond: Optional[Dict[str, list]], lo: int, hi: int, memo: Optional[dict] = None):
     """Slice every tensor of a reference-style conditioning dict ({'c_crossattn': [T], 'example_pair': [T],
-    'query': [T]}) along the batch dim."""
+    'query': [T]}) along the batch dim.  ``memo`` (shared between the conditional and the unconditional dict of one
+    shard) keeps tensor IDENTITY: entries that were the same object before slicing are the same object after it, which
+    is what lets the sampler encode a shared example_pair / query once per CFG pair."""
     if cond is None:
         return None
-    return {k: [t[lo:hi] for t in v] for k, v in cond.items()}
+    memo = {} if memo is None else memo
+
+    def cut(t):
+        key = (id(t), lo, hi)
+        if key not in memo:
+            memo[key] = (t, t[lo:hi])          # the source is kept alive so that its id cannot be reused
+        return memo[key][1]
+    return {k: [cut(t) for t in v] for k, v in cond.items()}
 
 
 def all_gather_latents(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
@@ -68,7 +77,8 @@ def sample_sharded(sample_fn: Callable, batch_size: int, conditioning, unconditi
     step = (hi - lo) if not chunk else chunk
     for a in range(lo, hi, max(step, 1)):
         b = min(hi, a + step)
-        outs.append(sample_fn(b - a, shard_conditioning(conditioning, a, b),
-                              shard_conditioning(unconditional_conditioning, a, b),
+        memo = {}
+        outs.append(sample_fn(b - a, shard_conditioning(conditioning, a, b, memo),
+                              shard_conditioning(unconditional_conditioning, a, b, memo),
                               None if x_T is None else x_T[a:b]))
     return all_gather_latents(torch.cat(outs), batch_size, group)
