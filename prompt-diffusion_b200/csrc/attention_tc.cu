@@ -29,7 +29,7 @@ namespace pd {
 constexpr int FA_BQ = 128, FA_GROUPS = 2, FA_BK = 128, FA_THREADS = 320, FA_MAX_STAGES = 3;
 constexpr int FA_TILE_BYTES = 128 * 128;   // one [128 rows][64 bf16] SWIZZLE_128B tile
 constexpr int FA_ALIGN_SLACK = 1024;
-constexpr float FA_RESCALE_THRESHOLD = 8.0f;   // log2 units
+constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or above it (or NaN) triggers the exact-max path
 #ifndef FA_ORDERED
 #define FA_ORDERED 0
 #endif
@@ -261,78 +261,78 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int e = 0; e < 128; ++e)
           if (e >= nv) s[e] = 0xff800000u;         // -inf: keys past Nk (stale / zero-filled columns)
       }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+      // ---- reference for the exponentials ------------------------------------------------------------------------
+      // P is bf16 and l / O accumulate in fp32, all with 8 exponent bits, so the reference m_ref only has to keep
+      // exp2(s * sc - m_ref) inside the fp32 range — it need not track the running row maximum.  Tile 0 fixes m_ref at
+      // its exact row maximum; later tiles SKIP the max pass (64 FMNMX3 of the ~420 instructions a thread issues per
+      // tile, on a section that is issue-bound, not SFU-bound) and exponentiate against the stale reference.  A row
+      // whose scores outgrow it by more than 2^64 shows up in its tile row-sum; only then (never on ordinary data
+      // after tile 0) the tile is redone behind an exact max + O / l rescale.
+      auto row_max = [&]() {
+        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
 #pragma unroll
-      for (int e = 2; e < 126; e += 4) {
-        mx0 = fmax3(mx0, __uint_as_float(s[e]), __uint_as_float(s[e + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(s[e + 2]), __uint_as_float(s[e + 3]));
-      }
-      const float mx = fmax3(mx0, mx1, fmaxf(__uint_as_float(s[126]), __uint_as_float(s[127]))) * sc;
+        for (int e = 2; e < 126; e += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(s[e]), __uint_as_float(s[e + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s[e + 2]), __uint_as_float(s[e + 3]));
+        }
+        return fmax3(mx0, mx1, fmaxf(__uint_as_float(s[126]), __uint_as_float(s[127]))) * sc;
+      };
+      if (j == 0) m_ref = fmaxf(row_max(), -1e30f);          // (a fully masked row keeps a finite reference)
       if (dbg) FA_DBG(dslot + 1, j);
-      // lazy reference update: keep the stale reference unless the row max grew by more than 2^THRESHOLD
-      float corr = 1.0f;
-      if (mx > m_ref + FA_RESCALE_THRESHOLD) {
-        corr = ex2_approx(m_ref - mx);             // first tile: exp2(-inf) = 0
-        m_ref = mx;
-        l_run *= corr;
-      }
       if (j > 0) {
         if constexpr (!ALIAS) {                    // P_g(j-1) V(j-1) retired: P_g is free, O_g is complete
           mbar_wait(&p_free[g], (uint32_t)(j - 1) & 1u, 550 + g);
           tc_fence_after();
         }
         // (ALIAS: s_full(j) was committed after P V(j-1) in issue order, so O_g is complete here too)
-        if (__any_sync(0xffffffffu, corr != 1.0f)) {
-#pragma unroll
-          for (int c = 0; c < KPAD; c += 16) {
-            uint32_t o[16];
-            tmem_ld16(tmem_o + (uint32_t)c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * corr);
-            tmem_st16(tmem_o + (uint32_t)c, o);
-          }
-        }
       }
-      const float nm = -m_ref;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      // The two groups take turns on the MUFU-bound exponential section (named barriers 3/4 carry the token):
-      // while one group exponentiates at the full SFU rate, the other loads S, takes its max and synchronises,
-      // instead of both stalling on the same pipe and then both idling it.
-#if FA_ORDERED
-      if (g == 0) { if (j > 0) asm volatile("bar.sync 3, 256;" ::: "memory"); }
-      else asm volatile("bar.sync 4, 256;" ::: "memory");
-#endif
+      float lt = 0.f;
       // scale-and-subtract (packed FFMA2), exp2, row sum (packed FADD2), bf16 pack, P -> TMEM.  FA_POLY of every 8
-      // element pairs take the polynomial exp2 on the FMA pipe, the rest MUFU.EX2: the section is otherwise bound
-      // by the SFU alone (128 MUFU per row and tile) while the FMA pipe idles.
+      // element pairs take the polynomial exp2 on the FMA pipe, the rest MUFU.EX2.
+      auto exp_tile = [&]() {
+        const float nm = -m_ref;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const int i = c * 32 + e;
-          float x0, x1, x2, x3;
-          ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sc, sc, nm, nm);
-          ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sc, sc, nm, nm);
-          // pairs are numbered (e >> 1) and (e >> 1) + 1 within the 16-pair chunk; pair k mod 8 >= 8 - FA_POLY -> polynomial
-          if (((e >> 1) & 7) >= 8 - FA_POLY) exp2_poly2(x0, x1); else { x0 = ex2_approx(x0); x1 = ex2_approx(x1); }
-          if ((((e >> 1) + 1) & 7) >= 8 - FA_POLY) exp2_poly2(x2, x3); else { x2 = ex2_approx(x2); x3 = ex2_approx(x3); }
-          fadd2(l0, l1, l0, l1, x0, x1);
-          fadd2(l2, l3, l2, l3, x2, x3);
-          pk[e >> 1] = pack_bf16x2(x0, x1);
-          pk[(e >> 1) + 1] = pack_bf16x2(x2, x3);
+          for (int e = 0; e < 32; e += 4) {
+            const int i = c * 32 + e;
+            float x0, x1, x2, x3;
+            ffma2(x0, x1, __uint_as_float(s[i]), __uint_as_float(s[i + 1]), sc, sc, nm, nm);
+            ffma2(x2, x3, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]), sc, sc, nm, nm);
+            // pairs are numbered (e >> 1) and (e >> 1) + 1 within the 16-pair chunk; pair k mod 8 >= 8 - FA_POLY -> polynomial
+            if (((e >> 1) & 7) >= 8 - FA_POLY) exp2_poly2(x0, x1); else { x0 = ex2_approx(x0); x1 = ex2_approx(x1); }
+            if ((((e >> 1) + 1) & 7) >= 8 - FA_POLY) exp2_poly2(x2, x3); else { x2 = ex2_approx(x2); x3 = ex2_approx(x3); }
+            fadd2(l0, l1, l0, l1, x0, x1);
+            fadd2(l2, l3, l2, l3, x2, x3);
+            pk[e >> 1] = pack_bf16x2(x0, x1);
+            pk[(e >> 1) + 1] = pack_bf16x2(x2, x3);
+          }
+          tmem_st16p(tmem_p + (uint32_t)(c * 16), pk);   // P_g: 64 columns of bf16 pairs
         }
-        tmem_st16p(tmem_p + (uint32_t)(c * 16), pk);   // P_g: 64 columns of bf16 pairs
-#if FA_ORDERED
-        if (c == 2) {                                  // hand the SFU over a little early: the tail overlaps
-          if (g == 0) asm volatile("bar.arrive 4, 256;" ::: "memory");
-          else if (!last) asm volatile("bar.arrive 3, 256;" ::: "memory");
+        lt = (l0 + l1) + (l2 + l3);
+      };
+      exp_tile();
+      // overflow guard (warp-uniform: the rescale uses warp-collective tcgen05.ld / st)
+      if (j > 0 && __any_sync(0xffffffffu, !(lt < FA_GROW_LIMIT))) {
+        const float mx = row_max();
+        float corr = 1.0f;
+        if (mx > m_ref) { corr = ex2_approx(m_ref - mx); m_ref = mx; l_run *= corr; }
+        tmem_st_wait();
+#pragma unroll
+        for (int c = 0; c < KPAD; c += 16) {
+          uint32_t o[16];
+          tmem_ld16(tmem_o + (uint32_t)c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * corr);
+          tmem_st16(tmem_o + (uint32_t)c, o);
         }
-#endif
+        exp_tile();                                  // P_g(j) rewritten against the new reference
       }
+      l_run += lt;
       tmem_st_wait();
-      l_run += (l0 + l1) + (l2 + l3);
       if (dbg) FA_DBG(dslot + 2, j);
       tc_fence_before();
       __syncwarp();

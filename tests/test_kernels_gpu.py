@@ -399,6 +399,32 @@ def test_attention_tcgen05(B, heads, Nq, Nk, d):
     assert err < 1e-2, err
 
 
+@pytest.mark.parametrize("d,engine", [(40, 3), (80, 3), (40, 5)])
+def test_attention_tcgen05_scores_outgrow_the_first_tile(d, engine):
+    """The tcgen05 kernels fix the softmax reference at the first key tile's row maximum and skip the max pass on later
+    tiles; a row whose later scores outgrow that reference by more than 2^64 must take the exact-max / rescale path.
+    Keys grow in magnitude along the sequence so that every later tile dwarfs the first (scores up to ~600 log2 units
+    above the first tile's), plus a block of rows whose scores DROP instead (the reference stays high: plain underflow)."""
+    ops = _ops()
+    B, heads, Nq, Nk = 1, 2, 1024 if engine == 5 else 256, 640
+    g = torch.Generator(device=DEV).manual_seed(13)
+    Cc = heads * d
+    q = torch.randn(B * Nq, Cc, device=DEV, generator=g)
+    k = torch.randn(B * Nk, Cc, device=DEV, generator=g)
+    v = torch.randn(B * Nk, Cc, device=DEV, generator=g)
+    ramp = torch.logspace(-2, 1.2, Nk, device=DEV)[:, None]          # key norm x1600 from the first to the last key
+    k = k * ramp
+    q[: Nq // 2] *= 6.0                                                # large queries: steep score growth
+    q[Nq // 2:] *= -1.0                                                # mirrored rows: their scores of the same keys fall
+    q, k, v = (t.to(torch.bfloat16) for t in (q, k, v))
+    out = torch.empty(B * Nq, Cc, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q, k, v, out, B, heads, Nq, Nk, d, engine=engine)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out.float()).all())
+    ref = _attn_ref(q.reshape(B, Nq, Cc), k.reshape(B, Nk, Cc), v.reshape(B, Nk, Cc), heads, d ** -0.5)
+    assert rel_l2(out.float().reshape(B, Nq, Cc), ref) < 1e-2
+
+
 TC4_ATTN_CASES = [(1, 8, 1024, 1024, 40), (1, 8, 4096, 4096, 40), (2, 4, 1100, 700, 40), (1, 2, 2304, 2304, 40),
                   (1, 4, 1536, 513, 64), (2, 3, 1024, 1000, 16), (1, 2, 520, 65, 48), (1, 1, 100, 64, 40)]
 

@@ -34,7 +34,7 @@ from prompt_diffusion_b200.synth import make_conds, synthetic_inputs, synthetic_
 mode = os.environ["PD_MODE"]
 model = ControlLDM(cfg, mode=mode, device=dev).load_state_dict(synthetic_state_dict(cfg, seed=0))
 smp = DDIMSampler(model)
-B, S = int(os.environ["PD_BATCH"]), 3
+B, S = int(os.environ["PD_BATCH"]), 4
 inp = {k: v.to(dev) for k, v in synthetic_inputs(cfg, B, 128, 128, seed=2).items()}     # identical on every rank
 cond, un = make_conds(inp)
 def sample_fn(b, c, u, xt):
