@@ -160,14 +160,17 @@ class _Net:
             raise ValueError(f"latent has {cx} channels, the model expects {pc.cin}")
         return self.buf(name, rows, pc.cin_pad, zero=True)
 
-    def load_latent(self, name, x):
-        """NCHW fp32 latent -> the pixel-major buffer conv_in reads (split hi / lo / hi columns in bf16 mode)."""
+    def load_latent(self, name, x, reps: int = 1):
+        """NCHW fp32 latent -> the pixel-major buffer conv_in reads (split hi / lo / hi columns in bf16 mode); ``reps``
+        copies of the batch one after the other (the two halves of a CFG batch see the same latent)."""
         B, Cx, H, W = x.shape
-        x_pm = self.latent_buffer(name, B * H * W, Cx)
-        if self.w.input_blocks[0][0].split == "in":
-            ops.nchw_to_nhwc_split(x, x_pm)
-        else:
-            ops.nchw_to_nhwc(x, x_pm)
+        x_pm = self.latent_buffer(name, reps * B * H * W, Cx)
+        for r in range(reps):
+            dst = x_pm[r * B * H * W:(r + 1) * B * H * W]
+            if self.w.input_blocks[0][0].split == "in":
+                ops.nchw_to_nhwc_split(x, dst)
+            else:
+                ops.nchw_to_nhwc(x, dst)
         return x_pm
 
     def conv(self, pc: PConv, x, out, B, H, W, stats=None, **kw):
@@ -218,12 +221,14 @@ class _Net:
         return self.pool.gn_covered(key, x.storage_offset() % x.stride(0), x.shape[1])
 
     # ---- timestep embedding (cldm.py:26-27,303-304; openaimodel.py:526-531; ResBlock emb_layers) ----
-    def embed(self, t: torch.Tensor) -> torch.Tensor:
-        """t int64 [B] on device -> fp32 [B, sum Cout]: every ResBlock's emb_layers(emb) at once."""
+    def embed(self, t: torch.Tensor, reps: int = 1) -> torch.Tensor:
+        """t int64 [B] on device -> fp32 [reps * B, sum Cout]: every ResBlock's emb_layers(emb) at once (``reps`` = 2: the
+        [uncond, cond] halves of a CFG batch share their timesteps, rows [B, 2B) repeat rows [0, B))."""
         w = self.w
-        B = t.shape[0]
+        B = t.shape[0] * reps
         temb = self.buf(f"{self.tag}.temb", B, self.cfg.model_channels)
-        ops.timestep_embedding(t, temb)
+        for r in range(reps):
+            ops.timestep_embedding(t, temb[r * t.shape[0]:(r + 1) * t.shape[0]])
         e1 = self.buf(f"{self.tag}.e1", B, self.cfg.time_embed_dim)
         ops.linear(temb, w.te0.w, e1, bias=w.te0.bias, act=PD_ACT_SILU)
         # emb itself is only ever consumed through ResBlock.emb_layers = SiLU -> Linear
@@ -447,12 +452,12 @@ class ControlNet(_Net):
         self._hint_cache = (key, list(pair_list) + [query], hint)
         return hint
 
-    def _run(self, x_pm, t, pair_list, query, context_list, B, H, W, sink):
+    def _run(self, x_pm, t, pair_list, query, context_list, B, H, W, sink, t_reps: int = 1):
         """Shared body.  ``sink(i, h, Hh, Ww, pc)`` is called with every block output and its zero conv
         (i = 12 is the middle block)."""
         self._need_weights()
         w = self.w
-        emb_all = self.embed(t)
+        emb_all = self.embed(t, t_reps)
         kv = self.context_kv(context_list)
         ctx_len = self._ctx_cache[3]
         hint = self.guided_hint(pair_list, query, B)
@@ -517,11 +522,11 @@ class ControlledUnetModel(_Net):
             cats.append((full, full[:, :ch_h], full[:, ch_h:], Hj, Wj))
         return cats
 
-    def encode(self, x_pm, t, context_list, B, H, W):
+    def encode(self, x_pm, t, context_list, B, H, W, t_reps: int = 1):
         """input_blocks + middle_block (cldm.py:25-32); outputs land in the decoder's concat slots."""
         self._need_weights()
         w = self.w
-        emb_all = self.embed(t)
+        emb_all = self.embed(t, t_reps)
         kv = self.context_kv(context_list)
         ctx_len = self._ctx_cache[3]
         cats = self._cat_buffers(B, H, W)
@@ -700,12 +705,27 @@ class ControlLDM:
         self.control_model.context_kv(ctx_list)
         self.control_model.guided_hint(list(cond["example_pair"]), cond["query"][0], ctx_list[0].shape[0])
 
-    def _denoise_pm(self, x_pm, t_dev, ctx_list, pair_list, query, B, H, W):
+    @torch.no_grad()
+    @_on_device
+    def apply_model_cfg(self, x, t, c_in):
+        """``apply_model(cat([x] * 2), cat([t] * 2), c_in)`` (cldm/ddim_hacked.py:189-192) without materialising the
+        duplicated latent / timestep tensors: the layout kernel writes x into both halves of the pixel-major input and
+        the timestep embedding is evaluated per half.  x fp32 [B, C, H, W], t int64 [B], ``c_in`` the [uncond, cond]
+        conditioning (2B rows; shared hints may stay at B rows).  Returns eps [2B, C, H, W] (rows [0, B) = uncond)."""
+        unet: ControlledUnetModel = self.model.diffusion_model
+        B, Cx, H, W = x.shape
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        x_pm = unet.load_latent("ldm.x", x, reps=2)
+        eps_pm = self._denoise_pm(x_pm, _to_dev_i64(t, self.device), list(c_in["c_crossattn"]), list(c_in["example_pair"]),
+                                  c_in["query"][0], 2 * B, H, W, t_reps=2)
+        return ops.nhwc_to_nchw(eps_pm, 2 * B, self.cfg.out_channels, H, W)
+
+    def _denoise_pm(self, x_pm, t_dev, ctx_list, pair_list, query, B, H, W, t_reps: int = 1):
         """UNet encoder -> ControlNet (zero-conv epilogues add scale*control onto the stored skips, in
         place) -> UNet decoder.  Equivalent to cldm.py:376-380."""
         unet: ControlledUnetModel = self.model.diffusion_model
         ctrl = self.control_model
-        st = unet.encode(x_pm, t_dev, ctx_list, B, H, W)
+        st = unet.encode(x_pm, t_dev, ctx_list, B, H, W, t_reps)
         nblk = len(unet.w.output_blocks)
         scales = list(self.control_scales)
         only_mid = self.only_mid_control
@@ -719,7 +739,7 @@ class ControlLDM:
                 slot = st.cats[nblk - 1 - i][2]
             ctrl.conv(pc, h, slot, 1, 1, B * Hh * Ww, res=slot, alpha=scales[i], stats=(B, Hh * Ww))
 
-        ctrl._run(x_pm, t_dev, pair_list, query, ctx_list, B, H, W, sink)
+        ctrl._run(x_pm, t_dev, pair_list, query, ctx_list, B, H, W, sink, t_reps)
         return unet.decode(st)
 
     # ---- optional sampler hooks (only reached on the inpainting-mask branch, ddim_hacked.py:154-157) ----

@@ -347,7 +347,11 @@ class DDIMSampler(object):
     def _eager_step(self, x, t, c, c_in, guided, coef, noise, x_prev, pred_x0):
         b = x.shape[0]
         if guided:
-            out = self.model.apply_model(torch.cat([x] * 2), torch.cat([t] * 2), c_in)
+            cfg_call = getattr(self.model, "apply_model_cfg", None)
+            if cfg_call is not None and x.dtype == torch.float32:
+                out = cfg_call(x, t, c_in)          # same eps, no duplicated latent / timestep tensors
+            else:
+                out = self.model.apply_model(torch.cat([x] * 2), torch.cat([t] * 2), c_in)
             e_u, e_c = out[:b], out[b:]
         else:
             e_u, e_c = None, self.model.apply_model(x, t, c)

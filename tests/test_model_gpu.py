@@ -313,6 +313,20 @@ def test_full_size_batch_properties(models, cfg):
         else:
             assert e1 <= 1e-2 and e2r <= 1e-2
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_apply_model_cfg_equals_duplicated_batch(models, cfg, mode):
+    """The sampler's guided step calls ``apply_model_cfg(x, t, c_in)`` instead of ``apply_model(cat([x] * 2),
+    cat([t] * 2), c_in)`` (ddim_hacked.py:189-192): same bits, no duplicated tensors; shared hints may stay at B rows."""
+    inp, cond, un, x_in, c_in = _cfg_inputs(cfg, 2, 128, 128)
+    m = models[mode]
+    t = torch.tensor([621, 41], dtype=torch.long, device=DEV)
+    ref = m.apply_model(x_in, torch.cat([t] * 2), c_in)
+    got = m.apply_model_cfg(inp["x_T"], t, c_in)
+    assert torch.equal(got, ref)
+    c_shared = dict(c_in, example_pair=[cond["example_pair"][0]], query=[cond["query"][0]])    # B-row hints, tiled inside
+    assert torch.equal(m.apply_model_cfg(inp["x_T"], t, c_shared), ref)
+
+
 def test_create_model_and_full_checkpoint_dict(models, cfg, state_dict_cpu):
     """Notebook set-up lines (cldm/model.py:8-28): create_model(yaml) + load_state_dict(get_state_dict(ckpt)) must give
     the same eps as the fixture's model, with the Lightning envelope and foreign entries (VAE / CLIP / EMA) present.
