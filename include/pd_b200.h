@@ -94,6 +94,8 @@ int pd_debug_force_stream_k(int32_t on);
 int pd_debug_group_norm_fused(int32_t on);
 /* A/B switch: 0 = pd_attention's auto selection never picks the four-group kernel (engine 5), 1 = default */
 int pd_debug_attention_tc4(int32_t on);
+/* same for the three-group / 128-key-tile kernel (engine 6, head dim <= 40) */
+int pd_debug_attention_tc3(int32_t on);
 /* same for the tcgen05 attention kernel: 6 phases x 32 tiles of uint64 stamps from block (0,0,0) */
 int pd_debug_attention_timeline(void* dev_buf);
 
@@ -230,7 +232,8 @@ int pd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const v
 /* same, with an explicit engine: 0 auto, 1 SIMT (fp32 math, any dtype), 2 warp-level mma.sync (bf16),
  * 3 tcgen05/TMEM/TMA (bf16, head dim <= 128), 4 single-pass short-key kernel (bf16, Nk <= 128, head dim <= 80: the
  * 77-token cross-attention; what auto picks for it), 5 four-query-group / 64-key-tile tcgen05 kernel (bf16, head dim <= 64;
- * measured slower than engine 3 on B200, kept as an explicit engine / PD_B200_ATTN4=1 only) */
+ * measured equal to engine 3 on B200, kept as an explicit engine / PD_B200_ATTN4=1 only), 6 three-query-group / 128-key-tile
+ * tcgen05 kernel (bf16, head dim <= 40; what auto picks when the query count is a multiple of 384) */
 int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
                     int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
                     int32_t Nk, int32_t d, float scale, int32_t dtype, int32_t engine, void* stream);

@@ -211,6 +211,13 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
     set_error("pd_attention: the four-group tcgen05 engine needs what engine 3 needs and d <= 64");
     return PD_ERR_UNSUPPORTED;
   }
+  // engine 6 = the three-group / 128-key-tile tcgen05 kernel (d <= 40)
+  if (engine == 6 && !(tc_ok && d <= 40)) {
+    set_error("pd_attention: the three-group tcgen05 engine needs what engine 3 needs and d <= 40");
+    return PD_ERR_UNSUPPORTED;
+  }
+  if (engine == 6 || (engine == 0 && tc_ok && attention_tc3_supported(d, Nq, Nk)))
+    return attention_tc3(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   if (engine == 5 || (engine == 0 && tc_ok && attention_tc4_supported(d, Nq, Nk)))
     return attention_tc4(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   if (engine == 3 || (engine == 0 && tc_ok)) return attention_tc(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);

@@ -36,7 +36,7 @@ constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or a
 #ifndef FA_POLY
 #define FA_POLY 0          // of every 8 element pairs, how many take the FMA-pipe exp2 (0..8); measured: 2 -> 792 us vs 0 -> 763 us (B16 h8 N4096 d40): the section is issue-bound, not SFU-bound
 #endif
-static unsigned long long* g_fa_dbg_host = nullptr;   // optional phase timeline (block 0 only), passed by value
+unsigned long long* g_fa_dbg_host = nullptr;   // optional phase timeline (block 0 only), passed by value (shared with attention_tc3 / tc4.cu)
 
 #define FA_DBG(slot, tile)                                                                       \
   do {                                                                                           \
@@ -141,6 +141,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       }
     }
   } else if (warp == W_MMA) {
+    // Single-lane issue ON PURPOSE.  Inside `if (lane == 0)` ptxas wraps every UTCHMMA / UTCBAR in an ELECT ... BRA.U.ANY
+    // retry loop (~150 clk per MMA); the warp-uniform elect.sync form used by the GEMM engine and by attention_tc3 / tc4
+    // issues faster, but here the slow issue is what keeps the two query groups OUT of phase: measured at B16 h8 N4096
+    // d40 (profiles/r02_attn_mma_modes.txt) 762 us as written, 788 us with elect.sync issue, 877 us with elect.sync
+    // and the two groups' Q K^T / P V streams interleaved (both groups then exponentiate at the same time and wait at
+    // the same time).
     if (lane == 0) {
       // descriptors: only the 14-bit start-address field changes between tiles, so every MMA operand is
       // base + a compile-time or per-stage constant in the low word

@@ -29,15 +29,27 @@ constexpr int F4_BQ = 128, F4_GROUPS = 4, F4_BK = 64, F4_THREADS = 640, F4_STAGE
 constexpr int F4_Q_BYTES = 128 * 128;      // [128 rows][64 bf16] SWIZZLE_128B
 constexpr int F4_KV_BYTES = 64 * 128;      // [64 keys][64 bf16]
 constexpr float F4_RESCALE_THRESHOLD = 8.0f;   // log2 units
-// setmaxnreg moves registers inside the CTA's launch allocation (640 threads x 96): the control warp group gives back
-// 128 x (96 - 56) = 5120, the four softmax warp groups take 512 x (104 - 96) = 4096 of them.  ptxas -v: no spills in
-// the softmax region at 104; at 32 / 112 the MMA-issuing thread spilled its descriptors instead.
+// Registers are a per-sub-partition resource (16384 each): five warps per sub-partition cap a thread at 96 at launch
+// (an 18-warp CTA at 112 is refused: "too many resources").  setmaxnreg then moves registers inside the CTA's launch
+// allocation: the control warp group gives back 128 x (96 - 56) = 5120, the four softmax warp groups take
+// 512 x (104 - 96) = 4096.  ptxas -v: no spills in the softmax loop at 104.
 constexpr int F4_REGS_CTRL = 56, F4_REGS_SOFTMAX = 104;
 #ifndef F4_POLY
 #define F4_POLY 0          // of every 8 element pairs, how many take the FMA-pipe exp2 (0..8)
 #endif
 
+extern unsigned long long* g_fa_dbg_host;     // attention_tc.cu: phase-timeline buffer set by pd_debug_attention_timeline
+
+// phase stamps of block (0,0,0): slots 0-3 = MMA thread saw p_full[g], 4-7 = group g has S in registers, 8-11 = group g
+// arrived on p_full (12 slots x 32 tiles of globaltimer ns)
+#define F4_DBG(slot, tile)                                                                       \
+  do {                                                                                           \
+    if (a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 32) \
+      a.dbg[(slot) * 32 + (tile)] = gtimer();                                                    \
+  } while (0)
+
 struct F4Args {
+  unsigned long long* dbg;
   int Nq, Nk;
   float scale_log2;
   uint32_t idesc_s_full, idesc_s_last, idesc_pv;
@@ -88,8 +100,14 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_slot;
   griddep_wait();                        // the set-up above overlapped the previous kernel's tail (PDL)
+  // every role reads the TMEM base into a register of ITS OWN branch: as one kernel-lifetime value ptxas parked it in
+  // local memory (the softmax branch needs every register) and re-loaded it in front of each tcgen05.mma
+  auto read_tmem_base = [&]() {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(s_u32(&tmem_base_slot)));
+    return v;
+  };
 
   if (warp >= 16) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(F4_REGS_CTRL));
@@ -109,7 +127,11 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
       }
     } else if (warp == W_MMA) {
-      if (lane == 0) {
+      // Warp-uniform loop, ONE ELECTED lane issues (elect.sync): inside an `if (lane == 0)` region ptxas wraps every
+      // UTCHMMA / UTCBAR in an ELECT ... BRA.U.ANY retry loop — measured here at ~150 clk per MMA, 0.58 us per group and
+      // key tile, which serialised the four groups behind this one thread (profiles/r02_attn4_timeline_a.txt).
+      {
+        const uint32_t tmem_base = read_tmem_base();
         const uint64_t qdesc0 = make_smem_desc(s_u32(q_s));
         const uint64_t kdesc0 = make_smem_desc(s_u32(k_s));
         const uint64_t vdesc0 = make_smem_desc_mn(s_u32(v_s), F4_KV_BYTES, 1024);
@@ -133,8 +155,11 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         mbar_wait(&k_full[0], 0, 300);
         tc_fence_after();
         const uint32_t id0 = a.ntiles == 1 ? a.idesc_s_last : a.idesc_s_full;
-        for (int g = 0; g < F4_GROUPS; ++g) issue_qk(g, 0, id0);
-        umma_commit(&k_empty[0]);
+        if (elect_one()) {
+          for (int g = 0; g < F4_GROUPS; ++g) issue_qk(g, 0, id0);
+          umma_commit(&k_empty[0]);
+        }
+        __syncwarp();
         int st = 0; uint32_t ph = 0;          // ring position of tile j
         for (int j = 0; j < a.ntiles; ++j) {
           int stn = st + 1; uint32_t phn = ph;
@@ -147,14 +172,18 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           for (int g = 0; g < F4_GROUPS; ++g) {
             mbar_wait(&p_full[g], (uint32_t)j & 1u, 400 + g);
             tc_fence_after();
-            issue_pv(g, st, j == 0, ksteps);
-            if (g == F4_GROUPS - 1) umma_commit(&v_empty[st]);
-            if (more) {
-              issue_qk(g, stn, idn);
-              if (g == F4_GROUPS - 1) umma_commit(&k_empty[stn]);
-            } else {
-              umma_commit(&o_final[g]);
+            if (lane == 0) F4_DBG(g, j);
+            if (elect_one()) {
+              issue_pv(g, st, j == 0, ksteps);
+              if (g == F4_GROUPS - 1) umma_commit(&v_empty[st]);
+              if (more) {
+                issue_qk(g, stn, idn);
+                if (g == F4_GROUPS - 1) umma_commit(&k_empty[stn]);
+              } else {
+                umma_commit(&o_final[g]);
+              }
             }
+            __syncwarp();
           }
           st = stn; ph = phn;
         }
@@ -163,6 +192,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   } else {
     // ---------------- softmax / correction / epilogue: thread == query row ----------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(F4_REGS_SOFTMAX));
+    const uint32_t tmem_base = read_tmem_base();
     const int g = warp >> 2;                       // query group
     const int qd4 = warp & 3;                      // TMEM lane quadrant this warp may touch
     const int r = qd4 * 32 + lane;
@@ -179,6 +209,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tmem_ld32p(tmem_s, s);
       tmem_ld32p(tmem_s + 32u, s + 32);
       tmem_ld_wait();
+      if (qd4 == 0 && lane == 0) F4_DBG(4 + g, j);
       if (last && a.n_last_valid < F4_BK) {
         const int nv = a.n_last_valid;
 #pragma unroll
@@ -237,6 +268,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
+      if (qd4 == 0 && lane == 0) F4_DBG(8 + g, j);
     }
     // ---------------- epilogue ----------------
     if (warp == 0 && lane == 0) griddep_launch();
@@ -271,15 +303,17 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   if (warp == W_MMA) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(read_tmem_base()), "r"(512));
   }
 }
 
 // d <= 64 with enough queries and keys to amortise a 512-query CTA: the long self-attention of the first level
-// Measured on B200 (scripts/attn_bench.py, profiles/r02_attn_bench.txt): B16 h8 N4096 d40 takes 1135 us here against
-// 764 us on the two-group kernel (9216 tokens: 11.3 ms vs 7.3 ms) — the aliased P/S columns serialise every group's
-// softmax -> P V -> Q K^T round trip and a 64-key tile pays the per-tile waits twice as often, which costs more than the
-// four warps per sub-partition gain.  Auto therefore does NOT select it (PD_B200_ATTN4=1 or engine 5 do).
+// Measured on B200 (profiles/r02_attn_bench.txt, r02_attn4_timeline_a/b.txt, r02_attn_mma_modes.txt): B16 h8 N4096 d40
+// took 1135 us as first written (single-lane MMA issue: 0.58 us per group and key tile on the issuing thread, the four
+// groups ran strictly one after the other), 1069 us without the spilled TMEM base, and 761 us with the warp-uniform
+// elected issue below — the same as the two-group kernel's 762 us; at 9216 tokens 7.57 vs 7.28 ms.  With 64-key tiles
+// the kernel needs 6 + 8 tcgen05.mma per 128 keys and group instead of 3 + 8 and is bound by the tensor pipe's
+// per-instruction cost.  Auto therefore does NOT select it (PD_B200_ATTN4=1 or engine 5 do).
 static int g_tc4_on = -1;     // -1: read PD_B200_ATTN4 once (default off)
 bool attention_tc4_supported(int d, int Nq, int Nk) {
   if (g_tc4_on < 0) {
@@ -292,6 +326,7 @@ bool attention_tc4_supported(int d, int Nq, int Nk) {
 int attention_tc4(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
                   int heads, int Nq, int Nk, int d, float scale, cudaStream_t s) {
   F4Args a;
+  a.dbg = g_fa_dbg_host;
   a.Nq = Nq; a.Nk = Nk;
   const int kpad = (d + 15) / 16 * 16;
   a.scale_log2 = scale * 1.4426950408889634f;

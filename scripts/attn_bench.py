@@ -19,9 +19,10 @@ def run(B, heads, Nq, Nk, d, engine, iters=10):
     return us, 4.0 * B * heads * Nq * Nk * d / us / 1e6
 print("   B  h    Nq    Nk    d eng |      us  TFLOP/s")
 for (B, h, Nq, Nk, d) in [(16, 8, 4096, 4096, 40), (16, 8, 4096, 77, 40), (16, 8, 1024, 1024, 80), (16, 8, 1024, 77, 80), (32, 8, 9216, 9216, 40)]:
-    for eng in (2, 3, 5):
+    for eng in (2, 3, 5, 6):
         if eng == 3 and d > 128: continue
         if eng == 5 and (d > 64 or Nk < 512): continue
+        if eng == 6 and (d > 40 or Nk < 256): continue
         if Nq > 8000 and eng == 2: continue
         try:
             us, tf = run(B, h, Nq, Nk, d, eng, iters=5 if Nq > 8000 else 10)

@@ -399,14 +399,14 @@ def test_attention_tcgen05(B, heads, Nq, Nk, d):
     assert err < 1e-2, err
 
 
-@pytest.mark.parametrize("d,engine", [(40, 3), (80, 3), (40, 5)])
+@pytest.mark.parametrize("d,engine", [(40, 3), (80, 3), (40, 5), (40, 6)])
 def test_attention_tcgen05_scores_outgrow_the_first_tile(d, engine):
     """The tcgen05 kernels fix the softmax reference at the first key tile's row maximum and skip the max pass on later
     tiles; a row whose later scores outgrow that reference by more than 2^64 must take the exact-max / rescale path.
     Keys grow in magnitude along the sequence so that every later tile dwarfs the first (scores up to ~600 log2 units
     above the first tile's), plus a block of rows whose scores DROP instead (the reference stays high: plain underflow)."""
     ops = _ops()
-    B, heads, Nq, Nk = 1, 2, 1024 if engine == 5 else 256, 640
+    B, heads, Nq, Nk = 1, 2, 1024 if engine in (5, 6) else 256, 640
     g = torch.Generator(device=DEV).manual_seed(13)
     Cc = heads * d
     q = torch.randn(B * Nq, Cc, device=DEV, generator=g)
@@ -446,6 +446,33 @@ def test_attention_tcgen05_four_groups(B, heads, Nq, Nk, d):
         k, v = kv[:, :Cc], kv[:, Cc:]
     out = torch.full((B * Nq, Cc + 8), 3.0, dtype=torch.bfloat16, device=DEV)
     ops.attention(q, k, v, out[:, :Cc], B, heads, Nq, Nk, d, engine=5)
+    torch.cuda.synchronize()
+    assert bool((out[:, Cc:] == 3.0).all()), "wrote past the head columns"
+    ref = _attn_ref(q.reshape(B, Nq, Cc), k.reshape(B, Nk, Cc), v.reshape(B, Nk, Cc), heads, d ** -0.5)
+    err = rel_l2(out[:, :Cc].float().reshape(B, Nq, Cc), ref)
+    assert err < 1e-2, err
+
+
+TC3_ATTN_CASES = [(1, 8, 1024, 1024, 40), (1, 8, 4096, 4096, 40), (2, 4, 1100, 700, 40), (1, 2, 2304, 2304, 40),
+                  (2, 3, 1024, 1000, 16), (1, 2, 520, 129, 32), (1, 1, 100, 128, 40), (1, 2, 384, 64, 24)]
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", TC3_ATTN_CASES)
+def test_attention_tcgen05_three_groups(B, heads, Nq, Nk, d):
+    """The three-query-group / 128-key-tile tcgen05 kernel (engine 6, head dim <= 40: S_g with P_g aliased, O_g in 40
+    TMEM columns) vs torch fp32 on the same bf16 operands — full tiles, ragged query / key counts, a single key tile."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(7)
+    Cc = heads * d
+    if Nq == Nk:
+        qkv = torch.randn(B * Nq, 3 * Cc, device=DEV, generator=g).to(torch.bfloat16)
+        q, k, v = qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:]
+    else:
+        q = torch.randn(B * Nq, Cc, device=DEV, generator=g).to(torch.bfloat16)
+        kv = torch.randn(B * Nk, 2 * Cc, device=DEV, generator=g).to(torch.bfloat16)
+        k, v = kv[:, :Cc], kv[:, Cc:]
+    out = torch.full((B * Nq, Cc + 8), 3.0, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q, k, v, out[:, :Cc], B, heads, Nq, Nk, d, engine=6)
     torch.cuda.synchronize()
     assert bool((out[:, Cc:] == 3.0).all()), "wrote past the head columns"
     ref = _attn_ref(q.reshape(B, Nq, Cc), k.reshape(B, Nk, Cc), v.reshape(B, Nk, Cc), heads, d ** -0.5)
