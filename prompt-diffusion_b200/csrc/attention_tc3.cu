@@ -28,6 +28,9 @@ constexpr int F3_KV_BYTES = 128 * 128;     // [128 keys][64 bf16]
 // Registers are a per-sub-partition resource (16384 each).  Launch: 512 threads x 128.  setmaxnreg: the control warp
 // group gives back 128 x (128 - 56) = 9216, the three softmax warp groups take 384 x (152 - 128) = 9216.
 constexpr int F3_REGS_CTRL = 56, F3_REGS_SOFTMAX = 152;
+#ifndef F3_STAGGER
+#define F3_STAGGER 1200        // clk between the first exponentials of consecutive groups
+#endif
 constexpr int F3_OCOLS = 40;                 // O_g columns = N extent of P V (head dim rounded up to 8, <= 40)
 constexpr float F3_GROW_LIMIT = 1.8446744e19f;   // 2^64, see attention_tc.cu
 #ifndef F3_POLY
@@ -156,32 +159,55 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           umma_commit(&k_empty[0]);
         }
         __syncwarp();
-        int st = 0; uint32_t ph = 0;          // ring position of tile j
-        for (int j = 0; j < a.ntiles; ++j) {
-          int stn = st + 1; uint32_t phn = ph;
-          if (stn == F3_STAGES) { stn = 0; phn ^= 1u; }
-          const bool more = j + 1 < a.ntiles;
-          const uint32_t idn = (j + 2 == a.ntiles) ? a.idesc_s_last : a.idesc_s_full;
-          const int ksteps = more ? F3_BK / 16 : (a.n_last_valid + 15) / 16;
-          mbar_wait(&v_full[st], ph, 310 + st);
-          if (more) mbar_wait(&k_full[stn], phn, 300 + stn);
+        // Groups are served IN ARRIVAL ORDER, not round-robin: each group's cycle (exponentials, then its P V + next
+        // Q K^T round trip through this warp) then runs on its own clock, so the phase offsets the softmax warps start
+        // with (F3_STAGGER) persist and one group's round trip hides under the other groups' exponentials.  Served in
+        // fixed order the three groups lock step: all exponentiate together, then all wait together
+        // (profiles/r02_attn3_timeline_a.txt: 1.85 us of exponentials + a 0.65 us bubble per key tile).
+        int jg0 = 0, jg1 = 0, jg2 = 0;                // next key tile of each group
+        int pv_cnt[F3_STAGES] = {0, 0, 0}, qk_cnt[F3_STAGES] = {0, 0, 0};   // groups that have issued on the stage's tile
+        int remaining = F3_GROUPS * a.ntiles;
+        long long t_poll = clock64();
+        while (remaining > 0) {
+#pragma unroll
           for (int g = 0; g < F3_GROUPS; ++g) {
-            mbar_wait(&p_full[g], (uint32_t)j & 1u, 400 + g);
+            const int jj = g == 0 ? jg0 : g == 1 ? jg1 : jg2;
+            if (jj >= a.ntiles) continue;
+            const int st = jj % F3_STAGES, stn = (jj + 1) % F3_STAGES;
+            const uint32_t ph = (uint32_t)(jj / F3_STAGES) & 1u, phn = (uint32_t)((jj + 1) / F3_STAGES) & 1u;
+            const bool more = jj + 1 < a.ntiles;
+            int ready = mbar_try_wait(&p_full[g], (uint32_t)jj & 1u) && mbar_try_wait(&v_full[st], ph) &&
+                        (!more || mbar_try_wait(&k_full[stn], phn));
+            ready = __shfl_sync(0xffffffffu, ready, 0);          // one verdict for the warp
+            if (!ready) continue;
             tc_fence_after();
-            if (lane == 0) F3_DBG(g, j);
+            if (lane == 0) F3_DBG(g, jj);
+            const uint32_t idn = (jj + 2 == a.ntiles) ? a.idesc_s_last : a.idesc_s_full;
+            const int ksteps = more ? F3_BK / 16 : (a.n_last_valid + 15) / 16;
+            const bool v_done = ++pv_cnt[st] == F3_GROUPS;
+            if (v_done) pv_cnt[st] = 0;
+            bool k_done = false;
+            if (more) { k_done = ++qk_cnt[stn] == F3_GROUPS; if (k_done) qk_cnt[stn] = 0; }
             if (elect_one()) {
-              issue_pv(g, st, j == 0, ksteps);
-              if (g == F3_GROUPS - 1) umma_commit(&v_empty[st]);
+              issue_pv(g, st, jj == 0, ksteps);
+              if (v_done) umma_commit(&v_empty[st]);
               if (more) {
                 issue_qk(g, stn, idn);
-                if (g == F3_GROUPS - 1) umma_commit(&k_empty[stn]);
+                if (k_done) umma_commit(&k_empty[stn]);
               } else {
                 umma_commit(&o_final[g]);
               }
             }
             __syncwarp();
+            if (g == 0) ++jg0; else if (g == 1) ++jg1; else ++jg2;
+            --remaining;
+            t_poll = clock64();
           }
-          st = stn; ph = phn;
+          if (clock64() - t_poll > 4000000000LL) {
+            if (lane == 0) printf("pd_b200 attention_tc3: MMA warp starved (block %d,%d,%d tiles %d %d %d of %d)\n", blockIdx.x,
+                                  blockIdx.y, blockIdx.z, jg0, jg1, jg2, a.ntiles);
+            __trap();
+          }
         }
       }
     }
@@ -197,6 +223,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t tmem_o = tmem_base + 384u + (uint32_t)(g * F3_OCOLS) + lane_off;
     const float sc = a.scale_log2;
     float m_ref = -INFINITY, l_run = 0.f;
+    {
+      // phase offset between the groups: a third of a group's cycle each (see the MMA warp)
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)g * F3_STAGGER) { }
+    }
     for (int j = 0; j < a.ntiles; ++j) {
       const bool last = j == a.ntiles - 1;
       mbar_wait(&s_full[g], (uint32_t)j & 1u, 500 + g);
@@ -307,9 +338,11 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
 }
 
-// Measured on B200 (profiles/r02_attn_mma_modes.txt): B32 h8 N9216 d40 takes 7.00 ms here against 7.28 ms on the
-// two-group kernel (-4 %); B16 h8 N4096 d40 775 vs 762 us, because 4096 queries are 10.67 CTAs of 384 and the last CTA
-// of every (batch, head) runs a third empty.  Auto therefore picks this kernel only when the query count is a multiple
+// Measured on B200 (profiles/r02_attn3_stagger.txt, r02_attn3_timeline_a/b.txt): B32 h8 N9216 d40 takes 6.83 ms here
+// against 7.29 ms on the two-group kernel (-6.3 %; 7.00 ms before the MMA warp served the groups in arrival order);
+// B16 h8 N4096 d40 759 vs 763 us: the steady state is 12 % faster (2.24 us per key tile of 384 queries against
+// 1.68 us per 256), but 4096 queries are 10.67 CTAs of 384 — the last CTA of every (batch, head) runs a third
+// empty and 1408 CTAs are 9.5 waves of 148.  Auto therefore picks this kernel only when the query count is a multiple
 // of 384 (the 96 x 96 latent of config 4); PD_B200_ATTN3=0 switches that off, engine 6 selects it explicitly.
 static int g_tc3_on = -1;     // -1: read PD_B200_ATTN3 once (default on)
 bool attention_tc3_supported(int d, int Nq, int Nk) {
