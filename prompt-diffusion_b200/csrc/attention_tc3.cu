@@ -82,6 +82,9 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (F3_GROUPS * F3_BQ), h = blockIdx.y, b = blockIdx.z;
   constexpr int W_TMA = 12, W_MMA = 13;
+  // query groups that hold at least one real row: a trailing CTA of a (batch, head) runs fewer groups instead of
+  // exponentiating zero-filled rows
+  const int n_act = min(F3_GROUPS, (a.Nq - q0 + F3_BQ - 1) / F3_BQ);
 
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_o);
@@ -155,7 +158,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tc_fence_after();
         const uint32_t id0 = a.ntiles == 1 ? a.idesc_s_last : a.idesc_s_full;
         if (elect_one()) {
-          for (int g = 0; g < F3_GROUPS; ++g) issue_qk(g, 0, id0);
+          for (int g = 0; g < n_act; ++g) issue_qk(g, 0, id0);
           umma_commit(&k_empty[0]);
         }
         __syncwarp();
@@ -166,13 +169,13 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // (profiles/r02_attn3_timeline_a.txt: 1.85 us of exponentials + a 0.65 us bubble per key tile).
         int jg0 = 0, jg1 = 0, jg2 = 0;                // next key tile of each group
         int pv_cnt[F3_STAGES] = {0, 0, 0}, qk_cnt[F3_STAGES] = {0, 0, 0};   // groups that have issued on the stage's tile
-        int remaining = F3_GROUPS * a.ntiles;
+        int remaining = n_act * a.ntiles;
         long long t_poll = clock64();
         while (remaining > 0) {
 #pragma unroll
           for (int g = 0; g < F3_GROUPS; ++g) {
             const int jj = g == 0 ? jg0 : g == 1 ? jg1 : jg2;
-            if (jj >= a.ntiles) continue;
+            if (g >= n_act || jj >= a.ntiles) continue;
             const int st = jj % F3_STAGES, stn = (jj + 1) % F3_STAGES;
             const uint32_t ph = (uint32_t)(jj / F3_STAGES) & 1u, phn = (uint32_t)((jj + 1) / F3_STAGES) & 1u;
             const bool more = jj + 1 < a.ntiles;
@@ -184,10 +187,10 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             if (lane == 0) F3_DBG(g, jj);
             const uint32_t idn = (jj + 2 == a.ntiles) ? a.idesc_s_last : a.idesc_s_full;
             const int ksteps = more ? F3_BK / 16 : (a.n_last_valid + 15) / 16;
-            const bool v_done = ++pv_cnt[st] == F3_GROUPS;
+            const bool v_done = ++pv_cnt[st] == n_act;
             if (v_done) pv_cnt[st] = 0;
             bool k_done = false;
-            if (more) { k_done = ++qk_cnt[stn] == F3_GROUPS; if (k_done) qk_cnt[stn] = 0; }
+            if (more) { k_done = ++qk_cnt[stn] == n_act; if (k_done) qk_cnt[stn] = 0; }
             if (elect_one()) {
               issue_pv(g, st, jj == 0, ksteps);
               if (v_done) umma_commit(&v_empty[st]);
@@ -223,6 +226,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t tmem_o = tmem_base + 384u + (uint32_t)(g * F3_OCOLS) + lane_off;
     const float sc = a.scale_log2;
     float m_ref = -INFINITY, l_run = 0.f;
+    if (g < n_act) {
     {
       // phase offset between the groups: a third of a group's cycle each (see the MMA warp)
       const long long t0 = clock64();
@@ -328,6 +332,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tma_store_commit();
       tma_store_wait_all();
     }
+    }   // g < n_act
   }
 
   tc_fence_before();
@@ -342,7 +347,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // against 7.29 ms on the two-group kernel (-6.3 %; 7.00 ms before the MMA warp served the groups in arrival order);
 // B16 h8 N4096 d40 759 vs 763 us: the steady state is 12 % faster (2.24 us per key tile of 384 queries against
 // 1.68 us per 256), but 4096 queries are 10.67 CTAs of 384 — the last CTA of every (batch, head) runs a third
-// empty and 1408 CTAs are 9.5 waves of 148.  Auto therefore picks this kernel only when the query count is a multiple
+// empty and 1408 CTAs are 9.5 waves of 148.  (Since then a trailing CTA runs only its non-empty groups.)  Auto therefore picks this kernel only when the query count is a multiple
 // of 384 (the 96 x 96 latent of config 4); PD_B200_ATTN3=0 switches that off, engine 6 selects it explicitly.
 static int g_tc3_on = -1;     // -1: read PD_B200_ATTN3 once (default on)
 bool attention_tc3_supported(int d, int Nq, int Nk) {
@@ -350,7 +355,7 @@ bool attention_tc3_supported(int d, int Nq, int Nk) {
     const char* e = getenv("PD_B200_ATTN3");
     g_tc3_on = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  return g_tc3_on && d <= 40 && Nq >= 768 && Nq % (F3_GROUPS * F3_BQ) == 0 && Nk >= 256;
+  return g_tc3_on && d <= 40 && Nq >= 768 && Nk >= 256;
 }
 
 int attention_tc3(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
