@@ -343,19 +343,21 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
 }
 
-// Measured on B200 (profiles/r02_attn3_stagger.txt, r02_attn3_timeline_a/b.txt): B32 h8 N9216 d40 takes 6.83 ms here
-// against 7.29 ms on the two-group kernel (-6.3 %; 7.00 ms before the MMA warp served the groups in arrival order);
-// B16 h8 N4096 d40 759 vs 763 us: the steady state is 12 % faster (2.24 us per key tile of 384 queries against
-// 1.68 us per 256), but 4096 queries are 10.67 CTAs of 384 — the last CTA of every (batch, head) runs a third
-// empty and 1408 CTAs are 9.5 waves of 148.  (Since then a trailing CTA runs only its non-empty groups.)  Auto therefore picks this kernel only when the query count is a multiple
-// of 384 (the 96 x 96 latent of config 4); PD_B200_ATTN3=0 switches that off, engine 6 selects it explicitly.
+// Measured on B200.  Kernel alone (profiles/r02_attn3_active.txt, r02_attn3_stagger.txt, timelines r02_attn3_timeline_*):
+// B16 h8 N4096 d40 711 us against 764 us on the two-group kernel, B32 h8 N9216 d40 6.46 against 7.28 ms — also under
+// sustained load between its neighbouring GEMMs (800 vs 844 us per qkv-GEMM + attention + out-GEMM iteration).
+// Inside the whole denoising step, same box, CUDA-graph replay (profiles/r02_attn3_insitu_ab.txt): config 4 (9216 tokens)
+// 125.3 against 128.5 ms per step (-2.5 %), but config 2 (4096 tokens) 23.9 / 24.5 against 23.5 / 24.1 ms (+0.3 ms): the
+// step runs at the 1 kW power cap and the 16-warp CTA with its polling MMA warp buys its 7 % with more power than the
+// step has to spare.  Auto therefore picks this kernel from 6144 queries up; PD_B200_ATTN3=0 switches that off,
+// PD_B200_ATTN3=2 selects it for every d <= 40 shape, engine 6 selects it explicitly.
 static int g_tc3_on = -1;     // -1: read PD_B200_ATTN3 once (default on)
 bool attention_tc3_supported(int d, int Nq, int Nk) {
   if (g_tc3_on < 0) {
     const char* e = getenv("PD_B200_ATTN3");
-    g_tc3_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_tc3_on = (e != nullptr && e[0] == '0') ? 0 : (e != nullptr && e[0] == '2') ? 2 : 1;
   }
-  return g_tc3_on && d <= 40 && Nq >= 768 && Nk >= 256;
+  return g_tc3_on && d <= 40 && Nq >= (g_tc3_on == 2 ? 768 : 6144) && Nk >= 256;
 }
 
 int attention_tc3(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
@@ -412,4 +414,4 @@ int attention_tc3(const void* q, int ldq, const void* k, int ldk, const void* v,
 }  // namespace pd
 
 // A/B switch: 0 = auto never picks the three-group kernel (engine 6 still selects it explicitly)
-extern "C" int pd_debug_attention_tc3(int32_t on) { pd::g_tc3_on = on != 0; return 0; }
+extern "C" int pd_debug_attention_tc3(int32_t on) { pd::g_tc3_on = on; return 0; }   // 0 off, 1 auto (>= 6144 queries), 2 every d <= 40 shape
