@@ -87,6 +87,11 @@ int pd_tune_dump(const char* path_host);
 int pd_debug_force_cta_group(int32_t cg);
 /* experiments: pin the N extent of the tile (multiple of 32 up to 256; 0 = heuristic) */
 int pd_debug_force_bn(int32_t bn);
+/* resident-B schedule of the tcgen05 conv engine (short-K layers: a worker loads its weight tile, all of K, into shared
+ * memory ONCE, keeps one N tile for life and streams only activations): 1 = wherever it fits, 0 = per the variant table.
+ * pd_debug_bres_launches counts the launches that took it. */
+int pd_debug_force_bres(int32_t on);
+uint64_t pd_debug_bres_launches(void);
 /* together with a forced CTA group: 1 = stream-K schedule of the tcgen05 conv engine wherever it applies (the (tile, k-block)
  * space is cut evenly over the CTAs; partial tiles are summed in K order by the last CTA to arrive), 0 = data-parallel */
 int pd_debug_force_stream_k(int32_t on);

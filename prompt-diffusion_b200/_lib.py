@@ -52,6 +52,8 @@ SIGNATURES = {
     "pd_tune_dump": (C.c_int, [C.c_char_p]),
     "pd_debug_force_cta_group": (C.c_int, [C.c_int32]),
     "pd_debug_force_bn": (C.c_int, [C.c_int32]),
+    "pd_debug_force_bres": (C.c_int, [C.c_int32]),
+    "pd_debug_bres_launches": (C.c_uint64, []),
     "pd_debug_force_stream_k": (C.c_int, [C.c_int32]),
     "pd_layer_norm_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "pd_debug_group_norm_fused": (C.c_int, [C.c_int32]),

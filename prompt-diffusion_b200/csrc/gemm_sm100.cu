@@ -51,7 +51,7 @@ struct TcArgs {
   int cpt0, nk0, nk1;           // 64-ch blocks per tap, k-blocks of segment 0 / 1
   int bw, bh, bn;               // pixel box of one 128-row M tile
   int tiles_x, tiles_y, tiles_b, m_tiles, n_tiles, BN, stages;   // BN = N extent of the (CG x 128) x BN tile
-  unsigned long long* dbg;      // optional timeline buffer [3 roles][64 tiles][2] (globaltimer ns), CTA 0 only
+  unsigned long long* dbg;      // optional timeline buffer [5 roles][64 tiles][2] (globaltimer ns), CTA 0 only
   int w_blocked;                // weights are k-block-major [K/64][Cout][64]: B tiles are contiguous in HBM (3-D map)
   int dbg_mode;                 // timing experiments only (wrong results): 1 = no MMAs issued, 2 = no TMA loads issued;
                                 // epilogue: 3 = no TMA stores, 8 = no epilogue work at all, 9 = no MMA and no TMA loads
@@ -74,6 +74,8 @@ struct TcArgs {
   int gn_ld, gn_rec_off, gn_rpi;
   int pad_x, pad_y;             // zero-padding before the first tap (ksize / 2 for the centred 1x1 / 3x3 kernels)
   int flat;                     // 1x1 stride-1 layer flattened to one long pixel row
+  int b_res;                    // 1: the CTA's whole B (weight) tile, all K blocks, stays RESIDENT in shared memory: it is
+                                // loaded once, every worker keeps one N tile for life and the ring carries A only
   uint32_t idesc;
 };
 
@@ -87,8 +89,17 @@ constexpr int SK_SLOT_FLOATS = 256 * 128;   // one CTA's half of a partial tile:
 struct PieceIter {
   int sk, nkb, num_tiles, step, tile;
   long long u, u_end;
-  __device__ PieceIter(int sk_, int worker, int nworkers, int num_tiles_, int nkb_) {
+  // n_tiles_res > 0 (resident-B launches, tiles numbered N-major: tile = nt * pm_tiles + pmt): worker w owns N tile
+  // w % n_tiles_res for life and strides over that tile's M tiles together with the other workers of the same residue.
+  __device__ PieceIter(int sk_, int worker, int nworkers, int num_tiles_, int nkb_, int n_tiles_res = 0) {
     sk = sk_; nkb = nkb_; num_tiles = num_tiles_; step = nworkers; tile = worker; u = 0; u_end = 0;
+    if (n_tiles_res > 0) {
+      const int nt = worker % n_tiles_res, pm_tiles = num_tiles_ / n_tiles_res;
+      step = (nworkers - nt + n_tiles_res - 1) / n_tiles_res;      // workers with this residue
+      tile = nt * pm_tiles + worker / n_tiles_res;
+      num_tiles = (nt + 1) * pm_tiles;
+      if (worker / n_tiles_res >= pm_tiles) tile = num_tiles;      // more workers than M tiles: nothing to do
+    }
     if (sk) {
       const long long U = (long long)num_tiles * nkb;
       u = U * worker / nworkers;
@@ -161,6 +172,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ __align__(8) uint64_t res_full[4];
+  __shared__ __align__(8) uint64_t b_full;
   __shared__ uint32_t tmem_base_slot;
   __shared__ int sk_last;
 
@@ -170,8 +182,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const int b_rows = a.BN / CG;            // rows of the B tile this CTA stages
   const int b_bytes = b_rows * TC_BK * 2;
-  const int stage_bytes = TC_A_BYTES + b_bytes;
   const int nkb = a.nk0 + a.nk1;
+  const bool bres = !SK && a.b_res != 0;
+  const int stage_bytes = bres ? TC_A_BYTES : TC_A_BYTES + b_bytes;
+  unsigned char* ring = smem + (bres ? nkb * b_bytes : 0);    // resident B: [nkb][b_rows x 64] in front of the A ring
+  const int nt_res = bres ? a.n_tiles : 0;
   const int pm_tiles = (a.m_tiles + CG - 1) / CG;      // M tiles of CG x 128 rows
   const int num_tiles = pm_tiles * a.n_tiles;
   const int worker = blockIdx.x / CG, nworkers = gridDim.x / CG;
@@ -183,6 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CG * (EPI == 8 ? 4 : 8)); }
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
+    mbar_init(&b_full, 1);
     if (EPI != 8) { tma_prefetch_desc(&map_o64); if (EPI < 8 && (EPI & 1)) tma_prefetch_desc(&map_r64); }
     fence_barrier_init();
   }
@@ -208,8 +224,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ================= TMA producer (both CTAs of a pair); warp-uniform loop, one elected lane issues =================
     {
       int stage = 0; uint32_t phase = 0;
-      PieceIter pit(SK, worker, nworkers, num_tiles, nkb);
+      PieceIter pit(SK, worker, nworkers, num_tiles, nkb, nt_res);
       int tile, kb0, kb1, tix = 0;
+      if (bres && pit.peek_tile() >= 0 && elect_one()) {
+        // the worker's weight tile, every K block, once (the even CTA's barrier collects both CTAs' bytes)
+        const int n0r = (worker % a.n_tiles) * a.BN + (int)cta_rank * b_rows;
+        if (cta_rank == 0) mbar_expect_tx(&b_full, (uint32_t)(CG * nkb * b_bytes));
+        for (int kb = 0; kb < nkb; ++kb) {
+          unsigned char* sb = smem + kb * b_bytes;
+          if (CG == 2) {
+            if (a.w_blocked) tma_load_3d_2sm(sb, &map_w, &b_full, 0, n0r, kb);
+            else tma_load_2d_2sm(sb, &map_w, &b_full, kb * TC_BK, n0r);
+          } else {
+            if (a.w_blocked) tma_load_3d(sb, &map_w, &b_full, 0, n0r, kb);
+            else tma_load_2d(sb, &map_w, &b_full, kb * TC_BK, n0r);
+          }
+        }
+      }
+      __syncwarp();
       for (; pit.next(tile, kb0, kb1); ++tix) {
         int nt, pmt;
         PD_TILE_COORDS(tile, nt, pmt);
@@ -218,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int tyi = (mt / a.tiles_x) % a.tiles_y;
         const int tbi = mt / (a.tiles_x * a.tiles_y);   // >= tiles_b for the phantom half of an odd last pair: TMA zero-fills
         const int x0 = txi * a.bw, y0 = tyi * a.bh, b0 = tbi * a.bn, n0 = nt * a.BN + (int)cta_rank * b_rows;
-        if (!SK && tile + nworkers >= num_tiles && lane == 0) griddep_launch();   // last tile of this CTA: let the next kernel in
+        if (!SK && pit.peek_tile() < 0 && lane == 0) griddep_launch();   // last tile of this CTA: let the next kernel in
         if (lane == 0) PD_DBG(0, tix, 0);
         // (tap, channel block) walk of segment 0 kept in counters: no integer divisions on the issue path
         // (one division per piece when a stream-K piece starts inside a tile)
@@ -230,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           if (kb == kb1 - 1 && lane == 0) PD_DBG(0, tix, 1);
-          unsigned char* sa = smem + stage * stage_bytes;
+          unsigned char* sa = ring + stage * stage_bytes;
           unsigned char* sb = sa + TC_A_BYTES;
           if (PD_MODE_IS(2) || PD_MODE_IS(9)) {
             if (cta_rank == 0 && elect_one()) mbar_arrive(&full_bar[stage]);
@@ -253,11 +285,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(CG * stage_bytes));
             if (CG == 2) {
               tma_load_4d_2sm(sa, am, &full_bar[stage], ac0, ax, ay, b0);
-              if (a.w_blocked) tma_load_3d_2sm(sb, &map_w, &full_bar[stage], 0, n0, wk >> 6);
+              if (bres) { }
+              else if (a.w_blocked) tma_load_3d_2sm(sb, &map_w, &full_bar[stage], 0, n0, wk >> 6);
               else tma_load_2d_2sm(sb, &map_w, &full_bar[stage], wk, n0);
             } else {
               tma_load_4d(sa, am, &full_bar[stage], ac0, ax, ay, b0);
-              if (a.w_blocked) tma_load_3d(sb, &map_w, &full_bar[stage], 0, n0, wk >> 6);
+              if (bres) { }
+              else if (a.w_blocked) tma_load_3d(sb, &map_w, &full_bar[stage], 0, n0, wk >> 6);
               else tma_load_2d(sb, &map_w, &full_bar[stage], wk, n0);
             }
           }
@@ -271,8 +305,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (cta_rank == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      PieceIter pit(SK, worker, nworkers, num_tiles, nkb);
+      PieceIter pit(SK, worker, nworkers, num_tiles, nkb, nt_res);
       int tile, kb0, kb1;
+      if (bres && pit.peek_tile() >= 0) { mbar_wait(&b_full, 0, 250); tc_fence_after(); }
       for (; pit.next(tile, kb0, kb1); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
@@ -283,9 +318,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase, 300 + stage);
           tc_fence_after();
-          const uint32_t sa = s_u32(smem + stage * stage_bytes);
+          const uint32_t sa = s_u32(ring + stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES);
+          const uint64_t bdesc = make_smem_desc(bres ? s_u32(smem + kb * b_bytes) : sa + TC_A_BYTES);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k) {
@@ -421,7 +456,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int rx = r % a.bw;
     const int ry = (r / a.bw) % a.bh;
     const int rb = r / (a.bw * a.bh);
-    unsigned char* gstg = smem + a.stages * stage_bytes + grp * 32768;   // 1024-aligned
+    unsigned char* gstg = ring + a.stages * stage_bytes + grp * 32768;   // 1024-aligned
     uint64_t* rbar = &res_full[grp * 2];
     uint32_t res_phase = 0;                // residual barriers complete once per tile that loads a residual
     const bool elected = (ew & 3) == 0 && lane == 0;
@@ -435,7 +470,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     int ln_nparts = 0;
     if (LNF && a.ln_parts_in != nullptr) ln_nparts = __ldg(reinterpret_cast<const int*>(a.ln_parts_in));
     int it = 0;
-    PieceIter pit(SK, worker, nworkers, num_tiles, nkb);
+    PieceIter pit(SK, worker, nworkers, num_tiles, nkb, nt_res);
     int tile, kb0, kb1;
     for (; pit.next(tile, kb0, kb1); ++it) {
       const int acc = it & 1;
@@ -789,6 +824,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           gather(0, v0);
           if (ns_mine > 1) gather(1, v1);
         }
+        if (ew == 0 && lane == 0) PD_DBG(3, it, 0);
         // staging buffers ready (residual slabs landed / the previous tile's stores have read them)
         if (RES) {
           mbar_wait(&rbar[0], res_phase, 500 + grp * 2);
@@ -797,11 +833,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (elected && !PD_MODE_IS(3)) tma_store_wait_read<0>();   // issued a whole tile ago: normally no wait at all
           epi_bar_sync(bar_id);
         }
+        if (ew == 0 && lane == 0) PD_DBG(3, it, 1);
         slab_math(0, v0);
         if (ns_mine > 1) slab_math(1, v1);
+        if (ew == 0 && lane == 0) PD_DBG(4, it, 0);
         // one fence / barrier per tile, then both stores in one bulk group
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
         epi_bar_sync(bar_id);
+        if (ew == 0 && lane == 0) PD_DBG(4, it, 1);
         if (elected && !PD_MODE_IS(3)) {
           for (int i = 0; i < ns_mine; ++i) store_slab(i);
           tma_store_commit();
@@ -842,6 +881,8 @@ static int g_dbg_mode = 0;
 static unsigned long long* g_dbg = nullptr;
 #endif
 static int g_force_bn = 0;   // experiments: pin the N extent of the tile (multiple of 32, <= 256)
+static int g_force_bres = 0; // experiments / tests: resident-B schedule wherever it applies
+static unsigned long long g_bres_launches = 0;   // launches that took the resident-B schedule (tests assert the path ran)
 static int g_force_cg = 0;   // 0 auto, 1 single-CTA tiles only, 2 CTA pairs whenever the epilogue allows (tests / A-B timing)
 static int g_n_fast = -1;    // tile order (PD_TILE_COORDS): -1 = read PD_B200_NFAST once (default 1)
 static std::vector<ProfRec> g_prof;
@@ -992,8 +1033,9 @@ bool conv2d_tc_supported(const pd_conv_params* p, const char** why) {
 
 // Launch variant: cg 0 = heuristic, 1 = single-CTA tiles, 2 = CTA pairs; sk = stream-K schedule (needs cg != 0;
 // 1 = required, else PD_ERR_UNSUPPORTED; 2 = where it applies);
-// bn = N extent override (0 = heuristic)
-struct TcVariant { int cg, sk, bn; };
+// bn = N extent override (0 = heuristic); bres = 1: resident-B schedule (short-K layers: the worker's weight tile, all
+// of K, is loaded into shared memory once; PD_ERR_UNSUPPORTED when it does not fit or does not apply)
+struct TcVariant { int cg, sk, bn, bres; };
 
 // stream-K scratch, one per device: partial accumulators (2 slots per CTA) and self-resetting arrival counters
 constexpr int SK_MAX_TILES = 32768;
@@ -1099,9 +1141,27 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
   const int CGv = best_cg;
   a.BN = best_bn;
   a.n_tiles = (p->Cout + a.BN - 1) / a.BN;
-  const int stage_bytes = TC_A_BYTES + (a.BN / CGv) * TC_BK * 2;
+  int stage_bytes = TC_A_BYTES + (a.BN / CGv) * TC_BK * 2;
   const int epi_bytes = a.epi_tma ? 4 * 16384 : 0;
   a.stages = (TC_SMEM_BUDGET - epi_bytes) / stage_bytes;
+  a.b_res = 0;
+  int res_bytes = 0;
+  if (var.bres != 0 || g_force_bres != 0) {
+    // resident B: needs the TMA epilogue, a data-parallel schedule, room for the whole K extent of the weight tile next
+    // to >= 3 A stages, and at least two M tiles per worker (otherwise nothing is re-used)
+    const int64_t workers = sms / CGv;
+    const int64_t pm = (a.m_tiles + CGv - 1) / CGv;
+    const int bres_bytes = (a.nk0 + a.nk1) * (a.BN / CGv) * TC_BK * 2;
+    const int st = (TC_SMEM_BUDGET - epi_bytes - bres_bytes) / TC_A_BYTES;
+    const bool ok = a.epi_tma && var.sk == 0 && bres_bytes < TC_SMEM_BUDGET - epi_bytes && st >= 3 && workers >= a.n_tiles &&
+                    pm * a.n_tiles >= 2 * workers;
+    if (ok) {
+      a.b_res = 1; a.n_fast = 0; res_bytes = bres_bytes; ++g_bres_launches;
+      stage_bytes = TC_A_BYTES; a.stages = st;
+    } else if (var.bres != 0) {
+      return PD_ERR_UNSUPPORTED;
+    }
+  }
   if (a.stages > TC_MAX_STAGES) a.stages = TC_MAX_STAGES;
   if (a.stages < 2) { set_error("conv_tc: not enough shared memory for 2 stages"); return PD_ERR_UNSUPPORTED; }
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)((TC_BM * CGv) >> 4) << 24);
@@ -1166,7 +1226,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
     }
   }
 
-  const size_t smem = (size_t)a.stages * stage_bytes + epi_bytes + 1024;
+  const size_t smem = (size_t)res_bytes + (size_t)a.stages * stage_bytes + epi_bytes + 1024;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                            const CUtensorMap, const CUtensorMap, const TcArgs);
 #define PD_TC_ROW(CGv_, SKv_)                                                                                          \
@@ -1263,7 +1323,7 @@ struct TuneKey {
 struct TuneRow { TuneKey k; TcVariant v; };
 static const TuneRow k_tune_table[] = {
 #include "tune_table.inc"
-    {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0}}   // terminator
+    {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0}}   // terminator
 };
 static std::map<TuneKey, TcVariant> g_tune;      // runtime cache: table rows + autotuned shapes (guarded by g_mu)
 static bool g_tune_loaded = false;
@@ -1286,7 +1346,7 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   dbg = g_dbg_mode != 0;
 #endif
   if (g_force_cg != 0 || p->out_dtype != PD_BF16 || dbg)
-    return conv2d_tc_impl(p, s, TcVariant{g_force_cg, g_force_cg != 0 && g_force_sk ? 2 : 0, 0});
+    return conv2d_tc_impl(p, s, TcVariant{g_force_cg, g_force_cg != 0 && g_force_sk ? 2 : 0, 0, 0});
   const int pad = p->ksize / 2;
   const int Ho = p->ksize == 2 ? p->H : (p->H + 2 * pad - p->ksize) / p->stride + 1;
   const int Wo = p->ksize == 2 ? p->W : (p->W + 2 * pad - p->ksize) / p->stride + 1;
@@ -1294,7 +1354,7 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   const TuneKey key{p->B * Ho * Wo, p->Cout, p->ksize * p->ksize * p->C + p->C2, p->ksize, p->stride, 0,
                     p->act == PD_ACT_GEGLU ? 8 : 0};
   bool tabled = false;
-  TcVariant tv{0, 0, 0};
+  TcVariant tv{0, 0, 0, 0};
   {
     std::lock_guard<std::mutex> lk(g_mu);          // released before the launch: conv2d_tc_impl takes g_mu itself
     tune_load_locked();
@@ -1302,23 +1362,31 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
     if (it != g_tune.end()) { tabled = true; tv = it->second; }
   }
   // a tabled stream-K row whose scratch cannot be had falls back to its data-parallel sibling inside impl (sk = 2)
-  if (tabled) return conv2d_tc_impl(p, s, TcVariant{tv.cg, tv.sk ? 2 : 0, tv.bn});
-  if (!g_autotune) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0});
+  if (tabled) {
+    const int rc = conv2d_tc_impl(p, s, TcVariant{tv.cg, tv.sk ? 2 : 0, tv.bn, tv.bres});
+    if (rc != PD_ERR_UNSUPPORTED || !tv.bres) return rc;
+    return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0});    // a resident-B row on a device with fewer SMs than it was tuned for
+  }
+  if (!g_autotune) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0});
   // ---- opt-in timing autotune (table regeneration) ----
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
   const bool in_place = p->res == p->out || p->x == p->out || (p->x2 != nullptr && p->x2 == p->out);
-  if (cap != cudaStreamCaptureStatusNone || in_place || g_prof_on) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0});
+  if (cap != cudaStreamCaptureStatusNone || in_place || g_prof_on) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0});
   cudaEvent_t e0, e1;
-  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaGetLastError(); return conv2d_tc_impl(p, s, TcVariant{0, 0, 0}); }
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaGetLastError(); return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0}); }
   // stream-K with the model's tile width, and with 128-wide tiles: fewer pieces per tile (cheaper fix-up) against
   // more operand traffic per FLOP
-  const TcVariant cands[6] = {{1, 0, 0}, {2, 0, 0}, {2, 1, 0}, {1, 1, 0}, {2, 1, 128}, {1, 1, 128}};
+  // resident-B candidates (short-K layers): tile widths whose whole-K weight tile fits next to the A ring
+  constexpr int NCAND = 13;
+  const TcVariant cands[NCAND] = {{1, 0, 0, 0}, {2, 0, 0, 0}, {2, 1, 0, 0}, {1, 1, 0, 0}, {2, 1, 128, 0}, {1, 1, 128, 0},
+                                  {1, 0, 160, 1}, {2, 0, 160, 1}, {1, 0, 128, 1}, {2, 0, 128, 1}, {2, 0, 192, 1}, {2, 0, 256, 1},
+                                  {1, 0, 96, 1}};
   float best_ms = 1e30f; TcVariant best = cands[0]; int last_run = -1, best_idx = 0;
-  for (int c = 0; c < 6; ++c) {
-    if (cands[c].bn != 0 && (p->Cout < cands[c].bn || p->act == PD_ACT_GEGLU)) continue;
+  for (int c = 0; c < NCAND; ++c) {
+    if (cands[c].bn != 0 && (p->Cout < cands[c].bn || (p->act == PD_ACT_GEGLU && (!cands[c].bres || cands[c].bn % 64 != 0)))) continue;
     int rc = conv2d_tc_impl(p, s, cands[c]);                // warm (tensor maps, L2)
-    if (rc == PD_ERR_UNSUPPORTED && cands[c].sk) continue;  // stream-K does not apply to this shape
+    if (rc == PD_ERR_UNSUPPORTED && (cands[c].sk || cands[c].bres)) continue;  // stream-K / resident B does not apply to this shape
     if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
     float ms = 0.f;
     cudaEventRecord(e0, s);
@@ -1370,12 +1438,15 @@ int pd_tune_dump(const char* path) {
   std::lock_guard<std::mutex> lk(pd::g_mu);
   pd::tune_load_locked();
   for (auto& kv : pd::g_tune)
-    fprintf(f, "{{%d, %d, %d, %d, %d, %d, %d}, {%d, %d, %d}},\n", kv.first.M, kv.first.N, kv.first.K, kv.first.ksize,
-            kv.first.stride, kv.first.c2, kv.first.epi, kv.second.cg, kv.second.sk, kv.second.bn);
+    fprintf(f, "{{%d, %d, %d, %d, %d, %d, %d}, {%d, %d, %d, %d}},\n", kv.first.M, kv.first.N, kv.first.K, kv.first.ksize,
+            kv.first.stride, kv.first.c2, kv.first.epi, kv.second.cg, kv.second.sk, kv.second.bn, kv.second.bres);
   fclose(f);
   return 0;
 }
 int pd_debug_force_bn(int bn) { pd::g_force_bn = (bn >= 32 && bn <= 256 && bn % 32 == 0) ? bn : 0; return 0; }
+// 1 = resident-B schedule wherever it fits (tests / A-B timing), 0 = per the variant table
+int pd_debug_force_bres(int on) { pd::g_force_bres = on != 0; return 0; }
+uint64_t pd_debug_bres_launches(void) { return pd::g_bres_launches; }
 int pd_debug_force_cta_group(int cg) { pd::g_force_cg = (cg == 1 || cg == 2) ? cg : 0; return 0; }
 // with a forced CTA group: 1 = stream-K schedule wherever it applies (falls back to data-parallel elsewhere)
 int pd_debug_force_stream_k(int on) { pd::g_force_sk = on != 0; return 0; }

@@ -698,6 +698,24 @@ static int gn_launch(const void* x, int ldx, void* out, int ldo, const float* ga
     if (want > GN_CHUNKS_MAX) want = GN_CHUNKS_MAX;
     if (want < 1) want = 1;
     if (fchunks > want) fchunks = want;
+    if (sizeof(T) == 4 && g_gn_fused && want <= capacity) {
+      // fp32 mode (the accuracy anchor): the row partition — and with it the fp32 summation order — must not depend on
+      // the batch size, so that a sharded run is bit-identical to the single-GPU one (parallel.sample_sharded).
+      // Always `want` chunks per image; when the whole batch cannot be co-resident, launch it a few images at a time.
+      const int ipl = capacity / want;                       // images per launch
+      for (int b0 = 0; b0 < B; b0 += ipl) {
+        const int nb = B - b0 < ipl ? B - b0 : ipl;
+        const T* xp = (const T*)x + (int64_t)b0 * HW * ldx; TO* op = (TO*)out + (int64_t)b0 * HW * ldo;
+        float* pp = partial + (int64_t)b0 * GN_CHUNKS_MAX * GN_GROUPS_MAX * 2;
+        unsigned int* sw = sync_words + 2 * b0;
+        void* args[] = {(void*)&xp, (void*)&ldx, (void*)&op, (void*)&ldo, (void*)&gamma, (void*)&beta, (void*)&pp,
+                        (void*)&HW, (void*)&C, (void*)&groups, (void*)&want, (void*)&eps, (void*)&act, (void*)&sw};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)gn_fused_kernel<T, TO>, dim3(want, nb), dim3(GN_THREADS),
+                                                    args, st_smem, s);
+        if (e != cudaSuccess) { set_error("pd_group_norm: cooperative launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+      }
+      return check_launch("gn_fused");
+    }
     if (fchunks >= 1 && g_gn_fused) {
       const T* xp = (const T*)x; TO* op = (TO*)out;
       void* args[] = {(void*)&xp, (void*)&ldx, (void*)&op, (void*)&ldo, (void*)&gamma, (void*)&beta, (void*)&partial,

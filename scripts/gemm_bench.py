@@ -47,9 +47,34 @@ ap.add_argument("--blocked", action="store_true", help="k-block-major weight lay
 ap.add_argument("--small", action="store_true", help="fixed-overhead study: tiny and short-K GEMMs")
 ap.add_argument("--modes", action="store_true", help="timing experiment: full kernel vs no-MMA vs no-TMA, per tile shape")
 ap.add_argument("--epi-modes", action="store_true", help="timing experiment on the epilogue of short-K layers (gemm_sm100.cu dbg_mode 3..7)")
+ap.add_argument("--bres", action="store_true", help="resident-B schedule against the tabled variant on the short-K layer shapes")
 a = ap.parse_args()
 BLOCKED = a.blocked
-if a.small:
+if a.bres:
+    from prompt_diffusion_b200 import _lib
+    L = _lib.lib
+    BLOCKED = True     # the packed model weights are k-block-major
+    shapes = [(16, 64, 64, 320, 320, 1, 1), (16, 64, 64, 320, 320, 1, 0), (16, 64, 64, 320, 960, 1, 0), (16, 64, 64, 320, 2560, 1, 0),
+              (16, 32, 32, 640, 640, 1, 1), (16, 32, 32, 640, 640, 1, 0), (16, 32, 32, 640, 1920, 1, 0), (16, 32, 32, 640, 5120, 1, 0),
+              (16, 16, 16, 1280, 1280, 1, 1)]
+    combos = [(1, 96), (1, 128), (1, 160), (2, 128), (2, 160), (2, 192), (2, 256)]
+    print("   B   HxW     C     N ks res | tabled us | " + " | ".join("cg%d bn%-3d" % c for c in combos) + "   (resident B; '-' = does not fit / apply)")
+    for s_ in shapes:
+        base = run(*s_, iters=a.iters)[0]
+        row = []
+        for cg, bn in combos:
+            if s_[4] < bn: row.append(None); continue
+            L.pd_debug_force_cta_group(cg); L.pd_debug_force_bn(bn); L.pd_debug_force_bres(1)
+            n0 = L.pd_debug_bres_launches()
+            try:
+                us = run(*s_, iters=a.iters)[0]
+            except RuntimeError:
+                us = None
+            took = L.pd_debug_bres_launches() > n0
+            L.pd_debug_force_cta_group(0); L.pd_debug_force_bn(0); L.pd_debug_force_bres(0)
+            row.append(us if took else None)
+        print("%4d %3dx%-3d %5d %5d %2d %3d | %9.1f | " % (*s_, base) + " | ".join("%9.1f" % r if r is not None else "        -" for r in row))
+elif a.small:
     print("   B   HxW     C     N ks res |     us")
     for s_ in [(1, 1, 128, 64, 64, 1, 0), (1, 1, 128 * 148, 64, 64, 1, 0), (1, 1, 128 * 148, 320, 128, 1, 0), (1, 1, 128 * 148, 320, 256, 1, 0),
                (1, 1, 128 * 148 * 2, 320, 256, 1, 0), (1, 1, 128 * 148 * 4, 320, 256, 1, 0), (1, 1, 128 * 148 * 4, 320, 256, 1, 1),
@@ -84,6 +109,10 @@ elif a.epi_modes:
         print("%4d %3dx%-3d %5d %5d %2d %3d | " % s_ + " | ".join("%6.1f" % r for r in row))
     _lib.lib.pd_debug_force_cta_group(0)
 elif a.one:
+    if os.environ.get("PD_BENCH_BRES"):          # "cg,bn": resident-B schedule with that tile (ncu captures)
+        from prompt_diffusion_b200 import _lib
+        cg_, bn_ = [int(v) for v in os.environ["PD_BENCH_BRES"].split(",")]
+        _lib.lib.pd_debug_force_cta_group(cg_); _lib.lib.pd_debug_force_bn(bn_); _lib.lib.pd_debug_force_bres(1)
     B, H, W, C, N, ks, res = a.one
     us, tf, gb = run(B, H, W, C, N, ks, bool(res), iters=a.iters, warm=2)
     print(f"B{B} {H}x{W} C{C}->N{N} k{ks} res={res}: {us:.1f} us  {tf:.0f} TFLOP/s  {gb:.0f} GB/s")

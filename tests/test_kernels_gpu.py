@@ -189,6 +189,39 @@ def test_conv_tcgen05_bf16_stream_k(case, cg):
     assert err2 == err
 
 
+BRES_CASES = [
+    # (case, cta group, pinned tile width): shapes with >= 2 M tiles per worker and a whole-K weight tile that fits
+    (dict(B=16, H=64, W=32, C=320, Cout=320, ksize=1, res=True), 1, 160),                # proj_in / to_out at C = 320
+    (dict(B=16, H=64, W=32, C=320, Cout=352, ksize=1, res=True, alpha=0.5, ldo_extra=64), 1, 160),   # partial last N tile
+    (dict(B=16, H=64, W=32, C=320, Cout=320, ksize=1, res=True), 2, 160),
+    (dict(B=16, H=32, W=32, C=640, Cout=640, ksize=1, res=True), 2, 160),                # C = 640: 100 KiB per CTA of a pair
+    (dict(B=16, H=64, W=64, C=64, Cout=64, ksize=3, rowvec=True, act=1), 1, 64),         # spatial tiles, 9 taps resident
+    (dict(B=16, H=64, W=64, C=64, Cout=128, ksize=3, C2=64), 2, 128),                     # second K segment
+    (dict(B=8, H=32, W=32, C=320, Cout=960, ksize=1), 2, 192),                           # to_q|k|v: 5 N tiles over 74 pairs
+    (dict(B=8, H=64, W=64, C=320, Cout=320, ksize=1, blocked=True), 1, 160),             # k-block-major weights (3-D map)
+]
+
+
+@pytest.mark.parametrize("case,cg,bn", BRES_CASES)
+def test_conv_tcgen05_bf16_resident_weights(case, cg, bn):
+    """Resident-B schedule forced on: every worker loads its weight tile (all K blocks) into shared memory once, keeps
+    one N tile for life and streams activations only.  Bits must equal the ordinary data-parallel schedule of the same
+    tile shape (same MMAs in the same order), and the path must actually have been taken."""
+    from prompt_diffusion_b200 import _lib
+    L = _lib.lib
+    L.pd_debug_force_cta_group(cg); L.pd_debug_force_bn(bn)
+    try:
+        ref_err = _conv_case(torch.bfloat16, _lib.PD_ENGINE_TC, **case)
+        n0 = L.pd_debug_bres_launches()
+        L.pd_debug_force_bres(1)
+        err = _conv_case(torch.bfloat16, _lib.PD_ENGINE_TC, **case)
+        assert L.pd_debug_bres_launches() == n0 + 1, "shape did not take the resident-B schedule"
+    finally:
+        L.pd_debug_force_bres(0); L.pd_debug_force_cta_group(0); L.pd_debug_force_bn(0)
+    assert err < 6e-3, err
+    assert err == ref_err, (err, ref_err)
+
+
 def test_conv_tc_rejects_unsupported():
     from prompt_diffusion_b200._lib import PD_ENGINE_TC
     with pytest.raises(RuntimeError):

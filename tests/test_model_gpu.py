@@ -313,6 +313,22 @@ def test_full_size_batch_properties(models, cfg):
         else:
             assert e1 <= 1e-2 and e2r <= 1e-2
 
+def test_fp32_eps_does_not_depend_on_the_batch_partition(models, cfg):
+    """What parallel.sample_sharded's bit-identity claim rests on (tests/test_multigpu.py runs it over NCCL on 2 GPUs):
+    in fp32 mode the eps of a prompt is the same bits whether it is computed in a batch of 3, 2 or 1 — no kernel's
+    summation order may depend on the batch size (GroupNorm's row partition did, through `capacity / B` chunks per
+    image: at 16x16 x 1280 channels a batch of 6 got 49 chunks, a batch of 2 got 64)."""
+    inp, cond, un, x_in, c_in = _cfg_inputs(cfg, 3, 128, 128)
+    m = models["fp32"]
+    B = x_in.shape[0]
+    t = torch.full((B,), 621, dtype=torch.long, device=DEV)
+    full = m.apply_model(x_in, t, c_in)
+    for rows in ([0, 1, 3, 4], [2, 5], [1, 4], list(range(B)) + list(range(B))):
+        idx = torch.tensor(rows, device=DEV)
+        part = m.apply_model(x_in[idx].contiguous(), t[idx], {k: [v[0][idx].contiguous()] for k, v in c_in.items()})
+        assert torch.equal(part, full[idx]), (rows, rel_l2(part, full[idx]))
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_apply_model_cfg_equals_duplicated_batch(models, cfg, mode):
     """The sampler's guided step calls ``apply_model_cfg(x, t, c_in)`` instead of ``apply_model(cat([x] * 2),
