@@ -22,10 +22,15 @@
 #include <mutex>
 #include <string>
 #include <tuple>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
 #include "tc_ptx.cuh"
+
+#ifndef PD_EPI_GB
+#define PD_EPI_GB 2
+#endif
 
 namespace pd {
 
@@ -89,10 +94,15 @@ constexpr int SK_SLOT_FLOATS = 256 * 128;   // one CTA's half of a partial tile:
 struct PieceIter {
   int sk, nkb, num_tiles, step, tile;
   long long u, u_end;
+  // (quotient, remainder) of the tile index by `div` (n_fast: the N tile count, else the M (pair) tile count), kept
+  // incrementally for the data-parallel schedules: no integer division per tile on the roles' critical paths.
+  // cq / cr belong to the tile next() returned last, q / r to the one it will return next.
+  int div, q, r, dq, dr, cq, cr;
   // n_tiles_res > 0 (resident-B launches, tiles numbered N-major: tile = nt * pm_tiles + pmt): worker w owns N tile
   // w % n_tiles_res for life and strides over that tile's M tiles together with the other workers of the same residue.
-  __device__ PieceIter(int sk_, int worker, int nworkers, int num_tiles_, int nkb_, int n_tiles_res = 0) {
+  __device__ PieceIter(int sk_, int worker, int nworkers, int num_tiles_, int nkb_, int div_, int n_tiles_res = 0) {
     sk = sk_; nkb = nkb_; num_tiles = num_tiles_; step = nworkers; tile = worker; u = 0; u_end = 0;
+    div = div_; cq = cr = 0;
     if (n_tiles_res > 0) {
       const int nt = worker % n_tiles_res, pm_tiles = num_tiles_ / n_tiles_res;
       step = (nworkers - nt + n_tiles_res - 1) / n_tiles_res;      // workers with this residue
@@ -100,6 +110,8 @@ struct PieceIter {
       num_tiles = (nt + 1) * pm_tiles;
       if (worker / n_tiles_res >= pm_tiles) tile = num_tiles;      // more workers than M tiles: nothing to do
     }
+    q = tile / div; r = tile - q * div;
+    dq = step / div; dr = step - dq * div;
     if (sk) {
       const long long U = (long long)num_tiles * nkb;
       u = U * worker / nworkers;
@@ -110,6 +122,9 @@ struct PieceIter {
     if (!sk) {
       if (tile >= num_tiles) return false;
       t = tile; kb0 = 0; kb1 = nkb; tile += step;
+      cq = q; cr = r;
+      q += dq; r += dr;
+      if (r >= div) { r -= div; ++q; }
       return true;
     }
     if (u >= u_end) return false;
@@ -118,12 +133,22 @@ struct PieceIter {
     const long long rem = u_end - u;
     kb1 = rem < (long long)(nkb - kb0) ? kb0 + (int)rem : nkb;
     u += kb1 - kb0;
+    cq = t / div; cr = t - cq * div;
     return true;
   }
   // tile of the piece the following next() will return, -1 if none (called after next())
   __device__ int peek_tile() const {
     if (!sk) return tile < num_tiles ? tile : -1;
     return u < u_end ? (int)(u / nkb) : -1;
+  }
+  // (N tile, M (pair) tile) of the tile next() returned last / of the tile peek_tile() names
+  __device__ void coords(int n_fast, int& nt, int& pmt) const {
+    if (n_fast) { pmt = cq; nt = cr; } else { nt = cq; pmt = cr; }
+  }
+  __device__ void peek_coords(int n_fast, int& nt, int& pmt) const {
+    int pq = q, pr = r;
+    if (sk) { const int t = (int)(u / nkb); pq = t / div; pr = t - pq * div; }
+    if (n_fast) { pmt = pq; nt = pr; } else { nt = pq; pmt = pr; }
   }
 };
 
@@ -157,10 +182,13 @@ struct PieceIter {
 //     separate GEGLU pass over it never exist
 // 10 / 11 = plain / GEGLU epilogue of a linear layer with the preceding LayerNorm folded in: the accumulator of the
 //     raw rows against gamma-scaled weights becomes rstd[m] * (acc - mean[m] * colsum[n]) + bias'[n]
+// ST: 1 = the epilogue also emits statistics of its output (GroupNorm column records gn_out / LayerNorm row partials
+// ln_parts_out); a separate instantiation (EPI 0..7 only) so that the ordinary kernels do not carry that code and its
+// ~60 loop-invariant registers (they spilled in every epilogue).
 // CG: 1 = one CTA per 128-row tile; 2 = CTA pair (cluster of 2, tcgen05 cta_group::2) per 256-row tile: each CTA
 // stages its own 128 A rows and HALF of the B tile, which halves the L2 -> smem weight traffic per FLOP (the
 // 1-CTA kernel is bound by exactly that traffic: 128 x (128 + BN) bytes per 128 x BN x 64 MACs).
-template <int EPI, int CG, int SK>
+template <int EPI, int CG, int SK, int ST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_o64,
@@ -188,6 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   unsigned char* ring = smem + (bres ? nkb * b_bytes : 0);    // resident B: [nkb][b_rows x 64] in front of the A ring
   const int nt_res = bres ? a.n_tiles : 0;
   const int pm_tiles = (a.m_tiles + CG - 1) / CG;      // M tiles of CG x 128 rows
+  const int tile_div = a.n_fast ? a.n_tiles : pm_tiles;
   const int num_tiles = pm_tiles * a.n_tiles;
   const int worker = blockIdx.x / CG, nworkers = gridDim.x / CG;
 
@@ -224,7 +253,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ================= TMA producer (both CTAs of a pair); warp-uniform loop, one elected lane issues =================
     {
       int stage = 0; uint32_t phase = 0;
-      PieceIter pit(SK, worker, nworkers, num_tiles, nkb, nt_res);
+      PieceIter pit(SK, worker, nworkers, num_tiles, nkb, tile_div, nt_res);
       int tile, kb0, kb1, tix = 0;
       if (bres && pit.peek_tile() >= 0 && elect_one()) {
         // the worker's weight tile, every K block, once (the even CTA's barrier collects both CTAs' bytes)
@@ -244,11 +273,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       __syncwarp();
       for (; pit.next(tile, kb0, kb1); ++tix) {
         int nt, pmt;
-        PD_TILE_COORDS(tile, nt, pmt);
+        pit.coords(a.n_fast, nt, pmt);
         const int mt = pmt * CG + (int)cta_rank;
-        const int txi = mt % a.tiles_x;
-        const int tyi = (mt / a.tiles_x) % a.tiles_y;
-        const int tbi = mt / (a.tiles_x * a.tiles_y);   // >= tiles_b for the phantom half of an odd last pair: TMA zero-fills
+        // (tbi >= tiles_b / txi >= tiles_x for the phantom half of an odd last pair: TMA zero-fills)
+        int txi = mt, tyi = 0, tbi = 0;
+        if (!a.flat) { txi = mt % a.tiles_x; tyi = (mt / a.tiles_x) % a.tiles_y; tbi = mt / (a.tiles_x * a.tiles_y); }
         const int x0 = txi * a.bw, y0 = tyi * a.bh, b0 = tbi * a.bn, n0 = nt * a.BN + (int)cta_rank * b_rows;
         if (!SK && pit.peek_tile() < 0 && lane == 0) griddep_launch();   // last tile of this CTA: let the next kernel in
         if (lane == 0) PD_DBG(0, tix, 0);
@@ -305,7 +334,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (cta_rank == 0) {
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      PieceIter pit(SK, worker, nworkers, num_tiles, nkb, nt_res);
+      PieceIter pit(SK, worker, nworkers, num_tiles, nkb, tile_div, nt_res);
       int tile, kb0, kb1;
       if (bres && pit.peek_tile() >= 0) { mbar_wait(&b_full, 0, 250); tc_fence_after(); }
       for (; pit.next(tile, kb0, kb1); ++it) {
@@ -460,27 +489,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint64_t* rbar = &res_full[grp * 2];
     uint32_t res_phase = 0;                // residual barriers complete once per tile that loads a residual
     const bool elected = (ew & 3) == 0 && lane == 0;
+    // non-GEGLU epilogues: staging buffer i of the group is driven (TMA loads / stores / waits) by lane 0 of warp i,
+    // lane 0 of warps 2, 3 prefetch the next tile's residual slabs
+    const int drv = (!GEGLU && lane == 0 && (ew & 3) < 2) ? (ew & 3) : (GEGLU && elected ? 0 : -1);
+    const int pfi = (lane == 0 && (ew & 3) >= 2) ? (ew & 3) - 2 : -1;
     const int bar_id = 1 + grp;
+    const uint32_t swz_row64 = (uint32_t)(r * 128 + ((r & 7) << 4)), swz_row32 = (uint32_t)(r * 64 + (((r >> 1) & 3) << 4));
     const int n64 = a.BN >> 6, nslabs = n64 + ((a.BN & 63) ? 1 : 0);
     const int ns_mine = (nslabs > grp ? 1 : 0) + (nslabs > grp + 2 ? 1 : 0);
     const float alpha = a.alpha;
     const long long sk_units = (long long)num_tiles * nkb;
-    if (!LNF && a.ln_parts_out != nullptr && blockIdx.x == 0 && ew == 0 && lane == 0)
+    if (!LNF && (ST != 0 && a.ln_parts_out != nullptr) && blockIdx.x == 0 && ew == 0 && lane == 0)
       *reinterpret_cast<int*>(a.ln_parts_out) = a.n_tiles * 2;       // header: partial count of this launch
     int ln_nparts = 0;
     if (LNF && a.ln_parts_in != nullptr) ln_nparts = __ldg(reinterpret_cast<const int*>(a.ln_parts_in));
     int it = 0;
-    PieceIter pit(SK, worker, nworkers, num_tiles, nkb, nt_res);
+    PieceIter pit(SK, worker, nworkers, num_tiles, nkb, tile_div, nt_res);
     int tile, kb0, kb1;
     for (; pit.next(tile, kb0, kb1); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       int nt, pmt;
-      PD_TILE_COORDS(tile, nt, pmt);
+      pit.coords(a.n_fast, nt, pmt);
       const int mt = pmt * CG + (int)cta_rank;
-      const int txi = mt % a.tiles_x;
-      const int tyi = (mt / a.tiles_x) % a.tiles_y;
-      const int tbi = mt / (a.tiles_x * a.tiles_y);
+      // flattened 1x1 layers (one long pixel row): no divisions on the epilogue's per-tile chain
+      int txi = mt, tyi = 0, tbi = 0;
+      if (!a.flat) { txi = mt % a.tiles_x; tyi = (mt / a.tiles_x) % a.tiles_y; tbi = mt / (a.tiles_x * a.tiles_y); }
       const int x0 = txi * a.bw, y0 = tyi * a.bh, b0 = tbi * a.bn;
       const int x = x0 + rx, y = y0 + ry, b = b0 + rb;
       const bool row_ok = x < a.Wo && y < a.Ho && b < a.B;
@@ -516,29 +550,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if constexpr (RES) {
           // with column statistics on, the other warps of the group may still be reading the staging buffers of the
           // previous tile: nobody refills them before everybody is done
-          if (a.gn_out != nullptr) epi_bar_sync(bar_id);
-          if (elected) {
+          if ((ST != 0 && a.gn_out != nullptr)) epi_bar_sync(bar_id);
+          // Buffer i has its own driver thread (lane 0 of the group's warp i): it waits for ITS store of the previous
+          // tile to have read the buffer and refills it with the residual slab; lane 0 of warps 2, 3 pull the next
+          // tile's slabs into L2 meanwhile.  Nobody else waits here: the mbarrier wait in front of the arithmetic is
+          // the only synchronisation the data needs (a single elected thread issuing five TMA instructions in a row
+          // behind a group barrier cost ~1 us per tile on the short-K layers, timeline in profiles/).
+          if (drv >= 0 && drv < ns_mine) {
             tma_store_wait_read<0>();
-            for (int i = 0; i < ns_mine; ++i) {
-              const int sl = grp + 2 * i;
-              const int w = sl < n64 ? 64 : 32;
-              mbar_expect_tx(&rbar[i], (uint32_t)(128 * w * 2));
-              tma_load_4d(gstg + i * 16384, w == 64 ? &map_r64 : &map_r32, &rbar[i], n0 + sl * 64, x0, y0, b0);
+            const int sl = grp + 2 * drv;
+            const int w = sl < n64 ? 64 : 32;
+            mbar_expect_tx(&rbar[drv], (uint32_t)(128 * w * 2));
+            tma_load_4d(gstg + drv * 16384, w == 64 ? &map_r64 : &map_r32, &rbar[drv], n0 + sl * 64, x0, y0, b0);
+          } else if (pfi >= 0 && pfi < ns_mine && pit.peek_tile() >= 0) {
+            int nnt, npmt;
+            pit.peek_coords(a.n_fast, nnt, npmt);
+            const int nmt = npmt * CG + (int)cta_rank;
+            int nx0 = nmt * a.bw, ny0 = 0, nb0 = 0;
+            if (!a.flat) {
+              nx0 = (nmt % a.tiles_x) * a.bw; ny0 = ((nmt / a.tiles_x) % a.tiles_y) * a.bh;
+              nb0 = (nmt / (a.tiles_x * a.tiles_y)) * a.bn;
             }
-            const int ntile = pit.peek_tile();
-            if (ntile >= 0) {
-              int nnt, npmt;
-              PD_TILE_COORDS(ntile, nnt, npmt);
-              const int nmt = npmt * CG + (int)cta_rank;
-              const int nx0 = (nmt % a.tiles_x) * a.bw, ny0 = ((nmt / a.tiles_x) % a.tiles_y) * a.bh;
-              const int nb0 = (nmt / (a.tiles_x * a.tiles_y)) * a.bn;
-              for (int i = 0; i < ns_mine; ++i) {
-                const int sl = grp + 2 * i;
-                tma_prefetch_4d(sl < n64 ? &map_r64 : &map_r32, nnt * a.BN + sl * 64, nx0, ny0, nb0);
-              }
-            }
+            const int sl = grp + 2 * pfi;
+            tma_prefetch_4d(sl < n64 ? &map_r64 : &map_r32, nnt * a.BN + sl * 64, nx0, ny0, nb0);
           }
-          epi_bar_sync(bar_id);
         }
       };
       const bool partial = SK != 0 && (kb1 - kb0) != nkb;
@@ -591,7 +626,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           __syncwarp();
           if (lane == 0) { if (CG == 2) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]); }
         }
-        if (!LNF && a.ln_parts_out != nullptr && row_ok)      // reached by whole tiles and by the stream-K reducer
+        if (!LNF && (ST != 0 && a.ln_parts_out != nullptr) && row_ok)      // reached by whole tiles and by the stream-K reducer
           reinterpret_cast<float2*>(a.ln_parts_out + 4)[(long long)(nt * 2 + grp) * a.ln_rows + m] = make_float2(0.f, 0.f);
         if (RES) res_phase ^= 1u;
         continue;
@@ -640,6 +675,89 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if constexpr (GEGLU) tma_store_4d(&map_o32, stg, (n0 + col0) >> 1, x0, y0, b0);
         else tma_store_4d(w == 64 ? &map_o64 : &map_o32, stg, n0 + col0, x0, y0, b0);
       };
+      // The W (64 or 32, compile time) columns of one slab: + bias, * alpha, + emb row, + residual (in place in the staging
+      // buffer), act, bf16, into the TMA-swizzled slab.  Two 8-column groups at a time with every parameter load (bias,
+      // column sums, emb row, residual chunk) issued ahead of the arithmetic: the per-group chain load -> add -> pack ->
+      // store was the latency that bound the short-K layers' epilogue (1.1 us of "math" per 128 x 160 tile, timeline).
+      auto slab_cols = [&](auto Wc, const int col0, const uint32_t stg_s, const uint32_t (&v)[64]) {
+        constexpr int W = decltype(Wc)::value;
+        constexpr int GB = PD_EPI_GB;          // 8-column groups whose parameter loads are issued together
+#pragma unroll
+        for (int g0 = 0; g0 < W / 8; g0 += GB) {
+          float4 bq[GB][2], cq[GB][2], rq[GB][2];
+          bf16x8 rs[GB];
+          uint32_t cell[GB];
+          bool in_cout[GB];
+#pragma unroll
+          for (int j = 0; j < GB; ++j) {
+            const int g = g0 + j;
+            // columns past Cout exist only in a partial last N tile; TMA clips them, the clamp keeps the reads legal
+            const int n = min(n0 + col0 + g * 8, a.Cout - 8);
+            in_cout[j] = n0 + col0 + g * 8 < a.Cout;
+            bq[j][0] = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+            bq[j][1] = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
+            if constexpr (LNF) {
+              cq[j][0] = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n));
+              cq[j][1] = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n + 4));
+            }
+            if constexpr (RV) {
+              rq[j][0] = __ldg(reinterpret_cast<const float4*>(rvp + n));
+              rq[j][1] = __ldg(reinterpret_cast<const float4*>(rvp + n + 4));
+            }
+            // 16-byte chunk g of row r inside the TMA-swizzled slab (SWIZZLE_128B / SWIZZLE_64B rows): the swizzle is an
+            // XOR of the chunk index into bits the 1024-aligned base and the row offset leave free
+            cell[j] = (stg_s + (W == 64 ? swz_row64 : swz_row32)) ^ (uint32_t)(g << 4);
+            if constexpr (RES) rs[j] = lds_bf16x8(cell[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < GB; ++j) {
+            const int g = g0 + j;
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+            if constexpr (LNF) {
+              const float cs[8] = {cq[j][0].x, cq[j][0].y, cq[j][0].z, cq[j][0].w, cq[j][1].x, cq[j][1].y, cq[j][1].z, cq[j][1].w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = (f[e] - ln_mu * cs[e]) * ln_rs;
+            }
+            {
+              const float4 q0 = bq[j][0], q1 = bq[j][1];
+              f[0] = (f[0] + q0.x) * alpha; f[1] = (f[1] + q0.y) * alpha; f[2] = (f[2] + q0.z) * alpha;
+              f[3] = (f[3] + q0.w) * alpha; f[4] = (f[4] + q1.x) * alpha; f[5] = (f[5] + q1.y) * alpha;
+              f[6] = (f[6] + q1.z) * alpha; f[7] = (f[7] + q1.w) * alpha;
+            }
+            if constexpr (RV) {
+              const float4 q0 = rq[j][0], q1 = rq[j][1];
+              f[0] += q0.x; f[1] += q0.y; f[2] += q0.z; f[3] += q0.w;
+              f[4] += q1.x; f[5] += q1.y; f[6] += q1.z; f[7] += q1.w;
+            }
+            if constexpr (RES) {
+              float rf[8];
+              unpack8(rs[j], rf);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += rf[e];
+            }
+            if constexpr (ACT) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
+            }
+            const bf16x8 pk = pack8(f);
+            sts_bf16x8(cell[j], pk);
+            if (!LNF && (ST != 0 && a.ln_parts_out != nullptr) && in_cout[j]) {
+              float rf[8];
+              unpack8(pk, rf);                       // statistics of the values as STORED (bf16-rounded)
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {       // packed fp32x2: half the issue slots
+                fadd2(lnp_s, lnp_s2, lnp_s, lnp_s2, rf[e], rf[e + 1]);
+                ffma2(lnp_q, lnp_q2, rf[e], rf[e + 1], rf[e], rf[e + 1], lnp_q, lnp_q2);
+              }
+            }
+          }
+          // scheduling fence: without it ptxas hoists the parameter loads of EVERY group of both slabs above the
+          // arithmetic (128 more live registers next to the 128 accumulator values) and spills
+          asm volatile("" ::: "memory");
+        }
+      };
       // per-element epilogue of one slab into its staging buffer
       auto slab_math = [&](int i, const uint32_t (&v)[64]) {
         const int sl = grp + 2 * i;
@@ -680,60 +798,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             sts_bf16x8(stg_s + (uint32_t)off, pack8(f));
           }
         } else {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (g * 8 < w) {
-              // columns past Cout exist only in a partial last N tile; TMA clips them, the clamp keeps the reads legal
-              const int n = min(n0 + col0 + g * 8, a.Cout - 8);
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
-              if constexpr (LNF) {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.ln_colsum + n + 4));
-                const float cs[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = (f[e] - ln_mu * cs[e]) * ln_rs;
-              }
-              {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.bias + n));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.bias + n + 4));
-                f[0] = (f[0] + q0.x) * alpha; f[1] = (f[1] + q0.y) * alpha; f[2] = (f[2] + q0.z) * alpha;
-                f[3] = (f[3] + q0.w) * alpha; f[4] = (f[4] + q1.x) * alpha; f[5] = (f[5] + q1.y) * alpha;
-                f[6] = (f[6] + q1.z) * alpha; f[7] = (f[7] + q1.w) * alpha;
-              }
-              if (RV) {
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(rvp + n));
-                const float4 q1 = __ldg(reinterpret_cast<const float4*>(rvp + n + 4));
-                f[0] += q0.x; f[1] += q0.y; f[2] += q0.z; f[3] += q0.w;
-                f[4] += q1.x; f[5] += q1.y; f[6] += q1.z; f[7] += q1.w;
-              }
-              // 16-byte chunk g of row r inside the TMA-swizzled slab (SWIZZLE_128B / SWIZZLE_64B rows)
-              const int off = w == 64 ? r * 128 + ((g ^ (r & 7)) << 4) : r * 64 + ((g ^ ((r >> 1) & 3)) << 4);
-              const uint32_t cell = stg_s + (uint32_t)off;
-              if (RES) {
-                float rf[8];
-                unpack8(lds_bf16x8(cell), rf);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] += rf[e];
-              }
-              if (ACT) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = silu_f(f[e]);
-              }
-              const bf16x8 pk = pack8(f);
-              sts_bf16x8(cell, pk);
-              if (!LNF && a.ln_parts_out != nullptr && n0 + col0 + g * 8 < a.Cout) {
-                float rf[8];
-                unpack8(pk, rf);                       // statistics of the values as STORED (bf16-rounded)
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {       // packed fp32x2: half the issue slots
-                  fadd2(lnp_s, lnp_s2, lnp_s, lnp_s2, rf[e], rf[e + 1]);
-                  ffma2(lnp_q, lnp_q2, rf[e], rf[e + 1], rf[e], rf[e + 1], lnp_q, lnp_q2);
-                }
-              }
-            }
-          }
+          if (w == 64) slab_cols(std::integral_constant<int, 64>{}, col0, stg_s, v);
+          else slab_cols(std::integral_constant<int, 32>{}, col0, stg_s, v);
         }
       };
       // GroupNorm column statistics of slab i, read back from the staging buffer (bf16 as stored) after the group
@@ -830,7 +896,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           mbar_wait(&rbar[0], res_phase, 500 + grp * 2);
           if (ns_mine > 1) mbar_wait(&rbar[1], res_phase, 501 + grp * 2);
         } else {
-          if (elected && !PD_MODE_IS(3)) tma_store_wait_read<0>();   // issued a whole tile ago: normally no wait at all
+          if (drv >= 0 && !PD_MODE_IS(3)) tma_store_wait_read<0>();  // issued a whole tile ago: normally no wait at all
           epi_bar_sync(bar_id);
         }
         if (ew == 0 && lane == 0) PD_DBG(3, it, 1);
@@ -841,21 +907,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
         epi_bar_sync(bar_id);
         if (ew == 0 && lane == 0) PD_DBG(4, it, 1);
-        if (elected && !PD_MODE_IS(3)) {
-          for (int i = 0; i < ns_mine; ++i) store_slab(i);
-          tma_store_commit();
-        }
-        if (a.gn_out != nullptr) {
+        if (drv >= 0 && drv < ns_mine && !PD_MODE_IS(3)) { store_slab(drv); tma_store_commit(); }
+        if ((ST != 0 && a.gn_out != nullptr)) {
           col_stats(0);
           if (ns_mine > 1) col_stats(1);
         }
-        if (!LNF && a.ln_parts_out != nullptr && row_ok)
+        if (!LNF && (ST != 0 && a.ln_parts_out != nullptr) && row_ok)
           reinterpret_cast<float2*>(a.ln_parts_out + 4)[(long long)(nt * 2 + grp) * a.ln_rows + m] = make_float2(lnp_s + lnp_s2, lnp_q + lnp_q2);
       }
       if (RES) res_phase ^= 1u;
       if (ew == 0 && lane == 0) PD_DBG(2, it, 1);
     }
-    if (elected) tma_store_wait_all();     // smem must outlive the bulk stores
+    if (drv >= 0) tma_store_wait_all();    // smem must outlive the bulk stores
   }
 
   tc_fence_before();
@@ -1230,23 +1293,30 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
                            const CUtensorMap, const CUtensorMap, const TcArgs);
 #define PD_TC_ROW(CGv_, SKv_)                                                                                          \
-  {conv_tc_kernel<0, CGv_, SKv_>, conv_tc_kernel<1, CGv_, SKv_>, conv_tc_kernel<2, CGv_, SKv_>,                      \
-   conv_tc_kernel<3, CGv_, SKv_>, conv_tc_kernel<4, CGv_, SKv_>, conv_tc_kernel<5, CGv_, SKv_>,                      \
-   conv_tc_kernel<6, CGv_, SKv_>, conv_tc_kernel<7, CGv_, SKv_>, nullptr, conv_tc_kernel<9, CGv_, SKv_>,            \
-   conv_tc_kernel<10, CGv_, SKv_>, conv_tc_kernel<11, CGv_, SKv_>}
-  static KernelFn kernels[2][2][12] = {{PD_TC_ROW(1, 0), PD_TC_ROW(2, 0)}, {PD_TC_ROW(1, 1), PD_TC_ROW(2, 1)}};
+  {conv_tc_kernel<0, CGv_, SKv_, 0>, conv_tc_kernel<1, CGv_, SKv_, 0>, conv_tc_kernel<2, CGv_, SKv_, 0>,             \
+   conv_tc_kernel<3, CGv_, SKv_, 0>, conv_tc_kernel<4, CGv_, SKv_, 0>, conv_tc_kernel<5, CGv_, SKv_, 0>,             \
+   conv_tc_kernel<6, CGv_, SKv_, 0>, conv_tc_kernel<7, CGv_, SKv_, 0>, nullptr, conv_tc_kernel<9, CGv_, SKv_, 0>,   \
+   conv_tc_kernel<10, CGv_, SKv_, 0>, conv_tc_kernel<11, CGv_, SKv_, 0>}
+#define PD_TC_ROW_ST(CGv_, SKv_)                                                                                       \
+  {conv_tc_kernel<0, CGv_, SKv_, 1>, conv_tc_kernel<1, CGv_, SKv_, 1>, conv_tc_kernel<2, CGv_, SKv_, 1>,             \
+   conv_tc_kernel<3, CGv_, SKv_, 1>, conv_tc_kernel<4, CGv_, SKv_, 1>, conv_tc_kernel<5, CGv_, SKv_, 1>,             \
+   conv_tc_kernel<6, CGv_, SKv_, 1>, conv_tc_kernel<7, CGv_, SKv_, 1>, nullptr, nullptr, nullptr, nullptr}
+  static KernelFn kernels[2][2][2][12] = {{{PD_TC_ROW(1, 0), PD_TC_ROW(2, 0)}, {PD_TC_ROW(1, 1), PD_TC_ROW(2, 1)}},
+                                          {{PD_TC_ROW_ST(1, 0), PD_TC_ROW_ST(2, 0)}, {PD_TC_ROW_ST(1, 1), PD_TC_ROW_ST(2, 1)}}};
 #undef PD_TC_ROW
+#undef PD_TC_ROW_ST
   static bool attr_set[PD_MAX_DEVICES] = {false};    // function attributes are per device (context)
   std::unique_lock<std::mutex> init_lk(g_mu);
   if (!attr_set[dev]) {
-    kernels[0][0][8] = conv_tc_kernel<8, 1, 0>;      // fp32 output: legacy epilogue, single CTA, data-parallel only
-    for (int k = 0; k < 2; ++k)
-      for (int c = 0; c < 2; ++c)
-        for (int i = 0; i < 12; ++i) {
-          if (kernels[k][c][i] == nullptr) continue;
-          cudaError_t e = cudaFuncSetAttribute(kernels[k][c][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-          if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        }
+    kernels[0][0][0][8] = conv_tc_kernel<8, 1, 0, 0>;   // fp32 output: legacy epilogue, single CTA, data-parallel only
+    for (int t = 0; t < 2; ++t)
+      for (int k = 0; k < 2; ++k)
+        for (int c = 0; c < 2; ++c)
+          for (int i = 0; i < 12; ++i) {
+            if (kernels[t][k][c][i] == nullptr) continue;
+            cudaError_t e = cudaFuncSetAttribute(kernels[t][k][c][i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+            if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+          }
     attr_set[dev] = true;
   }
   const int epi = !a.epi_tma ? 8 : (p->ln_stats != nullptr || p->ln_parts != nullptr) ? (p->act == PD_ACT_GEGLU ? 11 : 10) : p->act == PD_ACT_GEGLU ? 9
@@ -1291,7 +1361,9 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
     cudaEventRecord(rec.e0, s);
   }
   {
-    cudaError_t e = launch_pdl(kernels[a.sk][CGv - 1][epi], dim3((unsigned)grid), dim3(TC_THREADS), smem, s, (unsigned)CGv,
+    const int st = (a.gn_out != nullptr || a.ln_parts_out != nullptr) ? 1 : 0;
+    if (kernels[st][a.sk][CGv - 1][epi] == nullptr) { set_error("conv_tc: no kernel for epilogue %d with statistics output", epi); return PD_ERR_UNSUPPORTED; }
+    cudaError_t e = launch_pdl(kernels[st][a.sk][CGv - 1][epi], dim3((unsigned)grid), dim3(TC_THREADS), smem, s, (unsigned)CGv,
                                map_a0, map_a1, map_w, map_o64, map_o32, map_r64, map_r32, a);
     if (e != cudaSuccess) { set_error("conv_tc: launch failed: %s", cudaGetErrorString(e)); return (int)e; }
   }
