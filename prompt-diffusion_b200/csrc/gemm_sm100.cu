@@ -59,7 +59,8 @@ struct TcArgs {
   unsigned long long* dbg;      // optional timeline buffer [5 roles][64 tiles][2] (globaltimer ns), CTA 0 only
   int w_blocked;                // weights are k-block-major [K/64][Cout][64]: B tiles are contiguous in HBM (3-D map)
   int dbg_mode;                 // timing experiments only (wrong results): 1 = no MMAs issued, 2 = no TMA loads issued;
-                                // epilogue: 3 = no TMA stores, 8 = no epilogue work at all, 9 = no MMA and no TMA loads
+                                // epilogue: 3 = no TMA stores, 8 = no epilogue work at all, 9 = no MMA and no TMA loads;
+                                // 12 = only half of every A tile's rows is fetched (multicast what-if)
                                 // (4..7, 10, 11 existed for the per-slab epilogue of commit "GEMM epilogue: 16-byte shared-space...")
   int epi_tma;                  // 1: bf16 output staged in smem and written by TMA
   int n_fast;                   // tile order, see PD_TILE_COORDS
@@ -311,7 +312,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
           if (elect_one()) {
             // the even CTA's barrier collects the bytes of both CTAs' loads
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(CG * stage_bytes));
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(CG * (stage_bytes - (PD_MODE_IS(12) ? TC_A_BYTES / 2 : 0))));
             if (CG == 2) {
               tma_load_4d_2sm(sa, am, &full_bar[stage], ac0, ax, ay, b0);
               if (bres) { }
@@ -886,9 +887,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (ns_mine > 1) ld_slab(1, v1);
           tmem_ld_wait();
           arrive_empty();
-        } else {
-          gather(0, v0);
-          if (ns_mine > 1) gather(1, v1);
         }
         if (ew == 0 && lane == 0) PD_DBG(3, it, 0);
         // staging buffers ready (residual slabs landed / the previous tile's stores have read them)
@@ -900,8 +898,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           epi_bar_sync(bar_id);
         }
         if (ew == 0 && lane == 0) PD_DBG(3, it, 1);
-        slab_math(0, v0);
-        if (ns_mine > 1) slab_math(1, v1);
+        if (partial) {
+          // stream-K reducer: ONE slab at a time through v0 — 64 running sums next to the 64 loads in flight of the piece
+          // being added; with both slabs' sums live the gather spilled (~90 registers) and crawled
+          for (int i = 0; i < ns_mine; ++i) { gather(i, v0); slab_math(i, v0); }
+        } else {
+          slab_math(0, v0);
+          if (ns_mine > 1) slab_math(1, v1);
+        }
         if (ew == 0 && lane == 0) PD_DBG(4, it, 0);
         // one fence / barrier per tile, then both stores in one bulk group
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the TMA engine
@@ -1236,6 +1240,11 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
     uint64_t strides[3] = {(uint64_t)p->ldx * 2, (uint64_t)iW * p->ldx * 2, (uint64_t)iH * iW * p->ldx * 2};
     uint32_t box[4] = {TC_BK, (uint32_t)(a.bw * p->stride), (uint32_t)(a.bh * p->stride), (uint32_t)a.bn};
     uint32_t es[4] = {1, (uint32_t)p->stride, (uint32_t)p->stride, 1};
+#ifdef PD_DEBUG
+    // timing experiment 12 (wrong results): fetch only HALF of the A tile's pixel rows — what a CTA would issue if the
+    // other half came from a cluster peer by TMA multicast
+    if (g_dbg_mode == 12) { if (a.bn > 1) box[3] /= 2; else if (a.bh > 1) box[2] /= 2; else box[1] /= 2; }
+#endif
     int rc = encode_map(&map_a0, p->x, 4, dims, strides, box, es, "A0");
     if (rc) return rc;
   }
@@ -1404,7 +1413,10 @@ static int g_force_sk = 0;
 
 static void tune_load_locked() {
   if (g_tune_loaded) return;
-  for (const TuneRow* r = k_tune_table; r->k.M != 0; ++r) g_tune[r->k] = r->v;
+  // PD_B200_RETUNE=1 (with PD_B200_AUTOTUNE=1): start from an empty table so that every shape is timed again
+  const char* re = getenv("PD_B200_RETUNE");
+  if (!(re != nullptr && re[0] == '1'))
+    for (const TuneRow* r = k_tune_table; r->k.M != 0; ++r) g_tune[r->k] = r->v;
   g_tune_loaded = true;
 }
 
@@ -1450,8 +1462,9 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   // stream-K with the model's tile width, and with 128-wide tiles: fewer pieces per tile (cheaper fix-up) against
   // more operand traffic per FLOP
   // resident-B candidates (short-K layers): tile widths whose whole-K weight tile fits next to the A ring
-  constexpr int NCAND = 13;
+  constexpr int NCAND = 15;
   const TcVariant cands[NCAND] = {{1, 0, 0, 0}, {2, 0, 0, 0}, {2, 1, 0, 0}, {1, 1, 0, 0}, {2, 1, 128, 0}, {1, 1, 128, 0},
+                                  {2, 1, 256, 0}, {1, 1, 256, 0},
                                   {1, 0, 160, 1}, {2, 0, 160, 1}, {1, 0, 128, 1}, {2, 0, 128, 1}, {2, 0, 192, 1}, {2, 0, 256, 1},
                                   {1, 0, 96, 1}};
   float best_ms = 1e30f; TcVariant best = cands[0]; int last_run = -1, best_idx = 0;

@@ -48,9 +48,29 @@ ap.add_argument("--small", action="store_true", help="fixed-overhead study: tiny
 ap.add_argument("--modes", action="store_true", help="timing experiment: full kernel vs no-MMA vs no-TMA, per tile shape")
 ap.add_argument("--epi-modes", action="store_true", help="timing experiment on the epilogue of short-K layers (gemm_sm100.cu dbg_mode 3..7)")
 ap.add_argument("--bres", action="store_true", help="resident-B schedule against the tabled variant on the short-K layer shapes")
+ap.add_argument("--sk", action="store_true", help="stream-K tile shapes on the small-M (8x8 / 16x16 level) 3x3 layers")
 a = ap.parse_args()
 BLOCKED = a.blocked
-if a.bres:
+if a.sk:
+    from prompt_diffusion_b200 import _lib
+    L = _lib.lib
+    BLOCKED = True
+    shapes = [(16, 8, 8, 1280, 1280, 3, 1), (16, 8, 8, 2560, 1280, 3, 0), (16, 8, 8, 1280, 1280, 1, 1), (16, 16, 16, 1280, 1280, 3, 1), (16, 16, 16, 2560, 1280, 3, 0)]
+    combos = [(1, 128, 1), (1, 256, 1), (2, 128, 1), (2, 256, 1), (1, 128, 0), (2, 256, 0)]
+    print("   B   HxW     C     N ks res | tabled us | " + " | ".join("cg%d bn%-3d sk%d" % c for c in combos))
+    for s_ in shapes:
+        base = run(*s_, iters=a.iters)[0]
+        row = []
+        for cg, bn, sk in combos:
+            L.pd_debug_force_cta_group(cg); L.pd_debug_force_bn(bn); L.pd_debug_force_stream_k(sk)
+            try:
+                us = run(*s_, iters=a.iters)[0]
+            except RuntimeError:
+                us = float("nan")
+            L.pd_debug_force_cta_group(0); L.pd_debug_force_bn(0); L.pd_debug_force_stream_k(0)
+            row.append(us)
+        print("%4d %3dx%-3d %5d %5d %2d %3d | %9.1f | " % (*s_, base) + " | ".join("%13.1f" % r for r in row))
+elif a.bres:
     from prompt_diffusion_b200 import _lib
     L = _lib.lib
     BLOCKED = True     # the packed model weights are k-block-major
@@ -94,6 +114,21 @@ elif a.modes:
                 row.append(run(*s_, iters=a.iters)[0])
             _lib.lib.pd_debug_gemm_mode(0)
             print("%4d %3dx%-3d %5d %5d %2d %3d %2d | %8.1f | %8.1f | %8.1f" % (*s_, cg, *row))
+    _lib.lib.pd_debug_force_cta_group(0)
+elif os.environ.get("PD_HALF_A"):
+    # what-if (debug library): every CTA fetches only half of its A tile's rows (mode 12) against the full kernel
+    from prompt_diffusion_b200 import _lib
+    print("   B   HxW     C     N ks res cg |  full us | half-A us | no-epilogue us | half-A + no-epilogue us")
+    for s_ in [(16, 64, 64, 320, 320, 1, 0), (16, 64, 64, 320, 320, 1, 1), (16, 64, 64, 320, 960, 1, 0), (16, 64, 64, 320, 2560, 1, 0), (16, 64, 64, 320, 320, 3, 0),
+               (16, 64, 64, 640, 320, 3, 0), (16, 32, 32, 640, 640, 1, 1), (16, 32, 32, 640, 640, 3, 0), (16, 16, 16, 1280, 1280, 3, 0), (16, 8, 8, 1280, 1280, 3, 1)]:
+        for cg in (1, 2):
+            _lib.lib.pd_debug_force_cta_group(cg)
+            row = []
+            for mode in (0, 12, 8):
+                _lib.lib.pd_debug_gemm_mode(mode)
+                row.append(run(*s_, iters=a.iters)[0])
+            _lib.lib.pd_debug_gemm_mode(0)
+            print("%4d %3dx%-3d %5d %5d %2d %3d %2d | %8.1f | %9.1f | %9.1f" % (*s_, cg, *row))
     _lib.lib.pd_debug_force_cta_group(0)
 elif a.epi_modes:
     from prompt_diffusion_b200 import _lib

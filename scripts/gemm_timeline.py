@@ -7,6 +7,7 @@ B,H,W,C,N,ks,res = [int(v) for v in sys.argv[1:8]]
 if len(sys.argv) > 8: _lib.lib.pd_debug_force_cta_group(int(sys.argv[8]))
 if len(sys.argv) > 9: _lib.lib.pd_debug_force_bn(int(sys.argv[9]))
 if len(sys.argv) > 10: _lib.lib.pd_debug_force_bres(int(sys.argv[10]))
+if len(sys.argv) > 11: _lib.lib.pd_debug_force_stream_k(int(sys.argv[11]))
 dev="cuda"; M=B*H*W
 x=torch.randn(M,C,device=dev).to(torch.bfloat16); w=(torch.randn(N,ks*ks*C,device=dev)/math.sqrt(ks*ks*C)).to(torch.bfloat16)
 bias=torch.randn(N,device=dev); out=torch.empty(M,N,device=dev,dtype=torch.bfloat16)

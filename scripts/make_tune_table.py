@@ -1,7 +1,8 @@
 """Regenerate prompt-diffusion_b200/csrc/tune_table.inc (the committed per-shape launch-variant table of the tcgen05
 GEMM engine).
 
-On a B200 (gpurun):   PD_B200_AUTOTUNE=1 python scripts/make_tune_table.py --dump gpurun_out/tune_dump.inc
+On a B200 (gpurun):   PD_B200_AUTOTUNE=1 [PD_B200_RETUNE=1] python scripts/make_tune_table.py --dump gpurun_out/tune_dump.inc
+    (PD_B200_RETUNE=1 ignores the committed rows, so every shape is timed again)
     records the GEMM shapes of one apply_model per workload (pd_prof), then launches every unique shape once on
     synthetic operands with the opt-in timing autotune on and writes the winners with pd_tune_dump.
 Here (no GPU):        python scripts/make_tune_table.py --install gpurun_out/tune_dump.inc
@@ -26,7 +27,7 @@ if a.install:
     rows = sorted(set(l.strip() for l in open(a.install) if l.strip().startswith("{{")),
                   key=lambda l: [int(x) for x in l.replace("{", "").replace("}", "").split(",") if x.strip()])
     with open(TABLE, "w") as f:
-        f.write("// {{M, N, K, ksize, stride, 0, 8 if GEGLU epilogue}, {cta_group, stream_k, BN override}} — generated on a B200 by\n"
+        f.write("// {{M, N, K, ksize, stride, 0, 8 if GEGLU epilogue}, {cta_group, stream_k, BN override, resident B}} — generated on a B200 by\n"
                 "// scripts/make_tune_table.py (PD_B200_AUTOTUNE=1 timing of every GEMM shape of the listed workloads); committed so\n"
                 "// that the launch variant, and with it the fp32 summation order, never depends on timing noise.\n")
         for r in rows:

@@ -40,6 +40,14 @@ def measure(tag, reps=12):
 
 
 ref = None
+if os.environ.get("AB_QUICK"):
+    # (GroupNorm records from launches with K >= min_k, LayerNorm partials), each setting twice, interleaved
+    for rnd in range(2):
+        for min_k, ln_parts in ((10 ** 9, False), (10 ** 9, True), (1024, False)):
+            M.GN_STATS_MIN_K, M.LN_PARTS = min_k, ln_parts
+            measure(f"round {rnd} gn_stats_min_k={min_k:<10d} ln_parts={ln_parts}")
+    sys.exit(0)
+ref = None
 for tc4 in (0, 1):
     _lib.lib.pd_debug_attention_tc4(tc4)
     for min_k in (10 ** 9, 1024, 0):
