@@ -387,10 +387,13 @@ def main():
         step_ms = ev0.elapsed_time(ev1) / reps
         achieved = fl.value / (ms.value * 1e-3) / 1e12
         # DRAM traffic of the same kernel set from the committed ncu pass over one denoising step
-        # (scripts/gpu_final_profile.sh -> profiles/r01_conv_tc_traffic.json): bytes per launch, like `achieved`
+        # (scripts/gpu_round2_profile.sh + scripts/conv_traffic.py -> profiles/r02_conv_tc_traffic.json): bytes per launch, like `achieved`
         traffic, traffic_note = None, "no ncu traffic capture committed"
         try:
-            tj = json.load(open(os.path.join(REPO, "profiles", "r01_conv_tc_traffic.json")))
+            tpath = os.path.join(REPO, "profiles", "r02_conv_tc_traffic.json")
+            if not os.path.exists(tpath):
+                tpath = os.path.join(REPO, "profiles", "r01_conv_tc_traffic.json")
+            tj = json.load(open(tpath))
             traffic = tj["dram_bytes_per_denoise_step"] / tj["launches_per_denoise_step"]
             traffic_note = (f"ncu dram__bytes_read+write summed over the {tj['launches_per_denoise_step']} conv_tc launches of one "
                             f"denoising step ({tj['dram_bytes_per_denoise_step'] / 1e9:.2f} GB), divided by the launch count; "

@@ -20,6 +20,10 @@
 
 #include "tc_ptx.cuh"
 
+#ifndef F3_POLL_SLEEP
+#define F3_POLL_SLEEP 0
+#endif
+
 namespace pd {
 
 constexpr int F3_BQ = 128, F3_GROUPS = 3, F3_BK = 128, F3_THREADS = 512, F3_STAGES = 3;
@@ -172,6 +176,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         int remaining = n_act * a.ntiles;
         long long t_poll = clock64();
         while (remaining > 0) {
+          bool served = false;
 #pragma unroll
           for (int g = 0; g < F3_GROUPS; ++g) {
             const int jj = g == 0 ? jg0 : g == 1 ? jg1 : jg2;
@@ -204,8 +209,16 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             __syncwarp();
             if (g == 0) ++jg0; else if (g == 1) ++jg1; else ++jg2;
             --remaining;
+            served = true;
             t_poll = clock64();
           }
+#if F3_POLL_SLEEP > 0
+          // nothing was ready: back off instead of spinning 32 lanes on three barriers (the spin costs issue slots of
+          // the sub-partition this warp shares with three softmax warps, and power the step does not have to spare)
+          if (!served) __nanosleep(F3_POLL_SLEEP);
+#else
+          (void)served;
+#endif
           if (clock64() - t_poll > 4000000000LL) {
             if (lane == 0) printf("pd_b200 attention_tc3: MMA warp starved (block %d,%d,%d tiles %d %d %d of %d)\n", blockIdx.x,
                                   blockIdx.y, blockIdx.z, jg0, jg1, jg2, a.ntiles);
