@@ -235,10 +235,12 @@ int pd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const v
                  int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
                  int32_t Nk, int32_t d, float scale, int32_t dtype, void* stream);
 /* same, with an explicit engine: 0 auto, 1 SIMT (fp32 math, any dtype), 2 warp-level mma.sync (bf16),
- * 3 tcgen05/TMEM/TMA (bf16, head dim <= 128), 4 single-pass short-key kernel (bf16, Nk <= 128, head dim <= 80: the
- * 77-token cross-attention; what auto picks for it), 5 four-query-group / 64-key-tile tcgen05 kernel (bf16, head dim <= 64;
- * measured equal to engine 3 on B200, kept as an explicit engine / PD_B200_ATTN4=1 only), 6 three-query-group / 128-key-tile
- * tcgen05 kernel (bf16, head dim <= 40; what auto picks when the query count is a multiple of 384) */
+ * 3 tcgen05/TMEM/TMA (bf16, head dim <= 192; one query group per CTA above 128: the d = 160 levels),
+ * 4 single-pass mma.sync short-key kernel (bf16, Nk <= 128, head dim <= 80; auto keeps it for small query counts and the
+ * causal CLIP tower), 5 four-query-group / 64-key-tile tcgen05 kernel (bf16, head dim <= 64; measured equal to engine 3 on
+ * B200, kept as an explicit engine / PD_B200_ATTN4=1 only), 6 three-query-group / 128-key-tile tcgen05 kernel (bf16, head
+ * dim <= 40; what auto picks from 6144 queries up), 7 persistent tcgen05 short-key kernel (bf16, Nk <= 128, head dim <= 128:
+ * the 77-token cross-attention; what auto picks for it once there are >= 296 256-query units) */
 int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
                     int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
                     int32_t Nk, int32_t d, float scale, int32_t dtype, int32_t engine, void* stream);

@@ -50,8 +50,11 @@ __device__ __forceinline__ float xs_ex2(float x) {
 
 // DP: head dim padded to a multiple of 16; NK16: key capacity in units of 16; CAUSAL: query i sees keys <= i (the
 // CLIP text tower's self-attention, 77 tokens; a separate instantiation, the cross-attention code is unchanged)
+#ifndef XS_MINB
+#define XS_MINB 1
+#endif
 template <int DP, int NK16, bool CAUSAL>
-__global__ void __launch_bounds__(XTHREADS)
+__global__ void __launch_bounds__(XTHREADS, (DP <= 48 && NK16 <= 5) ? XS_MINB : 1)
 attention_short_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restrict__ k, int ldk,
                        const bf16* __restrict__ v, int ldv, bf16* __restrict__ out, int ldo, int Nq, int Nk, int d,
                        float scale_log2) {
@@ -98,6 +101,9 @@ attention_short_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restri
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks) {
     const int c0 = ks * 16 + 2 * t4, c1 = c0 + 8;
+#ifdef XS_NOQ
+    qa[ks][0] = qa[ks][1] = qa[ks][2] = qa[ks][3] = 0x3c003c00u + lane; continue;
+#endif
     qa[ks][0] = (ok0 && c0 < d) ? __ldg(reinterpret_cast<const uint32_t*>(qr0 + c0)) : 0u;
     qa[ks][1] = (ok1 && c0 < d) ? __ldg(reinterpret_cast<const uint32_t*>(qr1 + c0)) : 0u;
     qa[ks][2] = (ok0 && c1 < d) ? __ldg(reinterpret_cast<const uint32_t*>(qr0 + c1)) : 0u;
@@ -185,6 +191,9 @@ attention_short_kernel(const bf16* __restrict__ q, int ldq, const bf16* __restri
 #pragma unroll
   for (int j = 0; j < ON; ++j) {
     const int c = j * 8 + 2 * t4;
+#ifdef XS_NOSTORE
+    if (o[j][0] * inv0 != 12345.678f) continue;
+#endif
     if (c < d) {
       if (ok0) *reinterpret_cast<uint32_t*>(ob + (int64_t)row0 * ldo + c) = xs_pack(o[j][0] * inv0, o[j][1] * inv0);
       if (ok1) *reinterpret_cast<uint32_t*>(ob + (int64_t)row1 * ldo + c) = xs_pack(o[j][2] * inv1, o[j][3] * inv1);

@@ -194,7 +194,7 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
                       ((uintptr_t)out % 4) == 0;
   const bool tc_ok = attention_tc_supported(dtype, d, ldq, ldk, ldv, ldo, q, k, v, out);
   if (engine == 3 && !tc_ok) {
-    set_error("pd_attention: tcgen05 engine needs sm_100, bf16, d <= 128 (multiple of 8), 16B-aligned tensors and pitches");
+    set_error("pd_attention: tcgen05 engine needs sm_100, bf16, d <= 192 (multiple of 8), 16B-aligned tensors and pitches");
     return PD_ERR_UNSUPPORTED;
   }
   const bool short_ok = attention_short_supported(dtype, d, Nk, ldq, ldk, ldv, ldo, q, k, v, out);
@@ -204,6 +204,17 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
   }
   static int auto_short = -1;          // PD_B200_ATTN_SHORT=0: auto never picks the short-key engine (A/B timing)
   if (auto_short < 0) { const char* e = getenv("PD_B200_ATTN_SHORT"); auto_short = (e && e[0] == '0') ? 0 : 1; }
+  // engine 7 = the persistent tcgen05 short-key kernel (Nk <= 128, d <= 128); auto picks it for the 77-key cross-attention
+  // once there are enough 256-query units to fill the machine (PD_B200_ATTN_XTC=0: never)
+  const bool xtc_ok = attention_xtc_supported(dtype, d, Nk, ldq, ldk, ldv, ldo, q, k, v, out);
+  if (engine == 7 && !xtc_ok) {
+    set_error("pd_attention: the short-key tcgen05 engine needs sm_100, bf16, Nk <= 128, d <= 128 (multiple of 8), 16B-aligned tensors and pitches");
+    return PD_ERR_UNSUPPORTED;
+  }
+  static int auto_xtc = -1;
+  if (auto_xtc < 0) { const char* e = getenv("PD_B200_ATTN_XTC"); auto_xtc = (e && e[0] == '0') ? 0 : 1; }
+  if (engine == 7 || (engine == 0 && xtc_ok && auto_xtc && (long long)B * heads * ((Nq + 255) / 256) >= 296))
+    return attention_xtc(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   if (engine == 4 || (engine == 0 && short_ok && auto_short))
     return attention_short(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   // engine 5 = the four-group / 64-key-tile tcgen05 kernel (d <= 64); auto picks it for the long sequences it is built for

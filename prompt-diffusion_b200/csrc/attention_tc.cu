@@ -1,4 +1,4 @@
-// tcgen05 / TMEM / TMA streaming-softmax attention (bf16) for head dims <= 128 — the d = 40, 4096..9216-token
+// tcgen05 / TMEM / TMA streaming-softmax attention (bf16) for head dims <= 192 (one query group per CTA above 128) — the d = 40, 4096..9216-token
 // self-attention of the 64x64 / 96x96 latent level, the d = 80 level below it and their 77-key cross-attention
 // (CrossAttention.forward, ldm/modules/attention.py:171-193), which dominate the attention time of a step.
 //
@@ -65,21 +65,27 @@ struct FaArgs {
 //   registers (s_free) and the softmax threads never wait for the tensor pipe.
 // 64 < d <= 128 (ALIAS):        S_a [0,128) | S_b [128,256) | O_a [256,384) | O_b [384,512), P_g over S_g[:, 0:64)
 //   P aliases S; in-order execution of the tensor pipe (PV_g(j) issued before QK_g(j+1)) protects it.
-template <int KP16>
+// 128 < d <= 192 (NG = 1):       S [0,128) | O [128, 128 + KPAD), P over S[:, 0:64): ONE 128-query group per CTA (two O tiles
+//   of 160 columns do not fit next to two S tiles), three 64-channel chunks per Q / K / V tile, K and V single-buffered
+//   (144 KiB of tiles).  The d = 160 levels (16x16: 256 tokens, 8x8: 64 tokens, and their 77-key cross-attention) are
+//   two key tiles at most: latency-bound, the point is the tcgen05 data path instead of the mma.sync kernel.
+template <int KP16, int NG>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                     const FaArgs a) {
   constexpr bool ALIAS = KP16 > 4;
-  constexpr int ND = ALIAS ? 2 : 1;
+  constexpr int ND = (KP16 + 3) / 4;
   constexpr int KPAD = KP16 * 16;
-  constexpr uint32_t COL_S = 0, COL_P = ALIAS ? 0 : 256, COL_O = ALIAS ? 256 : 384;
+  static_assert(NG == 2 || (NG == 1 && KP16 > 8 && KP16 <= 12), "one query group only for 128 < d <= 192");
+  static_assert(NG == 1 || KP16 <= 8, "two query groups need d <= 128");
+  constexpr uint32_t COL_S = 0, COL_P = ALIAS ? 0 : 256, COL_O = NG == 1 ? 128 : ALIAS ? 256 : 384;
   constexpr uint32_t GSTRIDE_P = ALIAS ? 128 : 64, GSTRIDE_O = ALIAS ? 128 : 64;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stages = a.stages;
   unsigned char* q_s = smem;                                              // [group][chunk] tiles
-  unsigned char* k_s = q_s + FA_GROUPS * ND * FA_TILE_BYTES;              // [stage][chunk]
+  unsigned char* k_s = q_s + NG * ND * FA_TILE_BYTES;              // [stage][chunk]
   unsigned char* v_s = k_s + stages * ND * FA_TILE_BYTES;                 // [stage][chunk]
   uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + stages * ND * FA_TILE_BYTES);
   uint64_t& q_full = bars[0];
@@ -95,7 +101,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   uint32_t& tmem_base_slot = *reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (FA_GROUPS * FA_BQ), h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * (NG * FA_BQ), h = blockIdx.y, b = blockIdx.z;
   // Roles: warps 0-3 softmax A, 4-7 softmax B, 8 TMA, 9 MMA (the sub-partition arbiter favours high warp ids)
   constexpr int W_TMA = 8, W_MMA = 9;
 
@@ -123,8 +129,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
   if (warp == W_TMA) {
     if (lane == 0) {
-      mbar_expect_tx(&q_full, FA_GROUPS * ND * FA_TILE_BYTES);
-      for (int g = 0; g < FA_GROUPS; ++g)
+      mbar_expect_tx(&q_full, NG * ND * FA_TILE_BYTES);
+      for (int g = 0; g < NG; ++g)
         for (int c = 0; c < ND; ++c)
           tma_load_4d(q_s + (g * ND + c) * FA_TILE_BYTES, &map_q, &q_full, c * 64, h, q0 + g * FA_BQ, b);
       int st = 0; uint32_t ph = 0;
@@ -184,8 +190,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tc_fence_after();
       FA_DBG(0, 0);
       const uint32_t id0 = a.ntiles == 1 ? a.idesc_s_last : a.idesc_s_full;
-      issue_qk(0, 0, id0);
-      issue_qk(1, 0, id0);
+      for (int g = 0; g < NG; ++g) issue_qk(g, 0, id0);
       umma_commit(&k_empty[0]);
       int st = 0; uint32_t ph = 0;          // ring position of tile j
       for (int j = 0; j < a.ntiles; ++j) {
@@ -196,7 +201,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         if constexpr (!ALIAS) {
           if (more) {
             mbar_wait(&k_full[stn], phn, 300 + stn);
-            for (int g = 0; g < FA_GROUPS; ++g) {
+            for (int g = 0; g < NG; ++g) {
               mbar_wait(&s_free[g], (uint32_t)j & 1u, 450 + g);
               tc_fence_after();
               issue_qk(g, stn, idn);
@@ -205,7 +210,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             umma_commit(&k_empty[stn]);
           }
           mbar_wait(&v_full[st], ph, 310 + st);
-          for (int g = 0; g < FA_GROUPS; ++g) {
+          for (int g = 0; g < NG; ++g) {
             mbar_wait(&p_full[g], (uint32_t)j & 1u, 400 + g);
             tc_fence_after();
             if (g == 0) FA_DBG(1, j);
@@ -216,15 +221,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         } else {
           mbar_wait(&v_full[st], ph, 310 + st);
           if (more) mbar_wait(&k_full[stn], phn, 300 + stn);
-          for (int g = 0; g < FA_GROUPS; ++g) {
+          for (int g = 0; g < NG; ++g) {
             mbar_wait(&p_full[g], (uint32_t)j & 1u, 400 + g);
             tc_fence_after();
             if (g == 0) FA_DBG(1, j);
             issue_pv(g, st, j == 0, last);
-            if (g == 1) umma_commit(&v_empty[st]);
+            if (g == NG - 1) umma_commit(&v_empty[st]);
             if (more) {
               issue_qk(g, stn, idn);
-              if (g == 1) umma_commit(&k_empty[stn]);
+              if (g == NG - 1) umma_commit(&k_empty[stn]);
               if (g == 0) FA_DBG(0, j + 1);
             } else {
               umma_commit(&o_final[g]);
@@ -234,9 +239,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         st = stn; ph = phn;
       }
     }
-  } else {
+  } else if ((warp >> 2) < NG) {
     // ---------------- softmax / correction / epilogue: thread == query row ----------------
-    const int g = warp >> 2;                       // 0: warps 0-3, 1: warps 4-7
+    const int g = warp >> 2;                       // 0: warps 0-3, 1: warps 4-7 (idle when NG == 1)
     const int qd4 = warp & 3;                      // TMEM lane quadrant this warp may touch
     const int r = qd4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd4 * 32) << 16;
@@ -386,7 +391,7 @@ bool attention_tc_supported(int dtype, int d, int ldq, int ldk, int ldv, int ldo
                             const void* v, const void* out) {
   static int sm100 = -1;
   if (sm100 < 0) sm100 = pd_device_is_sm100();
-  return sm100 && dtype == PD_BF16 && d % 8 == 0 && d >= 16 && d <= 128 && ldq % 8 == 0 && ldk % 8 == 0 &&
+  return sm100 && dtype == PD_BF16 && d % 8 == 0 && d >= 16 && d <= 192 && ldq % 8 == 0 && ldk % 8 == 0 &&
          ldv % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 &&
          ((uintptr_t)v % 16) == 0 && ((uintptr_t)out % 16) == 0;
 }
@@ -396,7 +401,8 @@ int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, 
   FaArgs a;
   a.Nq = Nq; a.Nk = Nk; a.d = d;
   a.nd = (d + 63) / 64;
-  a.stages = a.nd == 1 ? 3 : 2;
+  a.stages = a.nd == 1 ? 3 : a.nd == 2 ? 2 : 1;     // K ring and V ring depth (144 KiB of tiles at three chunks per head)
+  const int ng = d > 128 ? 1 : FA_GROUPS;
   const int kpad = (d + 15) / 16 * 16;
   a.scale_log2 = scale * 1.4426950408889634f;
   a.ntiles = (Nk + FA_BK - 1) / FA_BK;
@@ -420,22 +426,23 @@ int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, 
     int rc = encode_map(t[i].m, t[i].p, 4, dims, strides, box, es, t[i].nm);
     if (rc) return rc;
   }
-  const size_t smem = (size_t)(FA_GROUPS * a.nd + 2 * a.stages * a.nd) * FA_TILE_BYTES + 256 + FA_ALIGN_SLACK;
-  dim3 grid((Nq + FA_GROUPS * FA_BQ - 1) / (FA_GROUPS * FA_BQ), heads, B);
-#define FA_LAUNCH(KP)                                                                                              \
+  const size_t smem = (size_t)(ng * a.nd + 2 * a.stages * a.nd) * FA_TILE_BYTES + 256 + FA_ALIGN_SLACK;
+  dim3 grid((Nq + ng * FA_BQ - 1) / (ng * FA_BQ), heads, B);
+#define FA_LAUNCH(KP, NGv)                                                                                         \
   case KP: {                                                                                                       \
     static bool attr_set = false;                                                                                  \
     if (!attr_set) {                                                                                               \
-      cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+      cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<KP, NGv>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                            (int)smem);                                                             \
       if (e != cudaSuccess) { set_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; } \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    cudaError_t le = launch_pdl(attention_tc_kernel<KP>, grid, dim3(FA_THREADS), smem, s, 1, mq, mk, mv, mo, a);   \
+    cudaError_t le = launch_pdl(attention_tc_kernel<KP, NGv>, grid, dim3(FA_THREADS), smem, s, 1, mq, mk, mv, mo, a);   \
     if (le != cudaSuccess) { set_error("attention_tc: launch failed: %s", cudaGetErrorString(le)); return (int)le; } \
   } break;
   switch (kpad / 16) {
-    FA_LAUNCH(1) FA_LAUNCH(2) FA_LAUNCH(3) FA_LAUNCH(4) FA_LAUNCH(5) FA_LAUNCH(6) FA_LAUNCH(7) FA_LAUNCH(8)
+    FA_LAUNCH(1, 2) FA_LAUNCH(2, 2) FA_LAUNCH(3, 2) FA_LAUNCH(4, 2) FA_LAUNCH(5, 2) FA_LAUNCH(6, 2) FA_LAUNCH(7, 2) FA_LAUNCH(8, 2)
+    FA_LAUNCH(9, 1) FA_LAUNCH(10, 1) FA_LAUNCH(11, 1) FA_LAUNCH(12, 1)
     default: set_error("attention_tc: unsupported head dim %d", d); return PD_ERR_UNSUPPORTED;
   }
 #undef FA_LAUNCH

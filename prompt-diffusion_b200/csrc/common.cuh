@@ -152,6 +152,11 @@ int attention_tc(const void* q, int ldq, const void* k, int ldk, const void* v, 
 bool attention_tc3_supported(int d, int Nq, int Nk);            // attention_tc3.cu: three query groups, 128-key tiles, d <= 40
 int attention_tc3(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
                   int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
+// attention_xtc.cu: persistent tcgen05 kernel for a short key sequence (Nk <= 128, d <= 128): the 77-key cross-attention
+bool attention_xtc_supported(int dtype, int d, int Nk, int ldq, int ldk, int ldv, int ldo, const void* q, const void* k,
+                             const void* v, const void* out);
+int attention_xtc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
+                  int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
 bool attention_tc4_supported(int d, int Nq, int Nk);            // attention_tc4.cu: four query groups, 64-key tiles
 int attention_tc4(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
                   int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);

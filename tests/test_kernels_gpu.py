@@ -406,7 +406,36 @@ def test_attention(B, heads, Nq, Nk, d, dt, engine, tol):
 TC_ATTN_CASES = [(1, 8, 256, 256, 40), (2, 8, 1024, 1024, 40), (2, 8, 100, 77, 40), (1, 8, 4096, 4096, 40),
                  (1, 4, 130, 130, 64), (2, 2, 384, 200, 32), (1, 8, 9216 // 4, 9216 // 4, 40),
                  (2, 8, 1024, 1024, 80), (2, 8, 1024, 77, 80), (1, 4, 300, 513, 128), (1, 2, 640, 1, 40),
-                 (1, 3, 128, 128, 16), (1, 8, 576, 576, 80)]
+                 (1, 3, 128, 128, 16), (1, 8, 576, 576, 80),
+                 # 128 < d <= 192: one query group per CTA, three channel chunks (the 16x16 / 8x8 levels and their cross-attention)
+                 (2, 8, 256, 256, 160), (2, 8, 64, 64, 160), (2, 8, 256, 77, 160), (1, 8, 64, 77, 160), (1, 2, 300, 513, 192),
+                 (1, 4, 130, 130, 144)]
+
+
+XTC_ATTN_CASES = [(2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 8, 300, 77, 40), (3, 5, 1000, 1, 64), (1, 2, 9216, 128, 40),
+                  (2, 3, 700, 100, 128), (1, 8, 2304, 77, 80), (1, 1, 64, 16, 16), (5, 8, 256, 77, 40)]
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", XTC_ATTN_CASES)
+def test_attention_tcgen05_short_keys(B, heads, Nq, Nk, d):
+    """Persistent tcgen05 kernel for a short key sequence (engine 7: the 77-token cross-attention) vs torch fp32 on the same
+    bf16 operands; ragged query counts, head changes inside a CTA's unit range, 1..128 keys.  Run twice (same bits)."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(17)
+    Cc = heads * d
+    q = torch.randn(B * Nq, Cc, device=DEV, generator=g).to(torch.bfloat16)
+    kv = torch.randn(B * Nk, 2 * Cc, device=DEV, generator=g).to(torch.bfloat16)
+    k, v = kv[:, :Cc], kv[:, Cc:]
+    out = torch.full((B * Nq, Cc + 8), 3.0, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q, k, v, out[:, :Cc], B, heads, Nq, Nk, d, engine=7)
+    torch.cuda.synchronize()
+    assert bool((out[:, Cc:] == 3.0).all()), "wrote past the head columns"
+    ref = _attn_ref(q.reshape(B, Nq, Cc), k.reshape(B, Nk, Cc), v.reshape(B, Nk, Cc), heads, d ** -0.5)
+    err = rel_l2(out[:, :Cc].float().reshape(B, Nq, Cc), ref)
+    assert err < 1e-2, err
+    out2 = torch.empty_like(out)
+    ops.attention(q, k, v, out2[:, :Cc], B, heads, Nq, Nk, d, engine=7)
+    assert torch.equal(out2[:, :Cc], out[:, :Cc])
 
 
 @pytest.mark.parametrize("B,heads,Nq,Nk,d", TC_ATTN_CASES)
