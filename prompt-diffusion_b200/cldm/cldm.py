@@ -44,6 +44,7 @@ _MODES = {"bf16": torch.bfloat16, "fp32": torch.float32}
 # split-precision GroupNorm output needs the records (one launch per step).
 GN_STATS_MIN_K = 1 << 30     # K extent from which a launch emits GroupNorm records
 LN_PARTS = False             # LayerNorm row partials from the producing GEMM (False: pd_layer_norm_stats pass)
+TIME_EMBED_TABLE = True      # _Net.embed: emb_layers(time_embed(t)) of all cfg.timesteps timesteps computed once, then gathered
 
 
 _on_device = ops.on_device
@@ -131,6 +132,7 @@ class _Net:
         self.model_channels = cfg.model_channels
         self.dtype = torch.float32            # reference attribute (use_fp16=False)
         self._ctx_cache = None                # (key, tensors kept alive, {st key: kv buffer})
+        self._emb_table = None                # (fp32 [cfg.timesteps, sum Cout], zero row): embed() of every schedule timestep
         self.tag = type(self).__name__
 
     # ---- weights -----------------------------------------------------------------------------
@@ -141,6 +143,7 @@ class _Net:
         with torch.cuda.device(self.device):
             self.w = PackedNet(self.cfg, sd, prefix, self.decoder, self.dt, self.device)
         self._ctx_cache = None
+        self._emb_table = None
         return self
 
     def _need_weights(self):
@@ -223,19 +226,45 @@ class _Net:
     # ---- timestep embedding (cldm.py:26-27,303-304; openaimodel.py:526-531; ResBlock emb_layers) ----
     def embed(self, t: torch.Tensor, reps: int = 1) -> torch.Tensor:
         """t int64 [B] on device -> fp32 [reps * B, sum Cout]: every ResBlock's emb_layers(emb) at once (``reps`` = 2: the
-        [uncond, cond] halves of a CFG batch share their timesteps, rows [B, 2B) repeat rows [0, B))."""
+        [uncond, cond] halves of a CFG batch share their timesteps, rows [B, 2B) repeat rows [0, B)).
+
+        The result depends on nothing but the integer timestep, and the schedule has ``cfg.timesteps`` of them: the first
+        call runs the three linears ONCE for t = 0 .. timesteps - 1 (M = 1000 rows, 81 MB of fp32 per net) and every later
+        call is a row gather (one launch instead of 3 + reps; the M = 16 GEMM over the 51 MB ``emb_layers`` matrix alone
+        cost 51 us per net and step).  Same bits as the direct evaluation: both sum K in order inside one CTA.  t must lie
+        in [0, cfg.timesteps) as in every reference call (out-of-range values are clamped by the gather);
+        ``TIME_EMBED_TABLE = False`` restores the direct evaluation."""
+        w = self.w
+        nb = t.shape[0]
+        B = nb * reps
+        emb_all = self.buf(f"{self.tag}.emb_all", B, w.emb_total, torch.float32)
+        if TIME_EMBED_TABLE:
+            if self._emb_table is None:
+                T = int(self.cfg.timesteps)
+                table = torch.empty(T, w.emb_total, dtype=torch.float32, device=self.device)
+                all_t = torch.arange(T, dtype=torch.int64, device=self.device)
+                self._embed_direct(all_t, 1, table, tag="tab")
+                self._emb_table = (table, torch.zeros(1, w.emb_total, dtype=torch.float32, device=self.device))
+            table, zero = self._emb_table
+            tt = t if t.dtype == torch.int64 and t.is_contiguous() else t.to(torch.int64).contiguous()
+            for r in range(reps):
+                ops.embedding_lookup(tt, table, zero, emb_all[r * nb:(r + 1) * nb], 1)
+            return emb_all
+        return self._embed_direct(t, reps, emb_all)
+
+    def _embed_direct(self, t: torch.Tensor, reps: int, emb_all: torch.Tensor, tag: str = "") -> torch.Tensor:
+        """timestep_embedding -> time_embed (Linear, SiLU, Linear) -> SiLU -> all emb_layers Linears as one GEMM."""
         w = self.w
         B = t.shape[0] * reps
-        temb = self.buf(f"{self.tag}.temb", B, self.cfg.model_channels)
+        temb = self.buf(f"{self.tag}.temb{tag}", B, self.cfg.model_channels)
         for r in range(reps):
             ops.timestep_embedding(t, temb[r * t.shape[0]:(r + 1) * t.shape[0]])
-        e1 = self.buf(f"{self.tag}.e1", B, self.cfg.time_embed_dim)
+        e1 = self.buf(f"{self.tag}.e1{tag}", B, self.cfg.time_embed_dim)
         ops.linear(temb, w.te0.w, e1, bias=w.te0.bias, act=PD_ACT_SILU)
         # emb itself is only ever consumed through ResBlock.emb_layers = SiLU -> Linear
         # (openaimodel.py:217-223), so the SiLU is applied once here.
-        e2 = self.buf(f"{self.tag}.e2", B, self.cfg.time_embed_dim)
+        e2 = self.buf(f"{self.tag}.e2{tag}", B, self.cfg.time_embed_dim)
         ops.linear(e1, w.te2.w, e2, bias=w.te2.bias, act=PD_ACT_SILU)
-        emb_all = self.buf(f"{self.tag}.emb_all", B, w.emb_total, torch.float32)
         ops.linear(e2, w.emb_all.w, emb_all, bias=w.emb_all.bias)
         return emb_all
 

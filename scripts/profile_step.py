@@ -17,6 +17,9 @@ ap.add_argument("--mode", default="bf16")
 ap.add_argument("--graph", type=int, default=0, help="1: time the CUDA-graph replay of the step instead of eager launches")
 a = ap.parse_args()
 torch.set_grad_enabled(False)
+if os.environ.get("PD_TIME_TABLE") == "0":          # A/B: direct evaluation of the timestep embedding every step
+    from prompt_diffusion_b200.cldm import cldm as _M
+    _M.TIME_EMBED_TABLE = False
 from prompt_diffusion_b200.cldm.ddim_hacked import set_step_graphs
 set_step_graphs(bool(a.graph))
 dev = "cuda:0"

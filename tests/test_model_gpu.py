@@ -313,6 +313,25 @@ def test_full_size_batch_properties(models, cfg):
         else:
             assert e1 <= 1e-2 and e2r <= 1e-2
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_time_embedding_table_gives_the_same_bits(models, cfg, mode):
+    """_Net.embed: emb_layers(time_embed(t)) gathered from the once-computed table of all cfg.timesteps timesteps must
+    equal the direct evaluation (timestep_embedding -> Linear, SiLU, Linear -> SiLU -> emb_layers, openaimodel.py:526-531,
+    217-223) bit for bit — mixed timesteps in one batch, first and last schedule entries."""
+    from prompt_diffusion_b200.cldm import cldm as M
+    inp, cond, un, x_in, c_in = _cfg_inputs(cfg, 2, 128, 128)
+    m = models[mode]
+    t = torch.tensor([0, 999, 501, 17], dtype=torch.long, device=DEV)
+    assert M.TIME_EMBED_TABLE
+    got = m.apply_model(x_in, t, c_in)
+    M.TIME_EMBED_TABLE = False
+    try:
+        ref = m.apply_model(x_in, t, c_in)
+    finally:
+        M.TIME_EMBED_TABLE = True
+    assert torch.equal(got, ref), rel_l2(got, ref)
+
+
 def test_fp32_eps_does_not_depend_on_the_batch_partition(models, cfg):
     """What parallel.sample_sharded's bit-identity claim rests on (tests/test_multigpu.py runs it over NCCL on 2 GPUs):
     in fp32 mode the eps of a prompt is the same bits whether it is computed in a batch of 3, 2 or 1 — no kernel's
