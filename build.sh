@@ -10,11 +10,11 @@ pids=()
 for f in elementwise norm softmax conv_simt attention_simt; do
   nvcc $FLAGS_ACC -c $f.cu -o ../../build/$f.o & pids+=($!)
 done
-for f in attention_mma attention_tc attention_tc3 attention_tc4 attention_xtc attention_short gemm_sm100; do
+for f in attention_mma attention_tc attention_tc3 attention_tc4 attention_xtc attention_ptc attention_short gemm_sm100; do
   nvcc $FLAGS_ACC -c $f.cu -o ../../build/$f.o & pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
 nvcc -shared -o $OUT.tmp ../../build/elementwise.o ../../build/norm.o ../../build/softmax.o ../../build/conv_simt.o \
-  ../../build/attention_simt.o ../../build/attention_mma.o ../../build/attention_tc.o ../../build/attention_tc3.o ../../build/attention_tc4.o ../../build/attention_xtc.o ../../build/attention_short.o ../../build/gemm_sm100.o -lcudart_static -ldl -lrt -lpthread
+  ../../build/attention_simt.o ../../build/attention_mma.o ../../build/attention_tc.o ../../build/attention_tc3.o ../../build/attention_tc4.o ../../build/attention_xtc.o ../../build/attention_ptc.o ../../build/attention_short.o ../../build/gemm_sm100.o -lcudart_static -ldl -lrt -lpthread
 mv -f $OUT.tmp $OUT
 echo "built $(realpath $OUT)"

@@ -99,6 +99,8 @@ int pd_debug_force_stream_k(int32_t on);
 int pd_debug_group_norm_fused(int32_t on);
 /* A/B switch: 0 = pd_attention's auto selection never picks the four-group kernel (engine 5), 1 = default */
 int pd_debug_attention_tc4(int32_t on);
+/* same for the persistent kernel (engine 8) */
+int pd_debug_attention_persistent(int32_t on);
 /* same for the three-group / 128-key-tile kernel (engine 6, head dim <= 40) */
 int pd_debug_attention_tc3(int32_t on);
 /* same for the tcgen05 attention kernel: 6 phases x 32 tiles of uint64 stamps from block (0,0,0) */
@@ -240,7 +242,10 @@ int pd_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const v
  * causal CLIP tower), 5 four-query-group / 64-key-tile tcgen05 kernel (bf16, head dim <= 64; measured equal to engine 3 on
  * B200, kept as an explicit engine / PD_B200_ATTN4=1 only), 6 three-query-group / 128-key-tile tcgen05 kernel (bf16, head
  * dim <= 40; what auto picks from 6144 queries up), 7 persistent tcgen05 short-key kernel (bf16, Nk <= 128, head dim <= 128:
- * the 77-token cross-attention; what auto picks for it once there are >= 296 256-query units) */
+ * the 77-token cross-attention; what auto picks for it once there are >= 296 256-query units), 8 persistent form of engine 3
+ * (bf16, head dim <= 64: one CTA per SM walks the (batch, head, 256-query) units, the next unit's Q / K loads and first
+ * Q K^T run under the current unit's tail; measured equal to engine 3 (the unit boundary is not where that kernel loses time):
+ * explicit engine, auto only with PD_B200_ATTN_PERSIST=1) */
 int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v,
                     int32_t ldv, void* out, int32_t ldo, int32_t B, int32_t heads, int32_t Nq,
                     int32_t Nk, int32_t d, float scale, int32_t dtype, int32_t engine, void* stream);

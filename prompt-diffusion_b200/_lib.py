@@ -60,6 +60,7 @@ SIGNATURES = {
     "pd_debug_attention_timeline": (C.c_int, [C.c_void_p]),
     "pd_debug_attention_tc4": (C.c_int, [C.c_int32]),
     "pd_debug_attention_tc3": (C.c_int, [C.c_int32]),
+    "pd_debug_attention_persistent": (C.c_int, [C.c_int32]),
     "pd_conv2d": (C.c_int, [C.POINTER(ConvParams), C.c_void_p]),
     "pd_conv2d_ln_parts_floats": (C.c_int64, [C.c_int64]),
     "pd_conv2d_gn_stats_supported": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),

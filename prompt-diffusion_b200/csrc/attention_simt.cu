@@ -227,6 +227,13 @@ int pd_attention_ex(const void* q, int32_t ldq, const void* k, int32_t ldk, cons
     set_error("pd_attention: the three-group tcgen05 engine needs what engine 3 needs and d <= 40");
     return PD_ERR_UNSUPPORTED;
   }
+  // engine 8 = the persistent two-group tcgen05 kernel (d <= 64): one CTA per SM walks the (batch, head, query pair) units
+  if (engine == 8 && !(tc_ok && d <= 64)) {
+    set_error("pd_attention: the persistent tcgen05 engine needs what engine 3 needs and d <= 64");
+    return PD_ERR_UNSUPPORTED;
+  }
+  if (engine == 8 || (engine == 0 && tc_ok && !attention_tc3_supported(d, Nq, Nk) && attention_ptc_supported(d, Nq, Nk, B, heads)))
+    return attention_ptc(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   if (engine == 6 || (engine == 0 && tc_ok && attention_tc3_supported(d, Nq, Nk)))
     return attention_tc3(q, ldq, k, ldk, v, ldv, out, ldo, B, heads, Nq, Nk, d, scale, s);
   if (engine == 5 || (engine == 0 && tc_ok && attention_tc4_supported(d, Nq, Nk)))

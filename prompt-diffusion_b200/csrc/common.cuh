@@ -157,6 +157,10 @@ bool attention_xtc_supported(int dtype, int d, int Nk, int ldq, int ldk, int ldv
                              const void* v, const void* out);
 int attention_xtc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
                   int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
+// attention_ptc.cu: persistent form of the streaming tcgen05 kernel (d <= 64): one CTA per SM walks (batch, head, query pair) units
+bool attention_ptc_supported(int d, int Nq, int Nk, int B, int heads);
+int attention_ptc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
+                  int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);
 bool attention_tc4_supported(int d, int Nq, int Nk);            // attention_tc4.cu: four query groups, 64-key tiles
 int attention_tc4(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* out, int ldo, int B,
                   int heads, int Nq, int Nk, int d, float scale, cudaStream_t s);

@@ -25,3 +25,6 @@ for s_ in [(16, 8, 256, 256, 160), (16, 8, 256, 77, 160), (16, 8, 64, 64, 160), 
 print("77-key cross-attention:    | short-key (mma.sync) us | tcgen05 streaming us | tcgen05 persistent short-key us")
 for s_ in [(16, 8, 4096, 77, 40), (16, 8, 1024, 77, 80), (32, 8, 9216, 77, 40), (32, 8, 2304, 77, 80), (2, 8, 4096, 77, 40)]:
     print("%4d %2d %5d %5d %4d | %11.1f | %10.1f | %10.1f" % (*s_, run(*s_, 4), run(*s_, 3), run(*s_, 7)))
+print("self-attention d <= 64:      | streaming (engine 3) us | three groups (6) us | persistent (8) us")
+for s_ in [(16, 8, 4096, 4096, 40), (32, 8, 9216, 9216, 40), (16, 8, 1024, 1024, 40)]:
+    print("%4d %2d %5d %5d %4d | %11.1f | %10.1f | %10.1f" % (*s_, run(*s_, 3, iters=5), run(*s_, 6, iters=5), run(*s_, 8, iters=5)))

@@ -9,7 +9,7 @@ mkdir -p build/variants
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 nvcc $FLAGS $defs -c prompt-diffusion_b200/csrc/$stem.cu -o build/variants/${stem}_$tag.o 2>&1 | grep -v "deprecated-gpu-targets" || true
 objs=""
-for f in elementwise norm softmax conv_simt attention_simt attention_mma attention_tc attention_tc3 attention_tc4 attention_xtc attention_short gemm_sm100; do
+for f in elementwise norm softmax conv_simt attention_simt attention_mma attention_tc attention_tc3 attention_tc4 attention_xtc attention_ptc attention_short gemm_sm100; do
   if [ "$f" == "$stem" ]; then objs="$objs build/variants/${stem}_$tag.o"; else objs="$objs build/$f.o"; fi
 done
 nvcc -shared -o build/variants/libpd_$tag.so $objs -lcudart_static -ldl -lrt -lpthread 2>&1 | grep -v "deprecated-gpu-targets" || true

@@ -412,6 +412,32 @@ TC_ATTN_CASES = [(1, 8, 256, 256, 40), (2, 8, 1024, 1024, 40), (2, 8, 100, 77, 4
                  (1, 4, 130, 130, 144)]
 
 
+PTC_ATTN_CASES = [(2, 8, 1024, 1024, 40), (1, 8, 4096, 4096, 40), (3, 5, 700, 650, 64), (1, 2, 300, 128, 16), (2, 8, 2304, 2304, 40),
+                  (1, 4, 130, 1000, 48), (16, 8, 256, 256, 32), (1, 1, 3000, 513, 40)]
+
+
+@pytest.mark.parametrize("B,heads,Nq,Nk,d", PTC_ATTN_CASES)
+def test_attention_tcgen05_persistent(B, heads, Nq, Nk, d):
+    """Persistent form of the streaming tcgen05 kernel (engine 8): one CTA per SM walks (batch, head, query pair) units.
+    Same arithmetic per unit as engine 3, so the two must agree bit for bit; also checked against torch fp32."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(27)
+    Cc = heads * d
+    q = torch.randn(B * Nq, Cc, device=DEV, generator=g).to(torch.bfloat16)
+    kv = torch.randn(B * Nk, 2 * Cc, device=DEV, generator=g).to(torch.bfloat16)
+    k, v = kv[:, :Cc], kv[:, Cc:]
+    out = torch.full((B * Nq, Cc + 8), 3.0, dtype=torch.bfloat16, device=DEV)
+    ops.attention(q, k, v, out[:, :Cc], B, heads, Nq, Nk, d, engine=8)
+    torch.cuda.synchronize()
+    assert bool((out[:, Cc:] == 3.0).all()), "wrote past the head columns"
+    ref = _attn_ref(q.reshape(B, Nq, Cc), k.reshape(B, Nk, Cc), v.reshape(B, Nk, Cc), heads, d ** -0.5)
+    err = rel_l2(out[:, :Cc].float().reshape(B, Nq, Cc), ref)
+    assert err < 1e-2, err
+    out3 = torch.empty_like(out)
+    ops.attention(q, k, v, out3[:, :Cc], B, heads, Nq, Nk, d, engine=3)
+    assert torch.equal(out3[:, :Cc], out[:, :Cc])
+
+
 XTC_ATTN_CASES = [(2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 8, 300, 77, 40), (3, 5, 1000, 1, 64), (1, 2, 9216, 128, 40),
                   (2, 3, 700, 100, 128), (1, 8, 2304, 77, 80), (1, 1, 64, 16, 16), (5, 8, 256, 77, 40)]
 
