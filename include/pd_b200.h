@@ -92,6 +92,12 @@ int pd_debug_force_bn(int32_t bn);
  * pd_debug_bres_launches counts the launches that took it. */
 int pd_debug_force_bres(int32_t on);
 uint64_t pd_debug_bres_launches(void);
+/* vertical-halo schedule of the tcgen05 conv engine (3x3, stride 1, one K segment, output W % 8 == 0 and H % 16 == 0): per
+ * 64-channel chunk the activation operand is fetched as three column-shifted 8 x 18-pixel boxes whose three row offsets are
+ * the dy taps — 3 instead of 9 activation loads per chunk.  1 = wherever it applies, 0 = per the variant table;
+ * pd_debug_vh_launches counts the launches that took it. */
+int pd_debug_force_vh(int32_t on);
+uint64_t pd_debug_vh_launches(void);
 /* together with a forced CTA group: 1 = stream-K schedule of the tcgen05 conv engine wherever it applies (the (tile, k-block)
  * space is cut evenly over the CTAs; partial tiles are summed in K order by the last CTA to arrive), 0 = data-parallel */
 int pd_debug_force_stream_k(int32_t on);

@@ -54,6 +54,8 @@ SIGNATURES = {
     "pd_debug_force_bn": (C.c_int, [C.c_int32]),
     "pd_debug_force_bres": (C.c_int, [C.c_int32]),
     "pd_debug_bres_launches": (C.c_uint64, []),
+    "pd_debug_force_vh": (C.c_int, [C.c_int32]),
+    "pd_debug_vh_launches": (C.c_uint64, []),
     "pd_debug_force_stream_k": (C.c_int, [C.c_int32]),
     "pd_layer_norm_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "pd_debug_group_norm_fused": (C.c_int, [C.c_int32]),

@@ -45,6 +45,7 @@ constexpr int TC_REGS_EPI = 208;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_SMEM_BUDGET = 227 * 1024 - 2048;
+constexpr int TC_VH_BOX_BYTES = 18 * 8 * 128;   // vertical-halo A box: 18 rows x 8 pixels x 64 channels (18 swizzle atoms)
 
 struct TcArgs {
   const float* bias; const float* rowvec; const void* res; void* out;
@@ -80,6 +81,10 @@ struct TcArgs {
   int gn_ld, gn_rec_off, gn_rpi;
   int pad_x, pad_y;             // zero-padding before the first tap (ksize / 2 for the centred 1x1 / 3x3 kernels)
   int flat;                     // 1x1 stride-1 layer flattened to one long pixel row
+  int vh;                       // 1: "vertical halo" schedule of a 3x3 stride-1 conv: per 64-channel chunk the A operand is
+                                // fetched as THREE column-shifted boxes of 8 x 18 pixels (one per dx); the three dy taps of
+                                // a box are 1024-byte-aligned row offsets into it.  3 instead of 9 A loads per chunk.
+  int vh_na, vh_nb;             // A-box slots / B stages of that schedule
   int b_res;                    // 1: the CTA's whole B (weight) tile, all K blocks, stays RESIDENT in shared memory: it is
                                 // loaded once, every worker keeps one N tile for life and the ring carries A only
   uint32_t idesc;
@@ -202,6 +207,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ __align__(8) uint64_t res_full[4];
   __shared__ __align__(8) uint64_t b_full;
+  __shared__ __align__(8) uint64_t a_full[TC_MAX_STAGES];     // vertical-halo schedule: A-box ring
+  __shared__ __align__(8) uint64_t a_empty[TC_MAX_STAGES];
   __shared__ uint32_t tmem_base_slot;
   __shared__ int sk_last;
 
@@ -213,8 +220,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int b_bytes = b_rows * TC_BK * 2;
   const int nkb = a.nk0 + a.nk1;
   const bool bres = !SK && a.b_res != 0;
-  const int stage_bytes = bres ? TC_A_BYTES : TC_A_BYTES + b_bytes;
-  unsigned char* ring = smem + (bres ? nkb * b_bytes : 0);    // resident B: [nkb][b_rows x 64] in front of the A ring
+  const bool vh = !SK && a.vh != 0;
+  const int stage_bytes = vh ? b_bytes : bres ? TC_A_BYTES : TC_A_BYTES + b_bytes;
+  // resident B: [nkb][b_rows x 64] in front of the A ring; vertical halo: [vh_na A boxes] in front of the B ring
+  unsigned char* ring = smem + (vh ? a.vh_na * TC_VH_BOX_BYTES : bres ? nkb * b_bytes : 0);
   const int nt_res = bres ? a.n_tiles : 0;
   const int pm_tiles = (a.m_tiles + CG - 1) / CG;      // M tiles of CG x 128 rows
   const int tile_div = a.n_fast ? a.n_tiles : pm_tiles;
@@ -229,6 +238,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CG * (EPI == 8 ? 4 : 8)); }
     for (int i = 0; i < 4; ++i) mbar_init(&res_full[i], 1);
     mbar_init(&b_full, 1);
+    for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     if (EPI != 8) { tma_prefetch_desc(&map_o64); if (EPI < 8 && (EPI & 1)) tma_prefetch_desc(&map_r64); }
     fence_barrier_init();
   }
@@ -254,6 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ================= TMA producer (both CTAs of a pair); warp-uniform loop, one elected lane issues =================
     {
       int stage = 0; uint32_t phase = 0;
+      int astage = 0; uint32_t aphase = 0;             // vertical-halo schedule: A-box ring position
       PieceIter pit(SK, worker, nworkers, num_tiles, nkb, tile_div, nt_res);
       int tile, kb0, kb1, tix = 0;
       if (bres && pit.peek_tile() >= 0 && elect_one()) {
@@ -288,6 +299,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (kb0 != 0 && kb0 < a.nk0) {
           const int tap = kb0 / a.cpt0;
           cb = kb0 - tap * a.cpt0; dy = tap / a.ksize; dx = tap - dy * a.ksize;
+        }
+        if (vh) {
+          // chunk-major walk: per 64-channel chunk three column-shifted A boxes, each followed by its three dy weight tiles
+          for (int c = 0; c < a.cpt0; ++c) {
+            for (int ddx = 0; ddx < 3; ++ddx) {
+              mbar_wait(&a_empty[astage], aphase ^ 1, 120 + astage);
+              if (elect_one()) {
+                unsigned char* sbox = smem + astage * TC_VH_BOX_BYTES;
+                if (cta_rank == 0) mbar_expect_tx(&a_full[astage], (uint32_t)(CG * TC_VH_BOX_BYTES));
+                if (CG == 2) tma_load_4d_2sm(sbox, &map_a0, &a_full[astage], c * TC_BK, x0 + ddx - 1, y0 - 1, b0);
+                else tma_load_4d(sbox, &map_a0, &a_full[astage], c * TC_BK, x0 + ddx - 1, y0 - 1, b0);
+              }
+              __syncwarp();
+              if (++astage == a.vh_na) { astage = 0; aphase ^= 1; }
+              for (int ddy = 0; ddy < 3; ++ddy) {
+                mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+                const int wkb = (ddy * 3 + ddx) * a.cpt0 + c;            // k-block of (tap, chunk) in the weight matrix
+                if (elect_one()) {
+                  unsigned char* sb = ring + stage * stage_bytes;
+                  if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(CG * b_bytes));
+                  if (CG == 2) {
+                    if (a.w_blocked) tma_load_3d_2sm(sb, &map_w, &full_bar[stage], 0, n0, wkb);
+                    else tma_load_2d_2sm(sb, &map_w, &full_bar[stage], wkb * TC_BK, n0);
+                  } else {
+                    if (a.w_blocked) tma_load_3d(sb, &map_w, &full_bar[stage], 0, n0, wkb);
+                    else tma_load_2d(sb, &map_w, &full_bar[stage], wkb * TC_BK, n0);
+                  }
+                }
+                __syncwarp();
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+              }
+            }
+          }
+          continue;
         }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
@@ -334,6 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ================= MMA issuer (even CTA of a pair); warp-uniform loop, one elected lane issues =================
     if (cta_rank == 0) {
       int stage = 0; uint32_t phase = 0;
+      int astage = 0; uint32_t aphase = 0;
       int it = 0;
       PieceIter pit(SK, worker, nworkers, num_tiles, nkb, tile_div, nt_res);
       int tile, kb0, kb1;
@@ -345,6 +391,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         tc_fence_after();
         if (lane == 0) PD_DBG(1, it, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        if (vh) {
+          for (int c = 0; c < a.cpt0; ++c) {
+            for (int ddx = 0; ddx < 3; ++ddx) {
+              mbar_wait(&a_full[astage], aphase, 320 + astage);
+              const uint32_t sbox = s_u32(smem + astage * TC_VH_BOX_BYTES);
+              for (int ddy = 0; ddy < 3; ++ddy) {
+                mbar_wait(&full_bar[stage], phase, 300 + stage);
+                tc_fence_after();
+                // rows y0 + ddy - 1 .. + 15 of the box: 16 consecutive 1024-byte swizzle atoms starting at atom ddy
+                const uint64_t adesc = make_smem_desc(sbox + (uint32_t)(ddy * 1024));
+                const uint64_t bdesc = make_smem_desc(s_u32(ring + stage * stage_bytes));
+                const bool very_last = c == a.cpt0 - 1 && ddx == 2 && ddy == 2;
+                if (elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < TC_BK / 16; ++k) {
+                    const uint32_t accum = (c | ddx | ddy | k) != 0 ? 1u : 0u;
+                    if (CG == 2) umma_bf16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, accum);
+                    else umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), a.idesc, accum);
+                  }
+                  if (CG == 2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                  if (ddy == 2) { if (CG == 2) umma_commit_2sm(&a_empty[astage]); else umma_commit(&a_empty[astage]); }
+                  if (very_last) { if (CG == 2) umma_commit_2sm(&tmem_full[acc]); else umma_commit(&tmem_full[acc]); }
+                }
+                __syncwarp();
+                if (++stage == a.stages) { stage = 0; phase ^= 1; }
+              }
+              if (++astage == a.vh_na) { astage = 0; aphase ^= 1; }
+            }
+          }
+          if (lane == 0) PD_DBG(1, it, 1);
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase, 300 + stage);
           tc_fence_after();
@@ -949,6 +1027,8 @@ static unsigned long long* g_dbg = nullptr;
 #endif
 static int g_force_bn = 0;   // experiments: pin the N extent of the tile (multiple of 32, <= 256)
 static int g_force_bres = 0; // experiments / tests: resident-B schedule wherever it applies
+static int g_force_vh = 0;   // experiments / tests: vertical-halo schedule wherever it applies
+static unsigned long long g_vh_launches = 0;
 static unsigned long long g_bres_launches = 0;   // launches that took the resident-B schedule (tests assert the path ran)
 static int g_force_cg = 0;   // 0 auto, 1 single-CTA tiles only, 2 CTA pairs whenever the epilogue allows (tests / A-B timing)
 static int g_n_fast = -1;    // tile order (PD_TILE_COORDS): -1 = read PD_B200_NFAST once (default 1)
@@ -1102,7 +1182,7 @@ bool conv2d_tc_supported(const pd_conv_params* p, const char** why) {
 // 1 = required, else PD_ERR_UNSUPPORTED; 2 = where it applies);
 // bn = N extent override (0 = heuristic); bres = 1: resident-B schedule (short-K layers: the worker's weight tile, all
 // of K, is loaded into shared memory once; PD_ERR_UNSUPPORTED when it does not fit or does not apply)
-struct TcVariant { int cg, sk, bn, bres; };
+struct TcVariant { int cg, sk, bn, bres, vh; };
 
 // stream-K scratch, one per device: partial accumulators (2 slots per CTA) and self-resetting arrival counters
 constexpr int SK_MAX_TILES = 32768;
@@ -1174,6 +1254,11 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
   if (p->ksize == 1 && p->stride == 1) a.bw = 128;   // partial last tile is masked
   a.bh = pow2_divisor(gH, 128 / a.bw);
   a.bn = 128 / (a.bw * a.bh);
+  // vertical-halo schedule: 3x3, stride 1, one K segment, bf16 through the TMA epilogue, data-parallel, 8 x 16 pixel tiles
+  const bool vh_ok = (var.vh != 0 || g_force_vh != 0) && p->ksize == 3 && p->stride == 1 && p->C2 == 0 && p->out_dtype == PD_BF16 &&
+                     var.sk == 0 && var.bres == 0 && gW % 8 == 0 && gH % 16 == 0 && (p->out_sx | p->out_sy | p->out_sb) == 0;
+  if (var.vh != 0 && !vh_ok) return PD_ERR_UNSUPPORTED;
+  if (vh_ok) { a.bw = 8; a.bh = 16; a.bn = 1; }
   a.tiles_x = (gW + a.bw - 1) / a.bw;
   a.tiles_y = (gH + a.bh - 1) / a.bh;
   a.tiles_b = (gB + a.bn - 1) / a.bn;
@@ -1229,6 +1314,22 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
       return PD_ERR_UNSUPPORTED;
     }
   }
+  a.vh = 0; a.vh_na = 0; a.vh_nb = 0;
+  if (vh_ok && !a.b_res) {
+    const int bb = (a.BN / CGv) * TC_BK * 2;
+    int na = 0, nb = 0;
+    for (int cand : {6, 4, 3}) {             // A-box slots: as many as leave a useful B ring
+      const int n = (TC_SMEM_BUDGET - epi_bytes - cand * TC_VH_BOX_BYTES) / bb;
+      if (n >= (cand == 6 ? 4 : cand == 4 ? 3 : 2)) { na = cand; nb = n; break; }
+    }
+    if (na != 0) {
+      a.vh = 1; a.vh_na = na; a.vh_nb = nb > TC_MAX_STAGES ? TC_MAX_STAGES : nb;
+      stage_bytes = bb; a.stages = a.vh_nb; res_bytes = na * TC_VH_BOX_BYTES;
+      ++g_vh_launches;
+    } else if (var.vh != 0) {
+      return PD_ERR_UNSUPPORTED;
+    }
+  }
   if (a.stages > TC_MAX_STAGES) a.stages = TC_MAX_STAGES;
   if (a.stages < 2) { set_error("conv_tc: not enough shared memory for 2 stages"); return PD_ERR_UNSUPPORTED; }
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)((TC_BM * CGv) >> 4) << 24);
@@ -1240,6 +1341,7 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
     uint64_t strides[3] = {(uint64_t)p->ldx * 2, (uint64_t)iW * p->ldx * 2, (uint64_t)iH * iW * p->ldx * 2};
     uint32_t box[4] = {TC_BK, (uint32_t)(a.bw * p->stride), (uint32_t)(a.bh * p->stride), (uint32_t)a.bn};
     uint32_t es[4] = {1, (uint32_t)p->stride, (uint32_t)p->stride, 1};
+    if (a.vh) { box[1] = 8; box[2] = 18; box[3] = 1; }       // one dx column of the halo: 8 pixels x (16 + 2) rows
 #ifdef PD_DEBUG
     // timing experiment 12 (wrong results): fetch only HALF of the A tile's pixel rows — what a CTA would issue if the
     // other half came from a cluster peer by TMA multicast
@@ -1404,7 +1506,7 @@ struct TuneKey {
 struct TuneRow { TuneKey k; TcVariant v; };
 static const TuneRow k_tune_table[] = {
 #include "tune_table.inc"
-    {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0}}   // terminator
+    {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}}   // terminator
 };
 static std::map<TuneKey, TcVariant> g_tune;      // runtime cache: table rows + autotuned shapes (guarded by g_mu)
 static bool g_tune_loaded = false;
@@ -1430,7 +1532,7 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   dbg = g_dbg_mode != 0;
 #endif
   if (g_force_cg != 0 || p->out_dtype != PD_BF16 || dbg)
-    return conv2d_tc_impl(p, s, TcVariant{g_force_cg, g_force_cg != 0 && g_force_sk ? 2 : 0, 0, 0});
+    return conv2d_tc_impl(p, s, TcVariant{g_force_cg, g_force_cg != 0 && g_force_sk ? 2 : 0, 0, 0, 0});
   const int pad = p->ksize / 2;
   const int Ho = p->ksize == 2 ? p->H : (p->H + 2 * pad - p->ksize) / p->stride + 1;
   const int Wo = p->ksize == 2 ? p->W : (p->W + 2 * pad - p->ksize) / p->stride + 1;
@@ -1438,7 +1540,7 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   const TuneKey key{p->B * Ho * Wo, p->Cout, p->ksize * p->ksize * p->C + p->C2, p->ksize, p->stride, 0,
                     p->act == PD_ACT_GEGLU ? 8 : 0};
   bool tabled = false;
-  TcVariant tv{0, 0, 0, 0};
+  TcVariant tv{0, 0, 0, 0, 0};
   {
     std::lock_guard<std::mutex> lk(g_mu);          // released before the launch: conv2d_tc_impl takes g_mu itself
     tune_load_locked();
@@ -1447,31 +1549,32 @@ int conv2d_tc(const pd_conv_params* p, cudaStream_t s) {
   }
   // a tabled stream-K row whose scratch cannot be had falls back to its data-parallel sibling inside impl (sk = 2)
   if (tabled) {
-    const int rc = conv2d_tc_impl(p, s, TcVariant{tv.cg, tv.sk ? 2 : 0, tv.bn, tv.bres});
-    if (rc != PD_ERR_UNSUPPORTED || !tv.bres) return rc;
-    return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0});    // a resident-B row on a device with fewer SMs than it was tuned for
+    const int rc = conv2d_tc_impl(p, s, TcVariant{tv.cg, tv.sk ? 2 : 0, tv.bn, tv.bres, tv.vh});
+    if (rc != PD_ERR_UNSUPPORTED || !(tv.bres || tv.vh)) return rc;
+    return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0, 0});    // a resident-B row on a device with fewer SMs than it was tuned for
   }
-  if (!g_autotune) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0});
+  if (!g_autotune) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0, 0});
   // ---- opt-in timing autotune (table regeneration) ----
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
   const bool in_place = p->res == p->out || p->x == p->out || (p->x2 != nullptr && p->x2 == p->out);
-  if (cap != cudaStreamCaptureStatusNone || in_place || g_prof_on) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0});
+  if (cap != cudaStreamCaptureStatusNone || in_place || g_prof_on) return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0, 0});
   cudaEvent_t e0, e1;
-  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaGetLastError(); return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0}); }
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { cudaGetLastError(); return conv2d_tc_impl(p, s, TcVariant{0, 0, 0, 0, 0}); }
   // stream-K with the model's tile width, and with 128-wide tiles: fewer pieces per tile (cheaper fix-up) against
   // more operand traffic per FLOP
   // resident-B candidates (short-K layers): tile widths whose whole-K weight tile fits next to the A ring
-  constexpr int NCAND = 15;
+  constexpr int NCAND = 19;
   const TcVariant cands[NCAND] = {{1, 0, 0, 0}, {2, 0, 0, 0}, {2, 1, 0, 0}, {1, 1, 0, 0}, {2, 1, 128, 0}, {1, 1, 128, 0},
                                   {2, 1, 256, 0}, {1, 1, 256, 0},
                                   {1, 0, 160, 1}, {2, 0, 160, 1}, {1, 0, 128, 1}, {2, 0, 128, 1}, {2, 0, 192, 1}, {2, 0, 256, 1},
-                                  {1, 0, 96, 1}};
+                                  {1, 0, 96, 1},
+                                  {1, 0, 0, 0, 1}, {2, 0, 0, 0, 1}, {2, 0, 160, 0, 1}, {2, 0, 128, 0, 1}};
   float best_ms = 1e30f; TcVariant best = cands[0]; int last_run = -1, best_idx = 0;
   for (int c = 0; c < NCAND; ++c) {
     if (cands[c].bn != 0 && (p->Cout < cands[c].bn || (p->act == PD_ACT_GEGLU && (!cands[c].bres || cands[c].bn % 64 != 0)))) continue;
     int rc = conv2d_tc_impl(p, s, cands[c]);                // warm (tensor maps, L2)
-    if (rc == PD_ERR_UNSUPPORTED && (cands[c].sk || cands[c].bres)) continue;  // stream-K / resident B does not apply to this shape
+    if (rc == PD_ERR_UNSUPPORTED && (cands[c].sk || cands[c].bres || cands[c].vh)) continue;  // schedule does not apply to this shape
     if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
     float ms = 0.f;
     cudaEventRecord(e0, s);
@@ -1523,8 +1626,8 @@ int pd_tune_dump(const char* path) {
   std::lock_guard<std::mutex> lk(pd::g_mu);
   pd::tune_load_locked();
   for (auto& kv : pd::g_tune)
-    fprintf(f, "{{%d, %d, %d, %d, %d, %d, %d}, {%d, %d, %d, %d}},\n", kv.first.M, kv.first.N, kv.first.K, kv.first.ksize,
-            kv.first.stride, kv.first.c2, kv.first.epi, kv.second.cg, kv.second.sk, kv.second.bn, kv.second.bres);
+    fprintf(f, "{{%d, %d, %d, %d, %d, %d, %d}, {%d, %d, %d, %d, %d}},\n", kv.first.M, kv.first.N, kv.first.K, kv.first.ksize,
+            kv.first.stride, kv.first.c2, kv.first.epi, kv.second.cg, kv.second.sk, kv.second.bn, kv.second.bres, kv.second.vh);
   fclose(f);
   return 0;
 }
@@ -1532,6 +1635,9 @@ int pd_debug_force_bn(int bn) { pd::g_force_bn = (bn >= 32 && bn <= 256 && bn % 
 // 1 = resident-B schedule wherever it fits (tests / A-B timing), 0 = per the variant table
 int pd_debug_force_bres(int on) { pd::g_force_bres = on != 0; return 0; }
 uint64_t pd_debug_bres_launches(void) { return pd::g_bres_launches; }
+// 1 = vertical-halo schedule of the 3x3 stride-1 convs wherever it applies (tests / A-B timing), 0 = per the variant table
+int pd_debug_force_vh(int on) { pd::g_force_vh = on != 0; return 0; }
+uint64_t pd_debug_vh_launches(void) { return pd::g_vh_launches; }
 int pd_debug_force_cta_group(int cg) { pd::g_force_cg = (cg == 1 || cg == 2) ? cg : 0; return 0; }
 // with a forced CTA group: 1 = stream-K schedule wherever it applies (falls back to data-parallel elsewhere)
 int pd_debug_force_stream_k(int on) { pd::g_force_sk = on != 0; return 0; }

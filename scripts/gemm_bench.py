@@ -49,9 +49,33 @@ ap.add_argument("--modes", action="store_true", help="timing experiment: full ke
 ap.add_argument("--epi-modes", action="store_true", help="timing experiment on the epilogue of short-K layers (gemm_sm100.cu dbg_mode 3..7)")
 ap.add_argument("--bres", action="store_true", help="resident-B schedule against the tabled variant on the short-K layer shapes")
 ap.add_argument("--sk", action="store_true", help="stream-K tile shapes on the small-M (8x8 / 16x16 level) 3x3 layers")
+ap.add_argument("--vh", action="store_true", help="vertical-halo schedule against the tabled variant on the 3x3 layer shapes")
 a = ap.parse_args()
 BLOCKED = a.blocked
-if a.sk:
+if a.vh:
+    from prompt_diffusion_b200 import _lib
+    L = _lib.lib
+    BLOCKED = True
+    shapes = [(16, 64, 64, 320, 320, 3, 0), (16, 64, 64, 640, 320, 3, 0), (16, 64, 64, 960, 320, 3, 0), (16, 32, 32, 640, 640, 3, 0),
+              (16, 32, 32, 1280, 640, 3, 0), (16, 32, 32, 320, 640, 3, 0), (16, 16, 16, 1280, 1280, 3, 0), (16, 16, 16, 2560, 1280, 3, 0)]
+    combos = [(1, 0), (2, 0), (2, 160), (2, 128), (2, 256)]
+    print("   B   HxW     C     N ks res | tabled us  TFLOP/s | " + " | ".join("vh cg%d bn%-3d" % c for c in combos))
+    for s_ in shapes:
+        base, tf, _ = run(*s_, iters=a.iters)
+        row = []
+        for cg, bn in combos:
+            if bn > s_[4]: row.append(None); continue
+            L.pd_debug_force_cta_group(cg); L.pd_debug_force_bn(bn); L.pd_debug_force_vh(1)
+            n0 = L.pd_debug_vh_launches()
+            try:
+                us = run(*s_, iters=a.iters)[0]
+            except RuntimeError:
+                us = None
+            took = L.pd_debug_vh_launches() > n0
+            L.pd_debug_force_cta_group(0); L.pd_debug_force_bn(0); L.pd_debug_force_vh(0)
+            row.append(us if took else None)
+        print("%4d %3dx%-3d %5d %5d %2d %3d | %9.1f %8.0f | " % (*s_, base, tf) + " | ".join("%12.1f" % r if r is not None else "           -" for r in row))
+elif a.sk:
     from prompt_diffusion_b200 import _lib
     L = _lib.lib
     BLOCKED = True

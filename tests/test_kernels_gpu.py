@@ -222,6 +222,36 @@ def test_conv_tcgen05_bf16_resident_weights(case, cg, bn):
     assert err == ref_err, (err, ref_err)
 
 
+VH_CASES = [
+    dict(B=2, H=32, W=32, C=320, Cout=320, ksize=3, rowvec=True),                # ResBlock conv1
+    dict(B=1, H=16, W=16, C=64, Cout=64, ksize=3),                               # smallest: two 8 x 16 tiles
+    dict(B=2, H=64, W=64, C=320, Cout=320, ksize=3, res=True, act=1),
+    dict(B=3, H=16, W=24, C=128, Cout=352, ksize=3, res=True, alpha=0.5, ldo_extra=64),   # odd tile counts, partial N tile
+    dict(B=2, H=32, W=32, C=640, Cout=640, ksize=3, blocked=True),
+    dict(B=1, H=48, W=48, C=1280, Cout=640, ksize=3, rowvec=True, blocked=True),
+]
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("case", VH_CASES)
+def test_conv_tcgen05_bf16_vertical_halo(case, cg):
+    """Vertical-halo schedule forced on: three column-shifted 8 x 18-pixel activation boxes per 64-channel chunk, the dy taps
+    as row offsets into them.  Against torch, and against the ordinary schedule (same products, different fp32 order)."""
+    from prompt_diffusion_b200 import _lib
+    L = _lib.lib
+    L.pd_debug_force_cta_group(cg)
+    try:
+        ref_err = _conv_case(torch.bfloat16, _lib.PD_ENGINE_TC, **case)
+        n0 = L.pd_debug_vh_launches()
+        L.pd_debug_force_vh(1)
+        err = _conv_case(torch.bfloat16, _lib.PD_ENGINE_TC, **case)
+        assert L.pd_debug_vh_launches() == n0 + 1, "shape did not take the vertical-halo schedule"
+    finally:
+        L.pd_debug_force_vh(0); L.pd_debug_force_cta_group(0)
+    assert err < 6e-3, err
+    assert abs(err - ref_err) < 1e-3, (err, ref_err)
+
+
 def test_conv_tc_rejects_unsupported():
     from prompt_diffusion_b200._lib import PD_ENGINE_TC
     with pytest.raises(RuntimeError):
