@@ -710,9 +710,139 @@ static int ln_stats_launch(const void* x, int ldx, float* stats, int64_t rows, i
   return PD_ERR_UNSUPPORTED;
 }
 
+
+// ---- register-resident GroupNorm for the small late-stage tensors (bf16) ---------------------------------------------------
+// GroupNorm groups are independent, so a CTA that owns ALL pixels of `ng` whole groups of one image needs no other CTA:
+// its slice (<= 12 16-byte vectors per thread, 512 threads) is loaded ONCE into registers with every load in flight, the statistics are
+// reduced inside the CTA, and the same registers are normalised and stored.  One ordinary (PDL) launch, no cooperative
+// launch, no global barrier, no second read — the cooperative kernel above costs ~15 us on a 16 x 64 x 1280 tensor whose
+// data would move in 1 us.  Used for HW <= 256 when a split into <= #SM slices of >= 256-byte rows fits 12 vectors per thread.
+constexpr int GS_THREADS = 512, GS_VT = 12;
+static int g_gn_small = -1;       // -1: read PD_B200_GN_SMALL once (default on)
+
+__global__ void __launch_bounds__(GS_THREADS, 1)
+gn_small_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ out, int ldo, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int HW, int cpg, int ng, float eps, int act) {
+  extern __shared__ float sm[];                 // [rpp][2][width] per-row-lane channel sums | sums of squares
+  __shared__ float s_g[2 * GN_GROUPS_MAX];      // (mean, rstd) of this CTA's groups
+  const int b = blockIdx.y;
+  const int width = ng * cpg, c0 = blockIdx.x * width;
+  const int nv = width >> 3;                    // 16-byte vectors per pixel row of the slice
+  const int rpp = GS_THREADS / nv;              // pixel rows covered by one pass of the thread grid
+  const int vcol = threadIdx.x % nv, row0 = threadIdx.x / nv;
+  const bool active = row0 < rpp;
+  const bf16* xp = x + (int64_t)b * HW * ldx + c0 + vcol * 8;
+  griddep_wait();
+  uint4 raw[GS_VT];
+#pragma unroll
+  for (int i = 0; i < GS_VT; ++i) {
+    const int r = row0 + i * rpp;
+    raw[i] = (active && r < HW) ? *reinterpret_cast<const uint4*>(xp + (int64_t)r * ldx) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  float su[8], sq[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) su[k] = sq[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < GS_VT; ++i) {             // rows past HW hold zeros: they add nothing
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(&raw[i]), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { su[k] += f[k]; sq[k] = fmaf(f[k], f[k], sq[k]); }
+  }
+  if (active) {
+    float* mine = sm + (size_t)row0 * 2 * width + vcol * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mine[k] = su[k]; mine[width + k] = sq[k]; }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int gi = warp; gi < ng; gi += GS_THREADS / 32) {
+    double a = 0.0, q = 0.0;
+    for (int c = lane; c < cpg; c += 32)
+      for (int t = 0; t < rpp; ++t) {           // fixed order: deterministic
+        a += (double)sm[(size_t)t * 2 * width + gi * cpg + c];
+        q += (double)sm[(size_t)t * 2 * width + width + gi * cpg + c];
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) {
+      const double n = (double)HW * (double)cpg;
+      const double mean = a / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_g[2 * gi] = (float)mean;
+      s_g[2 * gi + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) griddep_launch();
+  if (!active) return;
+  float sa[8], sb[8];                           // y = x * sa + sb
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = vcol * 8 + k, gi = c / cpg;
+    sa[k] = s_g[2 * gi + 1] * gamma[c0 + c];
+    sb[k] = fmaf(-s_g[2 * gi], sa[k], beta[c0 + c]);
+  }
+  bf16* op = out + (int64_t)b * HW * ldo + c0 + vcol * 8;
+#pragma unroll
+  for (int i = 0; i < GS_VT; ++i) {
+    const int r = row0 + i * rpp;
+    if (r < HW) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(&raw[i]), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float y = fmaf(f[k], sa[k], sb[k]);
+        if (act == PD_ACT_SILU) y = silu_f(y);
+        f[k] = y;
+      }
+      *reinterpret_cast<bf16x8*>(op + (int64_t)r * ldo) = pack8(f);
+    }
+  }
+}
+
+// groups per CTA for the register-resident kernel, 0 if the tensor does not fit its budget
+static int gn_small_groups(int B, int HW, int C, int groups) {
+  if (g_gn_small < 0) {
+    const char* e = getenv("PD_B200_GN_SMALL");
+    g_gn_small = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (!g_gn_small) return 0;
+  const int cpg = C / groups;
+  int best = 0;
+  for (int ng = 1; ng <= groups; ++ng) {
+    if (groups % ng != 0 || (ng * cpg) % 8 != 0) continue;
+    const int nv = ng * cpg / 8;
+    if (nv > GS_THREADS) break;
+    const int rpp = GS_THREADS / nv;
+    const int npass = (HW + rpp - 1) / rpp;
+    if (npass > GS_VT) break;                   // (npass grows with ng)
+    const long long ctas = (long long)(groups / ng) * B;
+    // measured (profiles/r02_gn_small.txt): wins where the slice rows are >= 256 bytes and the CTAs fit ONE wave of the
+    // one-CTA-per-SM grid (16 x 256 x 1280: 18.6 -> 11.0 us, 16 x 64 x 1280 / 2560: 14.9 -> 8.8 us); narrow slices and
+    // multi-wave grids lose to the cooperative kernel (16 x 1024 x 1280: 31 -> 83 us)
+    if (ng * cpg * 2 < 256 || ctas > num_sms()) continue;
+    best = ng;                                  // the coarsest split that still fits: most work per thread
+  }
+  if (HW > 256) return 0;
+  return best;
+}
+
 template <typename T, typename TO>
 static int gn_launch(const void* x, int ldx, void* out, int ldo, const float* gamma, const float* beta,
                      float* partial, int B, int HW, int C, int groups, float eps, int act, cudaStream_t s) {
+  if constexpr (sizeof(T) == 2 && sizeof(TO) == 2) {
+    const int ng = (ldx % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)out % 16) == 0) ? gn_small_groups(B, HW, C, groups) : 0;
+    if (ng > 0) {
+      const int cpg = C / groups, width = ng * cpg, rpp = GS_THREADS / (width / 8);
+      const size_t smem = (size_t)rpp * 2 * width * sizeof(float);      // <= 512 / nv * 2 * 8 nv * 4 = 32 KiB
+      cudaError_t le = launch_pdl(gn_small_kernel, dim3((unsigned)(groups / ng), (unsigned)B), dim3(GS_THREADS), smem, s, 1,
+                                  (const bf16*)x, ldx, (bf16*)out, ldo, gamma, beta, HW, cpg, ng, eps, act);
+      if (le != cudaSuccess) { set_error("pd_group_norm: launch failed: %s", cudaGetErrorString(le)); return (int)le; }
+      return check_launch("gn_small");
+    }
+  }
   int chunks = gn_num_chunks(HW);
   constexpr int Vv = VecIO<T>::V;
   const GnGrid gg = gn_grid(C, Vv);

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "norm or gn" 2>&1 | tail -3
+timeout 300 python scripts/norm_bench.py 2>&1 | grep "^gn\|kernel" | tee gpurun_out/r2_40_gn_small.txt
+scripts/gpu_ab_step.sh r2_40_ab_gn_small
