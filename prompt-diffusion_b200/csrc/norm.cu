@@ -75,6 +75,7 @@ gn_stats_kernel(const T* __restrict__ x, int ldx, float* __restrict__ partial, i
   const GnGrid g = gn_grid(C, V);
   const int tx = threadIdx.x % g.tx_n, ty = threadIdx.x / g.tx_n;
   const T* base = x + (int64_t)b * HW * ldx;
+  griddep_wait();                  // (PDL launch: x comes from the previous kernel of the stream)
   if (ty < g.ty_n) {
     for (int ps = 0; ps < g.passes; ++ps) {
       const int j = tx + ps * g.tx_n;
@@ -160,6 +161,7 @@ gn_apply_kernel(const T* __restrict__ x, int ldx, TO* __restrict__ out, int ldo,
   __shared__ float s_g[2 * GN_GROUPS_MAX];
   const int b = blockIdx.y;
   const int cpg = C / groups;
+  griddep_wait();                  // (PDL launch: the statistics kernel in front has completed and flushed)
   if (threadIdx.x < 2 * groups) s_g[threadIdx.x] = stats[(int64_t)b * GN_GROUPS_MAX * 2 + threadIdx.x];
   __syncthreads();
   const GnGrid g = gn_grid(C, V);
@@ -899,8 +901,11 @@ static int gn_launch(const void* x, int ldx, void* out, int ldo, const float* ga
       return check_launch("gn_fused");
     }
   }
-  gn_stats_kernel<T><<<dim3(chunks, B), GN_THREADS, st_smem, s>>>((const T*)x, ldx, partial, HW, C, groups, chunks, eps,
-                                                                stats, counters);
+  {
+    cudaError_t le = launch_pdl(gn_stats_kernel<T>, dim3((unsigned)chunks, (unsigned)B), dim3(GN_THREADS), st_smem, s, 1,
+                                (const T*)x, ldx, partial, HW, C, groups, chunks, eps, stats, counters);
+    if (le != cudaSuccess) { set_error("pd_group_norm: launch failed: %s", cudaGetErrorString(le)); return (int)le; }
+  }
   int rc = check_launch("gn_stats");
   if (rc) return rc;
   // apply: ~2 waves of 512-thread CTAs over (row_blocks, B)
@@ -908,8 +913,12 @@ static int gn_launch(const void* x, int ldx, void* out, int ldo, const float* ga
   int max_rb = (HW + 31) / 32;
   if (row_blocks > max_rb) row_blocks = max_rb;
   if (row_blocks < 1) row_blocks = 1;
-  gn_apply_kernel<T, TO><<<dim3(row_blocks, B), GN_THREADS, 0, s>>>(
-      (const T*)x, ldx, (TO*)out, ldo, gamma, beta, stats, HW, C, groups, act, row_blocks);
+  {
+    const float* stats_c = stats;
+    cudaError_t le = launch_pdl(gn_apply_kernel<T, TO>, dim3((unsigned)row_blocks, (unsigned)B), dim3(GN_THREADS), 0, s, 1,
+                                (const T*)x, ldx, (TO*)out, ldo, gamma, beta, stats_c, HW, C, groups, act, row_blocks);
+    if (le != cudaSuccess) { set_error("pd_group_norm: launch failed: %s", cudaGetErrorString(le)); return (int)le; }
+  }
   return check_launch("gn_apply");
 }
 

@@ -6,6 +6,8 @@ import torch
 from prompt_diffusion_b200 import ops, _lib
 dev = "cuda"
 bf = torch.bfloat16
+if os.environ.get("PD_GN_FUSED") == "0":      # A/B: statistics kernel + apply kernel (two PDL launches) instead of the cooperative kernel
+    _lib.lib.pd_debug_group_norm_fused(0)
 
 def timeit(fn, n, iters=20):
     """GPU time per call: the calls are captured into one CUDA graph (no host launch overhead in the number)."""
