@@ -64,6 +64,8 @@ struct TcArgs {
                                 // 12 = only half of every A tile's rows is fetched (multicast what-if)
                                 // (4..7, 10, 11 existed for the per-slab epilogue of commit "GEMM epilogue: 16-byte shared-space...")
   int epi_tma;                  // 1: bf16 output staged in smem and written by TMA
+  int stg_g1;                   // byte offset of epilogue group 1's staging buffers (group 0's come first; compact: a
+                                // 160-wide tile stages 40 KiB, not 64, and the ring gets the difference)
   int n_fast;                   // tile order, see PD_TILE_COORDS
   int sk;                       // 1: stream-K schedule (the (tile, k-block) space is cut evenly over the workers)
   float* sk_ws;                 // stream-K partial accumulators [worker][2 slots][CG][256 cols][128 rows] fp32
@@ -564,7 +566,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int rx = r % a.bw;
     const int ry = (r / a.bw) % a.bh;
     const int rb = r / (a.bw * a.bh);
-    unsigned char* gstg = ring + a.stages * stage_bytes + grp * 32768;   // 1024-aligned
+    unsigned char* gstg = ring + a.stages * stage_bytes + grp * a.stg_g1;   // 1024-aligned
     uint64_t* rbar = &res_full[grp * 2];
     uint32_t res_phase = 0;                // residual barriers complete once per tile that loads a residual
     const bool elected = (ew & 3) == 0 && lane == 0;
@@ -1294,7 +1296,18 @@ static int conv2d_tc_impl(const pd_conv_params* p, cudaStream_t s, TcVariant var
   a.BN = best_bn;
   a.n_tiles = (p->Cout + a.BN - 1) / a.BN;
   int stage_bytes = TC_A_BYTES + (a.BN / CGv) * TC_BK * 2;
-  const int epi_bytes = a.epi_tma ? 4 * 16384 : 0;
+  // epilogue staging, compact: group g stages the 64-column slabs g and g + 2 of the tile (the last slab may be 32 wide:
+  // 8 KiB); buffer 1 of a group sits 16 KiB behind its buffer 0
+  int epi_bytes = 0;
+  a.stg_g1 = 0;
+  if (a.epi_tma) {
+    const int n64 = a.BN >> 6, nsl = n64 + ((a.BN & 63) ? 1 : 0);
+    auto slab_bytes = [&](int sl) { return sl < n64 ? 16384 : (sl < nsl ? 8192 : 0); };
+    const int g0 = nsl > 2 ? 16384 + slab_bytes(2) : slab_bytes(0);
+    const int g1 = nsl > 3 ? 16384 + slab_bytes(3) : slab_bytes(1);
+    a.stg_g1 = g0;
+    epi_bytes = g0 + g1;
+  }
   a.stages = (TC_SMEM_BUDGET - epi_bytes) / stage_bytes;
   a.b_res = 0;
   int res_bytes = 0;
