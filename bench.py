@@ -252,6 +252,38 @@ def workload_config(args, where):
             "l2": "no flush: per-step working set (2.4 GB bf16 weights + activations) >> 126 MB L2"}
 
 
+def diffusers_loop_leg(model, cfg, base, B, size, scale, dev, n_steps=8):
+    """CONTEXT: the same workload through the diffusers-style ``PromptDiffusionPipeline`` (reference
+    pipeline_prompt_diffusion.py:1195-1290) built over this model's nets — the fused, graph-replayed step — and, for
+    comparison, its call-by-call route (controlnet(...) -> unet(...) -> scheduler.step(...)): ms per denoise step."""
+    from prompt_diffusion_b200 import PromptDiffusionPipeline
+    from prompt_diffusion_b200.pipeline_prompt_diffusion import set_fused_step
+    inp = {k: v.to(dev) for k, v in base.items()}
+    pipe = PromptDiffusionPipeline.from_ldm(model)
+    out = {"workload": f"{size}x{size}, batch {B}, CFG {scale}, {n_steps}-step DDIMScheduler loop"}
+    for name, fused in (("fused_ms_per_denoise_step", True), ("call_by_call_ms_per_denoise_step", False)):
+        marks = []
+
+        def cb(i, t, latents):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
+
+        prev = set_fused_step(fused)
+        try:
+            for _ in range(2):                   # first call builds the step graph / warms the buffers
+                marks.clear()
+                pipe(prompt_embeds=inp["c_crossattn"], negative_prompt_embeds=inp["uc_crossattn"], image=inp["query"],
+                     image_pair=inp["example_pair"], num_inference_steps=n_steps, guidance_scale=scale,
+                     latents=inp["x_T"], output_type="latent", callback=cb)
+        finally:
+            set_fused_step(prev)
+        torch.cuda.synchronize()
+        per = [marks[i].elapsed_time(marks[i + 1]) for i in range(1, len(marks) - 1)]
+        out[name] = sorted(per)[len(per) // 2]
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -423,6 +455,10 @@ def main():
                 extra["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             torch.cuda.empty_cache()
         if not args.no_config4:
+            try:
+                extra["diffusers_loop"] = diffusers_loop_leg(model, cfg, base, B, size, args.scale, dev)
+            except Exception as e:
+                extra["diffusers_loop"] = {"error": f"{type(e).__name__}: {e}"[:300]}
             try:
                 extra["config4"] = config4_leg(model, sampler, cfg, 16, 768, args.scale, dev)
             except Exception as e:

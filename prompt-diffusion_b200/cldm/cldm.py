@@ -625,16 +625,22 @@ class ControlLDM:
     """Drop-in for the sampler-facing surface of the reference's ``ControlLDM`` (cldm/cldm.py:328-382 on
     top of ldm/models/diffusion/ddpm.py:138-178 schedule buffers)."""
 
-    def __init__(self, cfg: CLDMConfig = CLDM_V15, mode: str = "bf16", device="cuda", only_mid_control=False):
+    def __init__(self, cfg: CLDMConfig = CLDM_V15, mode: str = "bf16", device="cuda", only_mid_control=False,
+                 _nets=None):
         self.cfg, self.mode = cfg, mode
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("prompt_diffusion_b200.ControlLDM runs on CUDA only (no CPU fallback)")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        pool = _Pool(self.device)
-        self.control_model = ControlNet(cfg, mode, self.device, pool)
-        self.model = SimpleNamespace(diffusion_model=ControlledUnetModel(cfg, mode, self.device, pool))
+        if _nets is None:
+            pool = _Pool(self.device)
+            self.control_model = ControlNet(cfg, mode, self.device, pool)
+            self.model = SimpleNamespace(diffusion_model=ControlledUnetModel(cfg, mode, self.device, pool))
+        else:
+            unet, self.control_model = _nets
+            self.model = SimpleNamespace(diffusion_model=unet)
+            pool = unet.pool
         self.pool = pool
         self.only_mid_control = only_mid_control
         self.control_scales = [1.0] * 13
@@ -646,6 +652,15 @@ class ControlLDM:
         self.first_stage_model = None       # AutoencoderKLDecoder once first_stage_model.* weights are loaded
         self.cond_stage_model = None        # FrozenCLIPTextEncoder once cond_stage_model.transformer.* weights are loaded
         self._register_schedule()
+
+    @classmethod
+    def from_nets(cls, unet: "ControlledUnetModel", control_model: "ControlNet", only_mid_control=False) -> "ControlLDM":
+        """The fused ``apply_model`` over two EXISTING nets (no weights are copied).  They must live in one buffer pool
+        — the ControlNet's zero-conv epilogues add onto the UNet's stored skips in place — i.e. come from one
+        ``ControlLDM`` or have been built with the same ``pool=``."""
+        if unet.pool is not control_model.pool or unet.mode != control_model.mode or unet.device != control_model.device:
+            raise ValueError("from_nets: the two nets must share one buffer pool, mode and device")
+        return cls(unet.cfg, unet.mode, unet.device, only_mid_control, _nets=(unet, control_model))
 
     # ddpm.py:138-158 (the buffers DDIMSampler.make_schedule reads)
     def _register_schedule(self):

@@ -146,7 +146,9 @@ class DDIMSampler(object):
             alphas = self.model.alphas_cumprod
             alphas_prev = self.model.alphas_cumprod_prev
             s1m = self.model.sqrt_one_minus_alphas_cumprod
-            sigmas = self.ddim_sigmas_for_original_num_steps
+            # mirrored as written (:209): the reference reads this table from the MODEL — it only exists on the sampler,
+            # so a model that does not provide it raises AttributeError here exactly like the reference does
+            sigmas = self.model.ddim_sigmas_for_original_num_steps
         else:
             alphas, alphas_prev = self.ddim_alphas, self.ddim_alphas_prev
             s1m, sigmas = self.ddim_sqrt_one_minus_alphas, self.ddim_sigmas

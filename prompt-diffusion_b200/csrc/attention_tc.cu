@@ -33,6 +33,9 @@ constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or a
 #ifndef FA_ORDERED
 #define FA_ORDERED 0
 #endif
+#ifndef FA_SWP
+#define FA_SWP 0           // > 0: exponential section software-pipelined by hand, MUFU.EX2 issued FA_SWP groups of four ahead of their consumers; measured (profiles/r02_attn_swp_variants.txt, B16 h8 N4096 d40): 0 -> 761 us, 1..4 -> 776 us: the consumer stall behind each MUFU pair is NOT what holds the section at 61 % of the SFU bound
+#endif
 #ifndef FA_POLY
 #define FA_POLY 0          // of every 8 element pairs, how many take the FMA-pipe exp2 (0..8); measured: 2 -> 792 us vs 0 -> 763 us (B16 h8 N4096 d40): the section is issue-bound, not SFU-bound
 #endif
@@ -303,6 +306,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       auto exp_tile = [&]() {
         const float nm = -m_ref;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#if FA_SWP
+        // Software pipeline over groups of four scores, in place on the S registers: the MUFU.EX2 of group g + FA_SWP are
+        // issued between the FADD2 / F2FP that consume group g and the FFMA2 of group g + FA_SWP + 1.  In the plain loop
+        // below ptxas puts every FADD2 / F2FP right behind its own two MUFU.EX2, so the in-order warp idles for the SFU
+        // latency once per pair (one warp alone: 16 clk per element against the SFU's 8).
+        constexpr int D = FA_SWP;
+        auto X = [&](int g) { ffma2_b32_v(s[4 * g], s[4 * g + 1], sc, nm); ffma2_b32_v(s[4 * g + 2], s[4 * g + 3], sc, nm); };
+#pragma unroll
+        for (int g = 0; g <= D; ++g) X(g);
+#pragma unroll
+        for (int g = 0; g < D; ++g) {
+          ex2_b32_v(s[4 * g]); ex2_b32_v(s[4 * g + 1]); ex2_b32_v(s[4 * g + 2]); ex2_b32_v(s[4 * g + 3]);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int g = 0; g < 32; ++g) {
+          const int e = g + D;                       // group whose exponentials are issued in this round
+          if (e < 32) ex2_b32_v(s[4 * e]);
+          fadd2_b32_v(l0, l1, s[4 * g], s[4 * g + 1]);
+          if (e < 32) ex2_b32_v(s[4 * e + 1]);
+          pk[(2 * g) & 15] = pack_bf16x2_b32_v(s[4 * g], s[4 * g + 1]);
+          if (e < 32) ex2_b32_v(s[4 * e + 2]);
+          fadd2_b32_v(l2, l3, s[4 * g + 2], s[4 * g + 3]);
+          if (e < 32) ex2_b32_v(s[4 * e + 3]);
+          pk[(2 * g + 1) & 15] = pack_bf16x2_b32_v(s[4 * g + 2], s[4 * g + 3]);
+          if (e + 1 < 32) X(e + 1);
+          if ((g & 7) == 7) tmem_st16p(tmem_p + (uint32_t)((g >> 3) * 16), pk);
+        }
+        lt = (l0 + l1) + (l2 + l3);
+        return;
+#endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];

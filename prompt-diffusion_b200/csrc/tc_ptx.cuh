@@ -257,6 +257,13 @@ __device__ __forceinline__ void ffma2_b32(uint32_t& x0, uint32_t& x1, float a, f
       "mov.b64 {%0, %1}, rx;\n\t}"
       : "+r"(x0), "+r"(x1) : "f"(a), "f"(c));
 }
+__device__ __forceinline__ void ffma2_b32_v(uint32_t& x0, uint32_t& x1, float a, float c) {
+  asm volatile("{\n\t.reg .b64 rx, ra, rc;\n\t"
+               "mov.b64 rx, {%0, %1};\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rc, {%3, %3};\n\t"
+               "fma.rn.f32x2 rx, rx, ra, rc;\n\t"
+               "mov.b64 {%0, %1}, rx;\n\t}"
+               : "+r"(x0), "+r"(x1) : "f"(a), "f"(c));
+}
 __device__ __forceinline__ void ex2_b32_v(uint32_t& x) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(x)); }
 __device__ __forceinline__ void fadd2_b32_v(float& l0, float& l1, uint32_t x0, uint32_t x1) {
   asm volatile("{\n\t.reg .b64 rl, rx;\n\t"

@@ -30,6 +30,21 @@ from .cldm.cldm import ControlledUnetModel
 from .promptdiffusioncontrolnet import PromptDiffusionControlNetModel
 
 
+_FUSED_STEP = True
+
+
+def fused_step_enabled() -> bool:
+    return _FUSED_STEP
+
+
+def set_fused_step(on: bool) -> bool:
+    """Switch the pipeline's fused step (taken when both shims share a buffer pool) on/off; off = the call-by-call
+    route through ``controlnet(...)`` / ``unet(...)`` / ``scheduler.step(...)``.  Returns the previous setting."""
+    global _FUSED_STEP
+    prev, _FUSED_STEP = _FUSED_STEP, bool(on)
+    return prev
+
+
 class DDIMScheduler:
     """Restatement of ``diffusers.DDIMScheduler`` for epsilon prediction (see the module docstring)."""
 
@@ -119,6 +134,58 @@ class PromptDiffusionPipeline:
         self.vae = vae                       # optional AutoencoderKLDecoder (output_type="pt")
         self.vae_scale_factor = vae_scale_factor
         self.device = self.unet.device
+        # Both shims over nets of ONE buffer pool (``from_ldm``, or nets built with the same ``pool=``): the loop runs the
+        # fused step of the ldm path — zero-conv epilogues adding onto the UNet's skips in place, no NCHW round trips of the
+        # 13 residuals, CFG + scheduler step in one kernel, the whole step replayed as a CUDA graph.
+        self._fused = self._sampler = None
+        u, c = self.unet.unet, self.controlnet.net
+        if u.pool is c.pool and u.mode == c.mode and isinstance(self.scheduler, DDIMScheduler):
+            from .cldm.cldm import ControlLDM
+            from .cldm.ddim_hacked import DDIMSampler
+            self._fused = ControlLDM.from_nets(u, c)
+            self._sampler = DDIMSampler(self._fused)
+
+    @classmethod
+    def from_ldm(cls, model, scheduler: Optional[DDIMScheduler] = None, vae=None) -> "PromptDiffusionPipeline":
+        """Pipeline over the two nets of a loaded ``ControlLDM`` (shared weights and buffer pool -> fused step)."""
+        cn = PromptDiffusionControlNetModel(model.cfg, model.mode, model.device, net=model.control_model)
+        return cls(model.model.diffusion_model, cn, scheduler, vae if vae is not None else model.first_stage_model)
+
+    def _fused_loop(self, latents, embeds, image, image_pair, do_cfg, guidance_scale, eta, generator, keep,
+                    controlnet_conditioning_scale, callback_on_step_end, callback, callback_steps):
+        """Steps 8 of ``__call__`` (:1209-1290) for the plain case (no guess_mode): per step ONE graph replay of
+        controlnet -> unet -> ``e_u + s (e_c - e_u)`` -> ``DDIMScheduler.step`` (cldm/ddim_hacked.py's fused step, fed
+        with this scheduler's coefficients)."""
+        sch, dev, B = self.scheduler, self.device, latents.shape[0]
+        ts = [int(v) for v in sch.timesteps.cpu()]
+        rows = []
+        for t in ts:                                                                    # DDIMScheduler.step, per timestep
+            prev_t = t - sch.num_train_timesteps // sch.num_inference_steps
+            a_t = float(sch.alphas_cumprod[t])
+            a_prev = float(sch.alphas_cumprod[prev_t]) if prev_t >= 0 else float(sch.final_alpha_cumprod)
+            std = eta * ((1.0 - a_prev) / (1.0 - a_t) * (1.0 - a_t / a_prev)) ** 0.5
+            rows.append([a_t, a_prev, std, (1.0 - a_t) ** 0.5, guidance_scale if do_cfg else 1.0, 1.0])
+        coef = torch.tensor(rows, dtype=torch.float32).to(dev)
+        conds = {"c_crossattn": [embeds], "example_pair": [image_pair], "query": [image]}
+        old_scales = list(self._fused.control_scales)
+        try:
+            for i, t in enumerate(ts):
+                self._fused.control_scales = [controlnet_conditioning_scale * keep[i]] * 13
+                noise = None
+                if eta > 0:
+                    noise = torch.randn(latents.shape, generator=generator, device=latents.device, dtype=latents.dtype)
+                t_vec = torch.full((B,), t, device=dev, dtype=torch.int64)
+                latents, _ = self._sampler._plain_step(latents, t_vec, conds, conds if do_cfg else None, do_cfg,
+                                                       coef[i], noise)
+                if callback_on_step_end is not None:
+                    outs = callback_on_step_end(self, i, sch.timesteps[i], {"latents": latents})
+                    if isinstance(outs, dict):
+                        latents = outs.pop("latents", latents)
+                if callback is not None and i % callback_steps == 0:
+                    callback(i, sch.timesteps[i], latents)
+        finally:
+            self._fused.control_scales = old_scales
+        return latents
 
     @torch.no_grad()
     def __call__(self, prompt_embeds: torch.Tensor, image: torch.Tensor, image_pair: torch.Tensor,
@@ -138,8 +205,9 @@ class PromptDiffusionPipeline:
         B = prompt_embeds.shape[0]
         H, W = image.shape[-2:]
         image, image_pair = image.to(dev, torch.float32), image_pair.to(dev, torch.float32)
-        if do_cfg and not guess_mode:                                                   # prepare_image :808-810
-            image, image_pair = torch.cat([image] * 2), torch.cat([image_pair] * 2)
+        fused = self._fused is not None and not guess_mode and fused_step_enabled()
+        if do_cfg and not guess_mode and not fused:                                     # prepare_image :808-810
+            image, image_pair = torch.cat([image] * 2), torch.cat([image_pair] * 2)     # (fused: B hints, tiled by the net)
         embeds = prompt_embeds.to(dev, torch.float32)
         if do_cfg:
             embeds = torch.cat([negative_prompt_embeds.to(dev, torch.float32), embeds])  # [uncond, cond] :1079-1080
@@ -151,6 +219,10 @@ class PromptDiffusionPipeline:
         latents = latents.to(dev, torch.float32) * self.scheduler.init_noise_sigma      # prepare_latents :690-709
         keep = [1.0 - float(i / len(timesteps) < control_guidance_start or (i + 1) / len(timesteps) > control_guidance_end)
                 for i in range(len(timesteps))]                                         # :1196-1202
+        if fused:
+            latents = self._fused_loop(latents, embeds, image, image_pair, do_cfg, guidance_scale, eta, generator, keep,
+                                       controlnet_conditioning_scale, callback_on_step_end, callback, callback_steps)
+            timesteps = []
         for i, t in enumerate(timesteps):
             x_in = torch.cat([latents] * 2) if do_cfg else latents                      # :1220-1221
             x_in = self.scheduler.scale_model_input(x_in, t)

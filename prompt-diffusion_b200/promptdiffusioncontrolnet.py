@@ -121,9 +121,19 @@ def ldm_key_to_diffusers(key: str, layers_per_block: int = 2) -> Optional[str]:
 
 class PromptDiffusionControlNetModel:
     def __init__(self, cfg: CLDMConfig = CLDM_V15, mode: str = "bf16", device="cuda",
-                 controlnet_conditioning_channel_order: str = "rgb", global_pool_conditions: bool = False):
-        self.net = ControlNet(cfg, mode, device)
+                 controlnet_conditioning_channel_order: str = "rgb", global_pool_conditions: bool = False,
+                 class_embed_type: Optional[str] = None, num_class_embeds: Optional[int] = None,
+                 addition_embed_type: Optional[str] = None, net: Optional[ControlNet] = None):
+        """``net``: wrap an existing ``cldm.ControlNet`` (e.g. ``ControlLDM.control_model``) instead of building one —
+        the pipeline then runs the fused step over the shared buffer pool."""
+        if class_embed_type is not None or num_class_embeds is not None or addition_embed_type is not None:
+            raise NotImplementedError("class / additional embeddings (promptdiffusioncontrolnet.py:288-320) are not "
+                                      "part of the SD1.5 prompt-diffusion configuration")
+        self.net = net if net is not None else ControlNet(cfg, mode, device)
         self.config = type("Config", (), {})()
+        self.config.class_embed_type, self.config.num_class_embeds = class_embed_type, num_class_embeds
+        self.config.addition_embed_type = addition_embed_type
+        self.class_embedding = None
         self.config.controlnet_conditioning_channel_order = controlnet_conditioning_channel_order
         self.config.global_pool_conditions = global_pool_conditions
         self.config.in_channels = cfg.in_channels
@@ -167,12 +177,18 @@ class PromptDiffusionControlNetModel:
             controlnet_cond = torch.flip(controlnet_cond, dims=[1])
         elif order != "rgb":
             raise ValueError(f"unknown `controlnet_conditioning_channel_order`: {order}")
-        for name, val in (("class_labels", class_labels), ("timestep_cond", timestep_cond),
-                          ("attention_mask", attention_mask), ("added_cond_kwargs", added_cond_kwargs),
+        # `class_labels` and `added_cond_kwargs` are read only behind `self.class_embedding is not None` /
+        # `config.addition_embed_type is not None` (:288-320): the SD1.5 prompt-diffusion config has neither, so the
+        # reference accepts and ignores them — mirrored.  (A config that asks for those embeddings is refused by the
+        # constructor.)  The rest feeds arithmetic this path does not have:
+        #   timestep_cond          -> TimestepEmbedding.cond_proj (None without `time_cond_proj_dim`: the reference fails);
+        #   attention_mask         -> a [B, 1, keys] bias on every SELF-attention (:257-259), which cannot broadcast over
+        #                             the 4096 / 1024 / 256 / 64-token levels of this UNet and is never passed by the
+        #                             pipeline (pipeline_prompt_diffusion.py:1237-1246);
+        #   cross_attention_kwargs -> attention processors (LoRA scale), not part of this model.
+        for name, val in (("timestep_cond", timestep_cond), ("attention_mask", attention_mask),
                           ("cross_attention_kwargs", cross_attention_kwargs)):
             if val is not None:
-                # the SD1.5 prompt-diffusion config has no class / additional embeddings and the pipeline never
-                # passes a mask (pipeline_prompt_diffusion.py:1237-1246)
                 raise NotImplementedError(f"{name} is not part of the SD1.5 prompt-diffusion path")
 
         # 1. time (promptdiffusioncontrolnet.py:262-276)

@@ -80,3 +80,88 @@ def test_diffusers_style_loop_equals_ldm_sampler(cfg, state_dict_cpu):
               image_pair=inp["example_pair"], num_inference_steps=3, guidance_scale=scale, latents=inp["x_T"],
               guess_mode=True, control_guidance_end=0.5)
     assert z2.shape == ref.shape and bool(torch.isfinite(z2).all()) and rel_l2(z2.cpu(), ref.cpu()) > 1e-3
+
+
+def test_diffusers_forward_optional_arguments(cfg, state_dict_cpu):
+    """promptdiffusioncontrolnet.py:188-203, :288-320: without a class embedding / `addition_embed_type` (the SD1.5
+    config) the reference accepts `class_labels` and `added_cond_kwargs` and ignores them; a python-number, 0-d and
+    1-d `timestep` give the same result (:262-276); `return_dict=False` returns the (down, mid) tuple (:386-391)."""
+    from prompt_diffusion_b200 import PromptDiffusionControlNetModel
+    from prompt_diffusion_b200.synth import synthetic_inputs
+    torch.set_grad_enabled(False)
+    cn = PromptDiffusionControlNetModel(cfg, mode="bf16", device=DEV).load_state_dict(state_dict_cpu)
+    inp = synthetic_inputs(cfg, 2, 64, 64, seed=8, device=DEV)
+    args = (inp["x_T"], 481, inp["c_crossattn"], inp["example_pair"], inp["query"])
+    base = cn(*args)
+    assert len(base.down_block_res_samples) == 12 and base.mid_block_res_sample.shape == (2, 1280, 1, 1)
+    extra = cn(*args, class_labels=torch.zeros(2, dtype=torch.long, device=DEV),
+               added_cond_kwargs={"text_embeds": torch.zeros(2, 1280, device=DEV)})
+    down, mid = cn(inp["x_T"], torch.tensor(481, device=DEV), *args[2:], return_dict=False)
+    vec = cn(inp["x_T"], torch.tensor([481, 481], device=DEV), *args[2:], conditioning_scale=0.5)
+    for a, b, c, d in zip(list(base.down_block_res_samples) + [base.mid_block_res_sample],
+                          list(extra.down_block_res_samples) + [extra.mid_block_res_sample], list(down) + [mid],
+                          list(vec.down_block_res_samples) + [vec.mid_block_res_sample]):
+        assert torch.equal(a, b) and torch.equal(a, c)
+        assert torch.allclose(a * 0.5, d, rtol=1e-2, atol=1e-6)
+    for kw in ({"attention_mask": torch.ones(2, 64, device=DEV)}, {"timestep_cond": torch.zeros(2, 8, device=DEV)},
+               {"cross_attention_kwargs": {"scale": 0.5}}):
+        with pytest.raises(NotImplementedError):
+            cn(*args, **kw)
+    with pytest.raises(NotImplementedError):
+        PromptDiffusionControlNetModel(cfg, device=DEV, addition_embed_type="text_time")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_diffusers_loop_fused_step_equals_call_by_call_route(cfg, state_dict_cpu, mode):
+    """``PromptDiffusionPipeline.from_ldm`` (both shims over ONE buffer pool) runs the fused, graph-replayed step; it
+    must land on the latents of the call-by-call route (controlnet(...) -> unet(...) -> scheduler.step(...)) of the
+    same pipeline and on ``DDIMSampler.sample`` — also with ``control_guidance_end`` (two control scales), ``eta`` > 0
+    (same generator stream), without CFG, and with both callbacks."""
+    from prompt_diffusion_b200 import ControlLDM, DDIMSampler, PromptDiffusionPipeline, _lib
+    from prompt_diffusion_b200.pipeline_prompt_diffusion import set_fused_step
+    from prompt_diffusion_b200.synth import make_conds, synthetic_inputs
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_grad_enabled(False)
+    tol = 1e-5 if mode == "fp32" else 5e-2
+    model = ControlLDM(cfg, mode=mode, device=DEV).load_state_dict(state_dict_cpu)
+    inp = synthetic_inputs(cfg, 2, 64, 64, seed=8, device=DEV)
+    cond, un = make_conds(inp)
+    pipe = PromptDiffusionPipeline.from_ldm(model)
+    assert pipe._fused is not None and pipe._fused.control_model is model.control_model
+
+    def run(fused, **kw):
+        prev = set_fused_step(fused)
+        try:
+            g = torch.Generator(device=DEV).manual_seed(5)
+            return pipe(prompt_embeds=inp["c_crossattn"], negative_prompt_embeds=inp["uc_crossattn"], image=inp["query"],
+                        image_pair=inp["example_pair"], latents=inp["x_T"], output_type="latent", generator=g, **kw)
+        finally:
+            set_fused_step(prev)
+
+    S, scale = 5, 7.5
+    ref, _ = DDIMSampler(model).sample(S, 2, (4, 8, 8), cond, verbose=False, eta=0.0, x_T=inp["x_T"],
+                                       unconditional_guidance_scale=scale, unconditional_conditioning=un)
+    seen, seen_end = [], []
+    n0 = _lib.launch_count()
+    zf = run(True, num_inference_steps=S, guidance_scale=scale, callback=lambda i, t, l: seen.append(int(t)),
+             callback_on_step_end=lambda p, i, t, kw: seen_end.append(i) or {"latents": kw["latents"]})
+    n_fused = _lib.launch_count() - n0
+    zc = run(False, num_inference_steps=S, guidance_scale=scale)
+    n_calls = _lib.launch_count() - n0 - n_fused
+    e_ref, e_route = rel_l2(zf.cpu(), ref.cpu()), rel_l2(zf.cpu(), zc.cpu())
+    print(f"[parity] diffusers loop fused step {mode}: vs DDIMSampler.sample {e_ref:.3e}, vs call-by-call route {e_route:.3e}; "
+          f"library launches {n_fused} fused vs {n_calls} call-by-call")
+    assert seen == [int(t) for t in pipe.scheduler.timesteps] and seen_end == list(range(S))
+    # same kernels, same graph; the coefficient rows differ in the last fp32 bit (float64 vs float32 square roots), which
+    # bf16 mode amplifies through the rounding of the latent in front of conv_in (measured 4.2e-3 after 5 steps)
+    assert e_ref <= (1e-5 if mode == "fp32" else 2e-2)
+    assert e_route <= tol
+    assert n_fused > S * 100
+    for kw in ({"control_guidance_end": 0.5, "controlnet_conditioning_scale": 0.7}, {"eta": 0.6}, {"guidance_scale": 1.0}):
+        a = run(True, num_inference_steps=4, **{"guidance_scale": scale, **kw})
+        b = run(False, num_inference_steps=4, **{"guidance_scale": scale, **kw})
+        err = rel_l2(a.cpu(), b.cpu())
+        print(f"[parity] diffusers loop fused vs call-by-call {mode} {kw}: {err:.3e}")
+        assert err <= tol
+    assert model.control_scales == [1.0] * 13 and pipe._fused.control_scales == [1.0] * 13
