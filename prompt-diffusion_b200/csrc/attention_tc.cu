@@ -33,8 +33,37 @@ constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or a
 #ifndef FA_ORDERED
 #define FA_ORDERED 0
 #endif
+#ifndef FA_ELECT
+#define FA_ELECT 1         // 1: the MMA warp runs its loop warp-uniformly and one ELECTED lane issues (plain predicated UTCHMMA instead of the ELECT ... BRA.U.ANY retry loop ptxas emits inside `if (lane == 0)`)
+#endif
+#if FA_ELECT
+#define FA_ISSUE if (elect_one())
+#define FA_SYNCW __syncwarp()
+#define FA_LANE0 (lane == 0)
+#else
+#define FA_ISSUE
+#define FA_SYNCW
+#define FA_LANE0 true
+#endif
+#ifndef FA_PARK
+#define FA_PARK 0          // 1: the TMA and MMA warps wait on their mbarriers with a suspend-time hint (parked by the hardware)
+#endif
+#if FA_PARK
+#define FA_ROLE_WAIT mbar_wait_parked
+#else
+#define FA_ROLE_WAIT mbar_wait
+#endif
+#ifndef FA_HANDOFF
+#define FA_HANDOFF 31      // (FA_PINGPONG with FA_SWP) group of four whose exponentials are the last ones before the SFU turn passes to the other query group
+#endif
+#ifndef FA_SPLIT
+#define FA_SPLIT 0         // > 0 (with FA_SWP): a never-taken branch every FA_SPLIT groups of the pipelined exponential section
+#endif
+#ifndef FA_PINGPONG
+#define FA_PINGPONG 1      // 1: the two query groups take strict turns in the exponential section (FlashAttention-3 style named barriers)
+#endif
 #ifndef FA_SWP
-#define FA_SWP 0           // > 0: exponential section software-pipelined by hand, MUFU.EX2 issued FA_SWP groups of four ahead of their consumers; measured (profiles/r02_attn_swp_variants.txt, B16 h8 N4096 d40): 0 -> 761 us, 1..4 -> 776 us: the consumer stall behind each MUFU pair is NOT what holds the section at 61 % of the SFU bound
+#define FA_SWP 2           // > 0: exponential section software-pipelined by hand, MUFU.EX2 issued FA_SWP groups of four ahead of their consumers; measured (profiles/r02_attn_swp_variants.txt, B16 h8 N4096 d40): 0 -> 761 us, 1..4 -> 776 us: the consumer stall behind each MUFU pair is NOT what holds the section at 61 % of the SFU bound
 #endif
 #ifndef FA_POLY
 #define FA_POLY 0          // of every 8 element pairs, how many take the FMA-pipe exp2 (0..8); measured: 2 -> 792 us vs 0 -> 763 us (B16 h8 N4096 d40): the section is issue-bound, not SFU-bound
@@ -78,6 +107,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                     const FaArgs a) {
   constexpr bool ALIAS = KP16 > 4;
+  constexpr bool SWP_ON = FA_SWP > 0 && !ALIAS;      // the hand-pipelined exponential section (d <= 64 instantiations only)
   constexpr int ND = (KP16 + 3) / 4;
   constexpr int KPAD = KP16 * 16;
   static_assert(NG == 2 || (NG == 1 && KP16 > 8 && KP16 <= 12), "one query group only for 128 < d <= 192");
@@ -138,11 +168,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           tma_load_4d(q_s + (g * ND + c) * FA_TILE_BYTES, &map_q, &q_full, c * 64, h, q0 + g * FA_BQ, b);
       int st = 0; uint32_t ph = 0;
       for (int j = 0; j < a.ntiles; ++j) {
-        mbar_wait(&k_empty[st], ph ^ 1u, 100 + st);
+        FA_ROLE_WAIT(&k_empty[st], ph ^ 1u, 100 + st);
         mbar_expect_tx(&k_full[st], ND * FA_TILE_BYTES);
         for (int c = 0; c < ND; ++c)
           tma_load_4d(k_s + (st * ND + c) * FA_TILE_BYTES, &map_k, &k_full[st], c * 64, h, j * FA_BK, b);
-        mbar_wait(&v_empty[st], ph ^ 1u, 110 + st);
+        FA_ROLE_WAIT(&v_empty[st], ph ^ 1u, 110 + st);
         mbar_expect_tx(&v_full[st], ND * FA_TILE_BYTES);
         for (int c = 0; c < ND; ++c)
           tma_load_4d(v_s + (st * ND + c) * FA_TILE_BYTES, &map_v, &v_full[st], c * 64, h, j * FA_BK, b);
@@ -156,7 +186,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     // d40 (profiles/r02_attn_mma_modes.txt) 762 us as written, 788 us with elect.sync issue, 877 us with elect.sync
     // and the two groups' Q K^T / P V streams interleaved (both groups then exponentiate at the same time and wait at
     // the same time).
-    if (lane == 0) {
+    if (FA_ELECT || lane == 0) {
       // descriptors: only the 14-bit start-address field changes between tiles, so every MMA operand is
       // base + a compile-time or per-stage constant in the low word
       const uint64_t qdesc0 = make_smem_desc(s_u32(q_s));
@@ -188,13 +218,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             umma_bf16_ts(oa, pa + (uint32_t)(8 * k), vd + (uint64_t)(k * 128), a.idesc_pv, (k != 0 || !first) ? 1u : 0u);
         }
       };
-      mbar_wait(&q_full, 0, 200);
-      mbar_wait(&k_full[0], 0, 300);
+      FA_ROLE_WAIT(&q_full, 0, 200);
+      FA_ROLE_WAIT(&k_full[0], 0, 300);
       tc_fence_after();
-      FA_DBG(0, 0);
+      if (FA_LANE0) FA_DBG(0, 0);
       const uint32_t id0 = a.ntiles == 1 ? a.idesc_s_last : a.idesc_s_full;
-      for (int g = 0; g < NG; ++g) issue_qk(g, 0, id0);
-      umma_commit(&k_empty[0]);
+      FA_ISSUE {
+        for (int g = 0; g < NG; ++g) issue_qk(g, 0, id0);
+        umma_commit(&k_empty[0]);
+      }
+      FA_SYNCW;
       int st = 0; uint32_t ph = 0;          // ring position of tile j
       for (int j = 0; j < a.ntiles; ++j) {
         int stn = st + 1; uint32_t phn = ph;
@@ -203,40 +236,49 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         const uint32_t idn = (j + 2 == a.ntiles) ? a.idesc_s_last : a.idesc_s_full;
         if constexpr (!ALIAS) {
           if (more) {
-            mbar_wait(&k_full[stn], phn, 300 + stn);
+            FA_ROLE_WAIT(&k_full[stn], phn, 300 + stn);
             for (int g = 0; g < NG; ++g) {
-              mbar_wait(&s_free[g], (uint32_t)j & 1u, 450 + g);
+              FA_ROLE_WAIT(&s_free[g], (uint32_t)j & 1u, 450 + g);
               tc_fence_after();
-              issue_qk(g, stn, idn);
-              if (g == 0) FA_DBG(0, j + 1);
+              FA_ISSUE {
+                issue_qk(g, stn, idn);
+                if (g == NG - 1) umma_commit(&k_empty[stn]);
+              }
+              FA_SYNCW;
+              if (g == 0 && FA_LANE0) FA_DBG(0, j + 1);
             }
-            umma_commit(&k_empty[stn]);
           }
-          mbar_wait(&v_full[st], ph, 310 + st);
+          FA_ROLE_WAIT(&v_full[st], ph, 310 + st);
           for (int g = 0; g < NG; ++g) {
-            mbar_wait(&p_full[g], (uint32_t)j & 1u, 400 + g);
+            FA_ROLE_WAIT(&p_full[g], (uint32_t)j & 1u, 400 + g);
             tc_fence_after();
-            if (g == 0) FA_DBG(1, j);
-            issue_pv(g, st, j == 0, last);
-            umma_commit(last ? &o_final[g] : &p_free[g]);
+            if (g == 0 && FA_LANE0) FA_DBG(1, j);
+            FA_ISSUE {
+              issue_pv(g, st, j == 0, last);
+              umma_commit(last ? &o_final[g] : &p_free[g]);
+              if (g == NG - 1) umma_commit(&v_empty[st]);
+            }
+            FA_SYNCW;
           }
-          umma_commit(&v_empty[st]);
         } else {
-          mbar_wait(&v_full[st], ph, 310 + st);
-          if (more) mbar_wait(&k_full[stn], phn, 300 + stn);
+          FA_ROLE_WAIT(&v_full[st], ph, 310 + st);
+          if (more) FA_ROLE_WAIT(&k_full[stn], phn, 300 + stn);
           for (int g = 0; g < NG; ++g) {
-            mbar_wait(&p_full[g], (uint32_t)j & 1u, 400 + g);
+            FA_ROLE_WAIT(&p_full[g], (uint32_t)j & 1u, 400 + g);
             tc_fence_after();
-            if (g == 0) FA_DBG(1, j);
-            issue_pv(g, st, j == 0, last);
-            if (g == NG - 1) umma_commit(&v_empty[st]);
-            if (more) {
-              issue_qk(g, stn, idn);
-              if (g == NG - 1) umma_commit(&k_empty[stn]);
-              if (g == 0) FA_DBG(0, j + 1);
-            } else {
-              umma_commit(&o_final[g]);
+            if (g == 0 && FA_LANE0) FA_DBG(1, j);
+            FA_ISSUE {
+              issue_pv(g, st, j == 0, last);
+              if (g == NG - 1) umma_commit(&v_empty[st]);
+              if (more) {
+                issue_qk(g, stn, idn);
+                if (g == NG - 1) umma_commit(&k_empty[stn]);
+              } else {
+                umma_commit(&o_final[g]);
+              }
             }
+            FA_SYNCW;
+            if (more && g == 0 && FA_LANE0) FA_DBG(0, j + 1);
           }
         }
         st = stn; ph = phn;
@@ -255,26 +297,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const int dslot = 2 + 4 * g;
     const float sc = a.scale_log2;
     float m_ref = -INFINITY, l_run = 0.f;
+#if FA_PINGPONG
+    if constexpr (NG == 2) { if (g == 1) asm volatile("bar.arrive %0, 256;" ::"r"(3) : "memory"); }   // group A goes first
+#endif
     for (int j = 0; j < a.ntiles; ++j) {
       const bool last = j == a.ntiles - 1;
       mbar_wait(&s_full[g], (uint32_t)j & 1u, 500 + g);
       tc_fence_after();
       if (dbg) FA_DBG(dslot, j);
       uint32_t s[128];
+      auto load_s = [&]() {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32p(tmem_s + (uint32_t)(c * 32), s + c * 32);
-      tmem_ld_wait();
-      if constexpr (!ALIAS) {
+        for (int c = 0; c < 4; ++c) tmem_ld32p(tmem_s + (uint32_t)(c * 32), s + c * 32);
+        tmem_ld_wait();
+        if (last && a.n_last_valid < FA_BK) {
+          const int nv = a.n_last_valid;
+#pragma unroll
+          for (int e = 0; e < 128; ++e)
+            if (e >= nv) s[e] = 0xff800000u;         // -inf: keys past Nk (stale / zero-filled columns)
+        }
+      };
+      auto release_s = [&]() {                       // S_g may be overwritten by Q K^T of the next tile
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[g]);    // S_g may be overwritten by Q K^T of the next tile
-      }
-      if (last && a.n_last_valid < FA_BK) {
-        const int nv = a.n_last_valid;
-#pragma unroll
-        for (int e = 0; e < 128; ++e)
-          if (e >= nv) s[e] = 0xff800000u;         // -inf: keys past Nk (stale / zero-filled columns)
-      }
+        if (lane == 0) mbar_arrive(&s_free[g]);
+      };
+      load_s();
+      if constexpr (!ALIAS) release_s();
       // ---- reference for the exponentials ------------------------------------------------------------------------
       // P is bf16 and l / O accumulate in fp32, all with 8 exponent bits, so the reference m_ref only has to keep
       // exp2(s * sc - m_ref) inside the fp32 range — it need not track the running row maximum.  Tile 0 fixes m_ref at
@@ -291,7 +340,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         return fmax3(mx0, mx1, fmaxf(__uint_as_float(s[126]), __uint_as_float(s[127]))) * sc;
       };
-      if (j == 0) m_ref = fmaxf(row_max(), -1e30f);          // (a fully masked row keeps a finite reference)
+      // The hand-pipelined section (SWP_ON) exponentiates IN PLACE and S_g is already released, so a tile cannot be
+      // redone: there the reference is settled BEFORE the section, with an exact row maximum on every tile (64 FMNMX3 on
+      // the ALU pipe, issued while the other query group owns the SFU) and the lazy rescale of the online softmax —
+      // O / l move to the new maximum only when it grew by more than 2^8 (p <= 256 is exact after the division by l).
+      bool grow = false;
+      float mx_tile = 0.f;
+      if constexpr (SWP_ON) {
+        mx_tile = row_max();
+        if (j == 0) m_ref = fmaxf(mx_tile, -1e30f);
+        else grow = mx_tile > m_ref + 8.0f;
+      } else {
+        if (j == 0) m_ref = fmaxf(row_max(), -1e30f);        // (a fully masked row keeps a finite reference)
+      }
       if (dbg) FA_DBG(dslot + 1, j);
       if (j > 0) {
         if constexpr (!ALIAS) {                    // P_g(j-1) V(j-1) retired: P_g is free, O_g is complete
@@ -300,43 +361,93 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         // (ALIAS: s_full(j) was committed after P V(j-1) in issue order, so O_g is complete here too)
       }
+      if constexpr (SWP_ON) {
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {         // warp-uniform: the rescale is warp-collective tcgen05.ld / st
+          float corr = 1.0f;
+          if (grow) { corr = ex2_approx(m_ref - mx_tile); m_ref = mx_tile; l_run *= corr; }
+#pragma unroll
+          for (int c = 0; c < KPAD; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(tmem_o + (uint32_t)c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * corr);
+            tmem_st16(tmem_o + (uint32_t)c, o);
+          }
+        }
+      }
       float lt = 0.f;
       // scale-and-subtract (packed FFMA2), exp2, row sum (packed FADD2), bf16 pack, P -> TMEM.  FA_POLY of every 8
       // element pairs take the polynomial exp2 on the FMA pipe, the rest MUFU.EX2.
       auto exp_tile = [&]() {
         const float nm = -m_ref;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#if FA_SWP
-        // Software pipeline over groups of four scores, in place on the S registers: the MUFU.EX2 of group g + FA_SWP are
-        // issued between the FADD2 / F2FP that consume group g and the FFMA2 of group g + FA_SWP + 1.  In the plain loop
-        // below ptxas puts every FADD2 / F2FP right behind its own two MUFU.EX2, so the in-order warp idles for the SFU
-        // latency once per pair (one warp alone: 16 clk per element against the SFU's 8).
-        constexpr int D = FA_SWP;
+        if constexpr (SWP_ON) {
+        // Software pipeline over groups of four scores, in place on the S registers: the exponentials of group g + FA_SWP
+        // are issued between the FADD2 / F2FP that consume group g and the FFMA2 of group g + FA_SWP + 1.  In the plain
+        // loop below ptxas puts every FADD2 / F2FP right behind its own two MUFU.EX2, so the in-order warp idles for the
+        // SFU latency once per pair (one warp alone: 16 clk per element against the SFU's 8).  FA_POLY of every 8 groups
+        // take the FMA-pipe polynomial instead of the SFU.  The bf16 pairs are packed IN PLACE into the first 16
+        // registers of each 32-score chunk (pair k of a chunk overwrites score k, consumed by pair k / 2 <= k), which is
+        // the consecutive block tcgen05.st wants: no register shuffling in front of the store.
+        constexpr int D = FA_SWP > 0 ? FA_SWP : 1;
+        const int g_turn = g;                         // (the loops below reuse the name g for the group of four)
+        auto is_poly = [](int g) {
+          const int r = g & 7;
+          return FA_POLY == 1 ? r == 3 : FA_POLY == 2 ? (r == 1 || r == 5) : FA_POLY == 3 ? (r == 1 || r == 4 || r == 6)
+               : FA_POLY == 4 ? (r & 1) == 1 : FA_POLY >= 5 ? r != 0 && r != 3 && r != 6 : false;
+        };
         auto X = [&](int g) { ffma2_b32_v(s[4 * g], s[4 * g + 1], sc, nm); ffma2_b32_v(s[4 * g + 2], s[4 * g + 3], sc, nm); };
+        auto P = [&](int g, int h) {                  // polynomial exp2 of pair h of group g
+          float x0 = __uint_as_float(s[4 * g + 2 * h]), x1 = __uint_as_float(s[4 * g + 2 * h + 1]);
+          exp2_poly2(x0, x1);
+          s[4 * g + 2 * h] = __float_as_uint(x0); s[4 * g + 2 * h + 1] = __float_as_uint(x1);
+        };
+        auto E = [&](int g, int k) {                  // k-th quarter of group g's exponentials
+          if (g >= 32) return;
+          if (!is_poly(g)) ex2_b32_v(s[4 * g + k]);
+          else if (k == 0) P(g, 0);
+          else if (k == 2) P(g, 1);
+        };
 #pragma unroll
         for (int g = 0; g <= D; ++g) X(g);
+#if FA_PINGPONG
+        // the group's turn on the SFU starts here (the FFMA2 above need no SFU) ...
+        if constexpr (NG == 2) asm volatile("bar.sync %0, 256;" ::"r"(3 + g_turn) : "memory");
+#endif
 #pragma unroll
-        for (int g = 0; g < D; ++g) {
-          ex2_b32_v(s[4 * g]); ex2_b32_v(s[4 * g + 1]); ex2_b32_v(s[4 * g + 2]); ex2_b32_v(s[4 * g + 3]);
-        }
-        uint32_t pk[16];
+        for (int g = 0; g < D; ++g) { E(g, 0); E(g, 1); E(g, 2); E(g, 3); }
 #pragma unroll
         for (int g = 0; g < 32; ++g) {
           const int e = g + D;                       // group whose exponentials are issued in this round
-          if (e < 32) ex2_b32_v(s[4 * e]);
+          const int c32 = (g >> 3) * 32, k = (2 * g) & 15;
+          E(e, 0);
           fadd2_b32_v(l0, l1, s[4 * g], s[4 * g + 1]);
-          if (e < 32) ex2_b32_v(s[4 * e + 1]);
-          pk[(2 * g) & 15] = pack_bf16x2_b32_v(s[4 * g], s[4 * g + 1]);
-          if (e < 32) ex2_b32_v(s[4 * e + 2]);
+          E(e, 1);
+          const uint32_t p0 = pack_bf16x2_b32_v(s[4 * g], s[4 * g + 1]);
+          E(e, 2);
           fadd2_b32_v(l2, l3, s[4 * g + 2], s[4 * g + 3]);
-          if (e < 32) ex2_b32_v(s[4 * e + 3]);
-          pk[(2 * g + 1) & 15] = pack_bf16x2_b32_v(s[4 * g + 2], s[4 * g + 3]);
+          E(e, 3);
+#if FA_PINGPONG
+          // ... and ends behind its last exponential: the remaining FADD2 / F2FP / tcgen05.st overlap the other group's start
+          if constexpr (NG == 2) { if (e == FA_HANDOFF) asm volatile("bar.arrive %0, 256;" ::"r"(3 + (g_turn ^ 1)) : "memory"); }
+#endif
+          const uint32_t p1 = pack_bf16x2_b32_v(s[4 * g + 2], s[4 * g + 3]);
+          s[c32 + k] = p0; s[c32 + k + 1] = p1;
           if (e + 1 < 32) X(e + 1);
-          if ((g & 7) == 7) tmem_st16p(tmem_p + (uint32_t)((g >> 3) * 16), pk);
+          if ((g & 7) == 7) tmem_st16p(tmem_p + (uint32_t)((g >> 3) * 16), s + c32);
+#if FA_SPLIT > 0
+          // basic-block boundary (a branch that is never taken): ptxas schedules inside a block, so the order written
+          // here — SFU exponentials, their consumers and the polynomial chains in the same rounds — cannot be undone by
+          // hoisting every polynomial chain in front of the first MUFU.EX2 or sinking every F2FP behind the last one
+          if ((g % FA_SPLIT) == FA_SPLIT - 1 && g != 31) {
+            if (a.Nq == -2 - g) asm volatile("trap;");   // a different impossible value each time: not foldable
+          }
+#endif
         }
         lt = (l0 + l1) + (l2 + l3);
         return;
-#endif
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
@@ -358,9 +469,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         }
         lt = (l0 + l1) + (l2 + l3);
       };
+#if FA_PINGPONG
+      // strict alternation of the two groups' exponential sections (named barriers 3 / 4 over the 256 softmax threads):
+      // a group exponentiates alone on its sub-partitions' SFUs while the other one does its TMEM / barrier round trip
+      if constexpr (NG == 2 && !SWP_ON) asm volatile("bar.sync %0, 256;" ::"r"(3 + g) : "memory");
+#endif
       exp_tile();
+#if FA_PINGPONG
+      if constexpr (NG == 2 && !SWP_ON) asm volatile("bar.arrive %0, 256;" ::"r"(3 + (g ^ 1)) : "memory");
+#endif
       // overflow guard (warp-uniform: the rescale uses warp-collective tcgen05.ld / st)
-      if (j > 0 && __any_sync(0xffffffffu, !(lt < FA_GROW_LIMIT))) {
+      if (!SWP_ON && j > 0 && __any_sync(0xffffffffu, !(lt < FA_GROW_LIMIT))) {
         const float mx = row_max();
         float corr = 1.0f;
         if (mx > m_ref) { corr = ex2_approx(m_ref - mx); m_ref = mx; l_run *= corr; }

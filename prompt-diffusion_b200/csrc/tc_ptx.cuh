@@ -30,6 +30,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the waiting thread is parked by the hardware until the phase completes or the
+// hint expires instead of returning to its polling loop every few dozen cycles — for role warps (TMA, MMA issue) that
+// share a sub-partition with warps whose issue slots matter.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(s_u32(bar)), "r"(parity), "r"(ns) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 4000u)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("pd_b200 tcgen05 kernel: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
 // Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
