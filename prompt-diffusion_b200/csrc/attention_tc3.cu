@@ -37,6 +37,9 @@ constexpr int F3_REGS_CTRL = 56, F3_REGS_SOFTMAX = 152;
 #endif
 constexpr int F3_OCOLS = 40;                 // O_g columns = N extent of P V (head dim rounded up to 8, <= 40)
 constexpr float F3_GROW_LIMIT = 1.8446744e19f;   // 2^64, see attention_tc.cu
+#ifndef F3_SWP
+#define F3_SWP 0           // > 0: exponential section software-pipelined by hand in place (see attention_tc.cu, FA_SWP)
+#endif
 #ifndef F3_POLY
 #define F3_POLY 0          // of every 8 element pairs, how many take the FMA-pipe exp2 (0..8)
 #endif
@@ -270,11 +273,61 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         return fmax3(mx0, mx1, fmaxf(__uint_as_float(s[126]), __uint_as_float(s[127]))) * sc;
       };
+#if F3_SWP
+      // hand-pipelined in-place section (attention_tc.cu, FA_SWP): the reference is settled before it — exact row maximum
+      // on every tile, O / l rescaled only when it grew by more than 2^8
+      {
+        const float mx_tile = row_max();
+        bool grow = false;
+        if (j == 0) m_ref = fmaxf(mx_tile, -1e30f);
+        else grow = mx_tile > m_ref + 8.0f;
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+          float corr = 1.0f;
+          if (grow) { corr = ex2_approx(m_ref - mx_tile); m_ref = mx_tile; l_run *= corr; }
+#pragma unroll
+          for (int c = 0; c < F3_OCOLS; c += 8) {
+            uint32_t o[8];
+            tmem_ld8(tmem_o + (uint32_t)c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * corr);
+            tmem_st8(tmem_o + (uint32_t)c, o);
+          }
+        }
+      }
+#else
       if (j == 0) m_ref = fmaxf(row_max(), -1e30f);
+#endif
       float lt = 0.f;
       auto exp_tile = [&]() {
         const float nm = -m_ref;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#if F3_SWP
+        constexpr int D = F3_SWP;
+        auto X = [&](int q) { ffma2_b32_v(s[4 * q], s[4 * q + 1], sc, nm); ffma2_b32_v(s[4 * q + 2], s[4 * q + 3], sc, nm); };
+        auto E = [&](int q, int k) { if (q < 32) ex2_b32_v(s[4 * q + k]); };
+#pragma unroll
+        for (int q = 0; q <= D; ++q) X(q);
+#pragma unroll
+        for (int q = 0; q < D; ++q) { E(q, 0); E(q, 1); E(q, 2); E(q, 3); }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int e = q + D, c32 = (q >> 3) * 32, k = (2 * q) & 15;
+          E(e, 0);
+          fadd2_b32_v(l0, l1, s[4 * q], s[4 * q + 1]);
+          E(e, 1);
+          const uint32_t p0 = pack_bf16x2_b32_v(s[4 * q], s[4 * q + 1]);
+          E(e, 2);
+          fadd2_b32_v(l2, l3, s[4 * q + 2], s[4 * q + 3]);
+          E(e, 3);
+          const uint32_t p1 = pack_bf16x2_b32_v(s[4 * q + 2], s[4 * q + 3]);
+          s[c32 + k] = p0; s[c32 + k + 1] = p1;     // in place: the consecutive block tcgen05.st wants
+          if (e + 1 < 32) X(e + 1);
+          if ((q & 7) == 7) tmem_st16p(tmem_s + (uint32_t)((q >> 3) * 16), s + c32);
+        }
+        lt = (l0 + l1) + (l2 + l3);
+        return;
+#endif
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
@@ -298,7 +351,7 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       exp_tile();
       // overflow guard (warp-uniform: the rescale uses warp-collective tcgen05.ld / st).  s_full(j) was committed after
       // P V(j-1) in issue order, so O_g holds every tile < j and no MMA touches it before p_full(j).
-      if (j > 0 && __any_sync(0xffffffffu, !(lt < F3_GROW_LIMIT))) {
+      if (!F3_SWP && j > 0 && __any_sync(0xffffffffu, !(lt < F3_GROW_LIMIT))) {
         const float mx = row_max();
         float corr = 1.0f;
         if (mx > m_ref) { corr = ex2_approx(m_ref - mx); m_ref = mx; l_run *= corr; }
