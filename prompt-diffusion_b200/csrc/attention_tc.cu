@@ -56,6 +56,9 @@ constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or a
 #ifndef FA_HANDOFF
 #define FA_HANDOFF 31      // (FA_PINGPONG with FA_SWP) group of four whose exponentials are the last ones before the SFU turn passes to the other query group
 #endif
+#ifndef FA_HAND
+#define FA_HAND 1          // 1 (with FA_SWP, needs -Xptxas -O1 for this file): hand-scheduled section, one polynomial pair per three SFU pairs
+#endif
 #ifndef FA_SPLIT
 #define FA_SPLIT 0         // > 0 (with FA_SWP): a never-taken branch every FA_SPLIT groups of the pipelined exponential section
 #endif
@@ -392,6 +395,73 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         // the consecutive block tcgen05.st wants: no register shuffling in front of the store.
         constexpr int D = FA_SWP > 0 ? FA_SWP : 1;
         const int g_turn = g;                         // (the loops below reuse the name g for the group of four)
+#if FA_HAND
+        // HAND-SCHEDULED section (this file is compiled with -Xptxas -O1, which keeps the order written here; at -O3 ptxas
+        // hoists every polynomial chain in front of the first MUFU.EX2 and the SFU then idles behind the FMA pipe).
+        // Rounds of eight scores = four pairs: pairs 0..2 go through the SFU, pair 3 through the FMA-pipe polynomial, whose
+        // six dependent stages sit one by one in the issue slots between the six MUFU.EX2 (8 clk of SFU each).  Round r
+        // issues the exponentials of round r + 1, the scale-and-subtract of round r + 2 and consumes (row sum, bf16 pack)
+        // round r: 8 exponentials per 48 SFU clk instead of 6.
+        {
+          auto X8 = [&](int r) {
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) ffma2_b32_v(s[8 * r + k], s[8 * r + k + 1], sc, nm);
+          };
+          uint32_t t0 = 0, t1 = 0, n0 = 0, n1 = 0, q0 = 0, q1 = 0;
+          uint32_t u0 = 0, u1 = 0, m0 = 0, m1 = 0, w0 = 0, w1 = 0;       // second polynomial chain (rounds with two of them)
+          auto C = [&](int r, int pr, float& la, float& lb) {          // consume pair pr of round r
+            const int i = 8 * r + 2 * pr, c32 = (r >> 2) * 32, k = (4 * r + pr) & 15;
+            fadd2_b32_v(la, lb, s[i], s[i + 1]);
+            const uint32_t pk = pack_bf16x2_b32_v(s[i], s[i + 1]);
+            s[c32 + k] = pk;
+          };
+          // FA_HAND == 2: every third round sends pair 2 through the polynomial as well (a third of the exponentials off
+          // the SFU: SFU and FMA pipe then carry about the same number of cycles per score)
+          auto two_poly = [](int r) { return FA_HAND == 2 && (r % 3) == 2; };
+          // exponentials of round r (MUFU pairs 0..2, polynomial pair 3), with the consumers of round r - 1 in between
+          auto round = [&](int r, bool consume, bool scale_next) {
+            const int b = 8 * r;
+            const bool ex = r < 16, tp = ex && two_poly(r);
+            if (ex) { ex2_b32_v(s[b]); poly_s1(s[b + 6], s[b + 7], t0, t1); }
+            if (tp) poly_s1(s[b + 4], s[b + 5], u0, u1);
+            if (ex) ex2_b32_v(s[b + 1]);
+            if (consume) C(r - 1, 0, l0, l1);
+            if (ex) { ex2_b32_v(s[b + 2]); poly_s2a(n0, n1, t0, t1); }
+            if (tp) poly_s2a(m0, m1, u0, u1);
+            if (consume) C(r - 1, 1, l2, l3);
+            if (ex) { ex2_b32_v(s[b + 3]); poly_s2b(s[b + 6], s[b + 7], n0, n1); }
+            if (tp) poly_s2b(s[b + 4], s[b + 5], m0, m1);
+            if (scale_next && r + 1 < 16) { ffma2_b32_v(s[b + 8], s[b + 9], sc, nm); ffma2_b32_v(s[b + 10], s[b + 11], sc, nm); }
+            if (ex && !tp) ex2_b32_v(s[b + 4]);
+            if (ex) poly_s3(q0, q1, s[b + 6], s[b + 7]);
+            if (tp) poly_s3(w0, w1, s[b + 4], s[b + 5]);
+            if (consume) C(r - 1, 2, l0, l1);
+            if (ex && !tp) ex2_b32_v(s[b + 5]);
+            if (ex) poly_s45<4>(q0, q1, s[b + 6], s[b + 7]);
+            if (tp) poly_s45<4>(w0, w1, s[b + 4], s[b + 5]);
+            if (scale_next && r + 1 < 16) { ffma2_b32_v(s[b + 12], s[b + 13], sc, nm); ffma2_b32_v(s[b + 14], s[b + 15], sc, nm); }
+            if (ex) poly_s45<5>(q0, q1, s[b + 6], s[b + 7]);
+            if (tp) poly_s45<5>(w0, w1, s[b + 4], s[b + 5]);
+            if (consume) C(r - 1, 3, l2, l3);
+            if (ex) poly_s6(s[b + 6], s[b + 7], q0, q1, t0, t1);
+            if (tp) poly_s6(s[b + 4], s[b + 5], w0, w1, u0, u1);
+            if (consume && ((r - 1) & 3) == 3) tmem_st16p(tmem_p + (uint32_t)(((r - 1) >> 2) * 16), s + ((r - 1) >> 2) * 32);
+          };
+          X8(0);
+#if FA_PINGPONG
+          if constexpr (NG == 2) asm volatile("bar.sync %0, 256;" ::"r"(3 + g_turn) : "memory");
+#endif
+#pragma unroll
+          for (int r = 0; r < 17; ++r) {
+            round(r, r > 0, true);
+#if FA_PINGPONG
+            if constexpr (NG == 2) { if (r == 15) asm volatile("bar.arrive %0, 256;" ::"r"(3 + (g_turn ^ 1)) : "memory"); }
+#endif
+          }
+          lt = (l0 + l1) + (l2 + l3);
+          return;
+        }
+#endif
         auto is_poly = [](int g) {
           const int r = g & 7;
           return FA_POLY == 1 ? r == 3 : FA_POLY == 2 ? (r == 1 || r == 5) : FA_POLY == 3 ? (r == 1 || r == 4 || r == 6)

@@ -415,13 +415,15 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 // Inside the whole denoising step, same box, CUDA-graph replay (profiles/r02_attn3_insitu_ab.txt): config 4 (9216 tokens)
 // 125.3 against 128.5 ms per step (-2.5 %), but config 2 (4096 tokens) 23.9 / 24.5 against 23.5 / 24.1 ms (+0.3 ms): the
 // step runs at the 1 kW power cap and the 16-warp CTA with its polling MMA warp buys its 7 % with more power than the
-// step has to spare.  Auto therefore picks this kernel from 6144 queries up; PD_B200_ATTN3=0 switches that off,
-// PD_B200_ATTN3=2 selects it for every d <= 40 shape, engine 6 selects it explicitly.
-static int g_tc3_on = -1;     // -1: read PD_B200_ATTN3 once (default on)
+// step has to spare.  Auto therefore picked this kernel from 6144 queries up — until the two-group kernel learnt to take
+// turns on the SFU with a hand-scheduled exponential section (attention_tc.cu: 648 us / 6.05 ms at the two shapes above,
+// profiles/r02_attn_bench_hand.txt), which beats this kernel at every size.  Auto no longer picks it: PD_B200_ATTN3=1
+// restores the 6144-query rule, PD_B200_ATTN3=2 selects it for every d <= 40 shape, engine 6 selects it explicitly.
+static int g_tc3_on = -1;     // -1: read PD_B200_ATTN3 once (default off)
 bool attention_tc3_supported(int d, int Nq, int Nk) {
   if (g_tc3_on < 0) {
     const char* e = getenv("PD_B200_ATTN3");
-    g_tc3_on = (e != nullptr && e[0] == '0') ? 0 : (e != nullptr && e[0] == '2') ? 2 : 1;
+    g_tc3_on = (e != nullptr && e[0] == '1') ? 1 : (e != nullptr && e[0] == '2') ? 2 : 0;
   }
   return g_tc3_on && d <= 40 && Nq >= (g_tc3_on == 2 ? 768 : 6144) && Nk >= 256;
 }

@@ -373,6 +373,57 @@ __device__ __forceinline__ void exp2_poly2(float& x0, float& x1) {
   x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
+// The polynomial exp2 of exp2_poly2 in six separately placeable stages on b32 registers (volatile: the hand-scheduled
+// exponential section of attention_tc.cu spreads them between its MUFU.EX2 issues).  x: the pair, t: scratch pair.
+__device__ __forceinline__ void poly_s1(uint32_t& x0, uint32_t& x1, uint32_t& t0, uint32_t& t1) {   // clamp, t = x + 1.5 * 2^23
+  asm volatile("{\n\t.reg .b64 rx, rt, rm;\n\t"
+               "max.f32 %0, %0, 0fC2FA0000;\n\tmax.f32 %1, %1, 0fC2FA0000;\n\t"
+               "mov.b64 rx, {%0, %1};\n\tmov.b64 rm, {0f4B400000, 0f4B400000};\n\t"
+               "add.rn.f32x2 rt, rx, rm;\n\t"
+               "mov.b64 {%2, %3}, rt;\n\t}"
+               : "+r"(x0), "+r"(x1), "=r"(t0), "=r"(t1));
+}
+__device__ __forceinline__ void poly_s2a(uint32_t& n0, uint32_t& n1, uint32_t t0, uint32_t t1) {   // n = t - 1.5 * 2^23 = round(x)
+  asm volatile("{\n\t.reg .b64 rn, rt, rm;\n\t"
+               "mov.b64 rt, {%2, %3};\n\tmov.b64 rm, {0fCB400000, 0fCB400000};\n\t"
+               "add.rn.f32x2 rn, rt, rm;\n\t"
+               "mov.b64 {%0, %1}, rn;\n\t}"
+               : "=r"(n0), "=r"(n1) : "r"(t0), "r"(t1));
+}
+__device__ __forceinline__ void poly_s2b(uint32_t& x0, uint32_t& x1, uint32_t n0, uint32_t n1) {   // f = x - n  (in x)
+  asm volatile("{\n\t.reg .b64 rx, rn, rm;\n\t"
+               "mov.b64 rx, {%0, %1};\n\tmov.b64 rn, {%2, %3};\n\tmov.b64 rm, {0fBF800000, 0fBF800000};\n\t"
+               "fma.rn.f32x2 rx, rn, rm, rx;\n\t"
+               "mov.b64 {%0, %1}, rx;\n\t}"
+               : "+r"(x0), "+r"(x1) : "r"(n0), "r"(n1));
+}
+__device__ __forceinline__ void poly_s3(uint32_t& p0, uint32_t& p1, uint32_t f0, uint32_t f1) {   // p = c3 f + c2
+  asm volatile("{\n\t.reg .b64 rp, rf, ra, rb;\n\t"
+               "mov.b64 rf, {%2, %3};\n\tmov.b64 ra, {0f3D64DDB6, 0f3D64DDB6};\n\tmov.b64 rb, {0f3E781C09, 0f3E781C09};\n\t"
+               "fma.rn.f32x2 rp, rf, ra, rb;\n\t"
+               "mov.b64 {%0, %1}, rp;\n\t}"
+               : "=r"(p0), "=r"(p1) : "r"(f0), "r"(f1));
+}
+template <int STAGE>                                                                               // p = p f + c1 | c0
+__device__ __forceinline__ void poly_s45(uint32_t& p0, uint32_t& p1, uint32_t f0, uint32_t f1) {
+  if constexpr (STAGE == 4)
+    asm volatile("{\n\t.reg .b64 rp, rf, rc;\n\t"
+                 "mov.b64 rp, {%0, %1};\n\tmov.b64 rf, {%2, %3};\n\tmov.b64 rc, {0f3F3170CA, 0f3F3170CA};\n\t"
+                 "fma.rn.f32x2 rp, rp, rf, rc;\n\t"
+                 "mov.b64 {%0, %1}, rp;\n\t}"
+                 : "+r"(p0), "+r"(p1) : "r"(f0), "r"(f1));
+  else
+    asm volatile("{\n\t.reg .b64 rp, rf, rc;\n\t"
+                 "mov.b64 rp, {%0, %1};\n\tmov.b64 rf, {%2, %3};\n\tmov.b64 rc, {0f3F7FFC9C, 0f3F7FFC9C};\n\t"
+                 "fma.rn.f32x2 rp, rp, rf, rc;\n\t"
+                 "mov.b64 {%0, %1}, rp;\n\t}"
+                 : "+r"(p0), "+r"(p1) : "r"(f0), "r"(f1));
+}
+__device__ __forceinline__ void poly_s6(uint32_t& x0, uint32_t& x1, uint32_t p0, uint32_t p1, uint32_t t0, uint32_t t1) {  // 2^n * p
+  asm volatile("mad.lo.s32 %0, %4, 0x800000, %2;\n\tmad.lo.s32 %1, %5, 0x800000, %3;"
+               : "=r"(x0), "=r"(x1) : "r"(p0), "r"(p1), "r"(t0), "r"(t1));
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

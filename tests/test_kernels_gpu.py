@@ -448,8 +448,9 @@ PTC_ATTN_CASES = [(2, 8, 1024, 1024, 40), (1, 8, 4096, 4096, 40), (3, 5, 700, 65
 
 @pytest.mark.parametrize("B,heads,Nq,Nk,d", PTC_ATTN_CASES)
 def test_attention_tcgen05_persistent(B, heads, Nq, Nk, d):
-    """Persistent form of the streaming tcgen05 kernel (engine 8): one CTA per SM walks (batch, head, query pair) units.
-    Same arithmetic per unit as engine 3, so the two must agree bit for bit; also checked against torch fp32."""
+    """Persistent form of the streaming tcgen05 kernel (engine 8): one CTA per SM walks (batch, head, query pair) units;
+    checked against torch fp32 and against engine 3 (same tiling and accumulation order; engine 3 has since moved a
+    quarter of its exponentials to an FMA-pipe polynomial, so the two agree to bf16 rounding, no longer bit for bit)."""
     ops = _ops()
     g = torch.Generator(device=DEV).manual_seed(27)
     Cc = heads * d
@@ -465,7 +466,7 @@ def test_attention_tcgen05_persistent(B, heads, Nq, Nk, d):
     assert err < 1e-2, err
     out3 = torch.empty_like(out)
     ops.attention(q, k, v, out3[:, :Cc], B, heads, Nq, Nk, d, engine=3)
-    assert torch.equal(out3[:, :Cc], out[:, :Cc])
+    assert rel_l2(out3[:, :Cc].float(), out[:, :Cc].float()) < 4e-3
 
 
 XTC_ATTN_CASES = [(2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80), (1, 8, 300, 77, 40), (3, 5, 1000, 1, 64), (1, 2, 9216, 128, 40),
