@@ -110,7 +110,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
                     const FaArgs a) {
   constexpr bool ALIAS = KP16 > 4;
-  constexpr bool SWP_ON = FA_SWP > 0 && !ALIAS;      // the hand-pipelined exponential section (d <= 64 instantiations only)
+#ifndef FA_SWP_ALIAS
+#define FA_SWP_ALIAS 1     // 1: the hand-scheduled section also for 64 < d <= 128 (P over S, two groups): 77.1 -> 72.8 us at B16 h8 N1024 d80
+#endif
+  constexpr bool SWP_ON = FA_SWP > 0 && (!ALIAS || (FA_SWP_ALIAS && NG == 2));      // the hand-pipelined exponential section
   constexpr int ND = (KP16 + 3) / 4;
   constexpr int KPAD = KP16 * 16;
   static_assert(NG == 2 || (NG == 1 && KP16 > 8 && KP16 <= 12), "one query group only for 128 < d <= 192");

@@ -54,10 +54,13 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity,
   }
 }
 // Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
+#ifndef PD_PARK
+#define PD_PARK 0          // 1: every bounded wait parks its thread with a suspend-time hint instead of re-polling
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!(PD_PARK ? mbar_try_wait_hint(bar, parity, 4000u) : mbar_try_wait(bar, parity))) {
     if (clock64() - t0 > 4000000000LL) {
       printf("pd_b200 tcgen05 kernel: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x,
              threadIdx.x, parity);
