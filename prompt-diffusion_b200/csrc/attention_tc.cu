@@ -59,6 +59,9 @@ constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or a
 #ifndef FA_HAND
 #define FA_HAND 1          // 1 (with FA_SWP, needs -Xptxas -O1 for this file): hand-scheduled section, one polynomial pair per three SFU pairs
 #endif
+#ifndef FA_HANDOFF_R
+#define FA_HANDOFF_R 15    // (FA_HAND) round of eight scores behind whose exponentials the SFU turn passes to the other group
+#endif
 #ifndef FA_SPLIT
 #define FA_SPLIT 0         // > 0 (with FA_SWP): a never-taken branch every FA_SPLIT groups of the pipelined exponential section
 #endif
@@ -458,7 +461,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           for (int r = 0; r < 17; ++r) {
             round(r, r > 0, true);
 #if FA_PINGPONG
-            if constexpr (NG == 2) { if (r == 15) asm volatile("bar.arrive %0, 256;" ::"r"(3 + (g_turn ^ 1)) : "memory"); }
+            if constexpr (NG == 2) { if (r == FA_HANDOFF_R) asm volatile("bar.arrive %0, 256;" ::"r"(3 + (g_turn ^ 1)) : "memory"); }
 #endif
           }
           lt = (l0 + l1) + (l2 + l3);
