@@ -10,17 +10,27 @@
 //   warp 8    : TMA producer — Q (both groups) once, then K and V tiles of 128 keys into two independent rings.
 //               The tensor maps view q/k/v as (d, heads, tokens, batch); a 64-wide box over a 40-wide head makes
 //               TMA zero-fill channels 40..63, so no padding pass and no padded copies exist.
-//   warp 9    : MMA issuer — S_g[128x128] = Q_g K^T (smem x smem) into TMEM; O_g[128xd] += P_g V with the A
-//               operand P_g read FROM TMEM (bf16, written by the softmax threads over the first 64 columns of
-//               S_g) and the V tile used in place as the MN-major B operand.  Issue order per key tile:
-//               PV_a(j), QK_a(j+1), PV_b(j), QK_b(j+1) — the tensor pipe executes in order, so S_g(j+1) can
-//               never overtake the read of P_g(j), and group B's exponentials cover group A's MMA latency.
+//   warp 9    : MMA issuer (warp-uniform loop, one ELECTED lane issues) — S_g[128x128] = Q_g K^T (smem x smem) into
+//               TMEM; O_g[128xd] += P_g V with the A operand P_g read FROM TMEM (bf16, written by the softmax threads)
+//               and the V tile used in place as the MN-major B operand.  d <= 64: P has its own TMEM columns and
+//               Q K^T of tile j + 1 is issued as soon as S(j) sits in registers; above, P lies over S and the in-order
+//               tensor pipe (P V(j) issued before Q K^T(j+1)) protects it.
 //   warps 0-3 : softmax of group A, warps 4-7: group B — ONE THREAD PER QUERY ROW (TMEM lane == row): the row
-//               max / sum need no shuffles.  S is read from TMEM exactly once (128 registers), the max uses
-//               3-input FMNMX, scale-and-subtract is a packed FFMA2, the row sum a packed FADD2, P goes back to
-//               TMEM with tcgen05.st.  O is rescaled lazily: only when a row max grew by more than 2^8 (the
-//               stale reference keeps p <= 256, exact after the final division by l).
+//               max / sum need no shuffles.  S is read from TMEM exactly once (128 registers).
+//               The two groups take STRICT TURNS on the SFU (named barriers 3 / 4, FlashAttention-3's ping-pong): a
+//               group exponentiates alone on its sub-partitions while the other one does its round trip (P -> TMEM,
+//               arrive, P V + next Q K^T on the tensor pipe, S -> registers, row maximum).  The section itself is
+//               hand-scheduled in place on the S registers (FA_SWP / FA_HAND below): rounds of eight scores, three
+//               pairs through MUFU.EX2, one through an FMA-pipe polynomial whose stages sit in the issue slots between
+//               the MUFU issues; packed FFMA2 scale-and-subtract two rounds ahead, packed FADD2 row sum and bf16 pack
+//               one round behind, P back to TMEM with tcgen05.st from the registers it was packed into.
+//               Reference: exact row maximum on every tile, O / l rescaled lazily — only when the maximum grew by
+//               more than 2^8 (p <= 256 is exact after the final division by l).
 //   epilogue  : O / l -> bf16 -> swizzled smem (the dead Q tile) -> TMA store (clips columns >= d, rows >= Nq).
+//
+// THIS FILE IS COMPILED WITH -Xptxas -O1 (build.sh): at -O3 ptxas re-schedules the hand-written section (every polynomial
+// chain in front of the first MUFU.EX2): 712 instead of 648 us at B16 h8 N4096 d40.  History of the design and every
+// measured alternative: DESIGN.md section 4.0.
 //
 #include "tc_ptx.cuh"
 
@@ -30,9 +40,7 @@ constexpr int FA_BQ = 128, FA_GROUPS = 2, FA_BK = 128, FA_THREADS = 320, FA_MAX_
 constexpr int FA_TILE_BYTES = 128 * 128;   // one [128 rows][64 bf16] SWIZZLE_128B tile
 constexpr int FA_ALIGN_SLACK = 1024;
 constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or above it (or NaN) triggers the exact-max path
-#ifndef FA_ORDERED
-#define FA_ORDERED 0
-#endif
+// ---- build switches: the defaults are the shipped kernel; the others are measured alternatives (profiles/r02_attn_*) ----
 #ifndef FA_ELECT
 #define FA_ELECT 1         // 1: the MMA warp runs its loop warp-uniformly and one ELECTED lane issues (plain predicated UTCHMMA instead of the ELECT ... BRA.U.ANY retry loop ptxas emits inside `if (lane == 0)`)
 #endif
@@ -72,7 +80,7 @@ constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or a
 #define FA_SWP 2           // > 0: exponential section software-pipelined by hand, MUFU.EX2 issued FA_SWP groups of four ahead of their consumers; measured (profiles/r02_attn_swp_variants.txt, B16 h8 N4096 d40): 0 -> 761 us, 1..4 -> 776 us: the consumer stall behind each MUFU pair is NOT what holds the section at 61 % of the SFU bound
 #endif
 #ifndef FA_POLY
-#define FA_POLY 0          // of every 8 element pairs, how many take the FMA-pipe exp2 (0..8); measured: 2 -> 792 us vs 0 -> 763 us (B16 h8 N4096 d40): the section is issue-bound, not SFU-bound
+#define FA_POLY 0          // (without FA_HAND) of every 8 groups of four, how many take the FMA-pipe exp2; at -O3 ptxas hoists the chains in front of the SFU work: neutral or slower
 #endif
 unsigned long long* g_fa_dbg_host = nullptr;   // optional phase timeline (block 0 only), passed by value (shared with attention_tc3 / tc4.cu)
 
