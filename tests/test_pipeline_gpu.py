@@ -165,3 +165,17 @@ def test_diffusers_loop_fused_step_equals_call_by_call_route(cfg, state_dict_cpu
         print(f"[parity] diffusers loop fused vs call-by-call {mode} {kw}: {err:.3e}")
         assert err <= tol
     assert model.control_scales == [1.0] * 13 and pipe._fused.control_scales == [1.0] * 13
+
+
+def test_from_nets_needs_one_buffer_pool(cfg, state_dict_cpu):
+    """``ControlLDM.from_nets`` fuses two existing nets only when they share a buffer pool (the ControlNet's zero-conv
+    epilogues add onto the UNet's stored skips in place); separately built shims keep the call-by-call route."""
+    from prompt_diffusion_b200 import ControlLDM, PromptDiffusionControlNetModel, PromptDiffusionPipeline
+    model = ControlLDM(cfg, mode="bf16", device=DEV).load_state_dict(state_dict_cpu)
+    fused = ControlLDM.from_nets(model.model.diffusion_model, model.control_model)
+    assert fused.pool is model.pool and fused.control_model is model.control_model
+    other = PromptDiffusionControlNetModel(cfg, mode="bf16", device=DEV)
+    with pytest.raises(ValueError):
+        ControlLDM.from_nets(model.model.diffusion_model, other.net)
+    assert PromptDiffusionPipeline(model.model.diffusion_model, other)._fused is None
+    assert PromptDiffusionPipeline.from_ldm(model)._fused is not None
