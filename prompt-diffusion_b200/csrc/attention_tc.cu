@@ -70,6 +70,9 @@ constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or a
 #ifndef FA_HANDOFF_R
 #define FA_HANDOFF_R 15    // (FA_HAND) round of eight scores behind whose exponentials the SFU turn passes to the other group
 #endif
+#ifndef FA_CDIST
+#define FA_CDIST 1         // (FA_HAND) the row sum / bf16 pack of round r - FA_CDIST sit between the exponentials of round r
+#endif
 #ifndef FA_SPLIT
 #define FA_SPLIT 0         // > 0 (with FA_SWP): a never-taken branch every FA_SPLIT groups of the pipelined exponential section
 #endif
@@ -433,41 +436,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           // the SFU: SFU and FMA pipe then carry about the same number of cycles per score)
           auto two_poly = [](int r) { return FA_HAND == 2 && (r % 3) == 2; };
           // exponentials of round r (MUFU pairs 0..2, polynomial pair 3), with the consumers of round r - 1 in between
+          constexpr int CD = FA_CDIST;                  // rounds between a pair's exponentials and its consumers
           auto round = [&](int r, bool consume, bool scale_next) {
             const int b = 8 * r;
             const bool ex = r < 16, tp = ex && two_poly(r);
             if (ex) { ex2_b32_v(s[b]); poly_s1(s[b + 6], s[b + 7], t0, t1); }
             if (tp) poly_s1(s[b + 4], s[b + 5], u0, u1);
             if (ex) ex2_b32_v(s[b + 1]);
-            if (consume) C(r - 1, 0, l0, l1);
+            if (consume) C(r - CD, 0, l0, l1);
             if (ex) { ex2_b32_v(s[b + 2]); poly_s2a(n0, n1, t0, t1); }
             if (tp) poly_s2a(m0, m1, u0, u1);
-            if (consume) C(r - 1, 1, l2, l3);
+            if (consume) C(r - CD, 1, l2, l3);
             if (ex) { ex2_b32_v(s[b + 3]); poly_s2b(s[b + 6], s[b + 7], n0, n1); }
             if (tp) poly_s2b(s[b + 4], s[b + 5], m0, m1);
             if (scale_next && r + 1 < 16) { ffma2_b32_v(s[b + 8], s[b + 9], sc, nm); ffma2_b32_v(s[b + 10], s[b + 11], sc, nm); }
             if (ex && !tp) ex2_b32_v(s[b + 4]);
             if (ex) poly_s3(q0, q1, s[b + 6], s[b + 7]);
             if (tp) poly_s3(w0, w1, s[b + 4], s[b + 5]);
-            if (consume) C(r - 1, 2, l0, l1);
+            if (consume) C(r - CD, 2, l0, l1);
             if (ex && !tp) ex2_b32_v(s[b + 5]);
             if (ex) poly_s45<4>(q0, q1, s[b + 6], s[b + 7]);
             if (tp) poly_s45<4>(w0, w1, s[b + 4], s[b + 5]);
             if (scale_next && r + 1 < 16) { ffma2_b32_v(s[b + 12], s[b + 13], sc, nm); ffma2_b32_v(s[b + 14], s[b + 15], sc, nm); }
             if (ex) poly_s45<5>(q0, q1, s[b + 6], s[b + 7]);
             if (tp) poly_s45<5>(w0, w1, s[b + 4], s[b + 5]);
-            if (consume) C(r - 1, 3, l2, l3);
+            if (consume) C(r - CD, 3, l2, l3);
             if (ex) poly_s6(s[b + 6], s[b + 7], q0, q1, t0, t1);
             if (tp) poly_s6(s[b + 4], s[b + 5], w0, w1, u0, u1);
-            if (consume && ((r - 1) & 3) == 3) tmem_st16p(tmem_p + (uint32_t)(((r - 1) >> 2) * 16), s + ((r - 1) >> 2) * 32);
+            if (consume && ((r - CD) & 3) == 3) tmem_st16p(tmem_p + (uint32_t)(((r - CD) >> 2) * 16), s + ((r - CD) >> 2) * 32);
           };
           X8(0);
 #if FA_PINGPONG
           if constexpr (NG == 2) asm volatile("bar.sync %0, 256;" ::"r"(3 + g_turn) : "memory");
 #endif
 #pragma unroll
-          for (int r = 0; r < 17; ++r) {
-            round(r, r > 0, true);
+          for (int r = 0; r < 16 + CD; ++r) {
+            round(r, r >= CD, true);
 #if FA_PINGPONG
             if constexpr (NG == 2) { if (r == FA_HANDOFF_R) asm volatile("bar.arrive %0, 256;" ::"r"(3 + (g_turn ^ 1)) : "memory"); }
 #endif

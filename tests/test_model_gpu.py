@@ -216,6 +216,33 @@ def test_apply_model_config2_shape_vs_oracle_gpu(models, cfg, state_dict_cpu):
         assert err <= TOL[mode], (mode, err)
 
 
+def test_apply_model_config2_full_batch_vs_oracle_gpu(models, cfg, state_dict_cpu):
+    """BASELINE config 2 at its FULL size — 512^2, batch 8, CFG => B_eff 16, 65536 x 320 activations, 128 heads of
+    4096-token self-attention, the shapes every tuned launch variant of the bench runs — against the oracle evaluated in
+    fp32 on this GPU (its 8.6 GB score tensors fit in HBM here).  Both entry points of the product: ``apply_model`` on the
+    duplicated batch and ``apply_model_cfg`` (the sampler's call: no duplicated latent, hints at B and tiled)."""
+    from oracle import cldm_oracle as O
+    sd_gpu = {k: v.to(DEV) for k, v in state_dict_cpu.items()}
+    inp, cond, un, x_in, c_in = _cfg_inputs(cfg, 8, 512, 512)
+    t = torch.full((16,), 481, dtype=torch.long, device=DEV)
+    ref = O.apply_model(sd_gpu, cfg, x_in, t, c_in)
+    del sd_gpu
+    torch.cuda.empty_cache()
+    c_shared = {"c_crossattn": c_in["c_crossattn"], "example_pair": cond["example_pair"], "query": cond["query"]}
+    for mode in ("fp32", "bf16"):
+        eps = models[mode].apply_model(x_in, t, c_in)
+        err = rel_l2(eps, ref)
+        eps2 = models[mode].apply_model_cfg(inp["x_T"], t[:8], c_shared)
+        err2 = rel_l2(eps2, ref)
+        per_image = max(rel_l2(eps[i], ref[i]) for i in range(16))
+        print(f"[parity] apply_model 512^2 batch 8 (B_eff 16) {mode} vs oracle(gpu fp32): eps rel-L2 = {err:.3e} "
+              f"(worst image {per_image:.3e}); apply_model_cfg {err2:.3e}")
+        assert eps.shape == (16, 4, 64, 64)
+        assert err <= TOL[mode] and err2 <= TOL[mode], (mode, err, err2)
+    del ref
+    torch.cuda.empty_cache()
+
+
 def test_apply_model_config4_shape_vs_oracle_gpu(models, cfg, state_dict_cpu):
     """A slice of BASELINE config 4 (768^2 -> 96x96 latent, 9216-token self-attention: the attention-bound stress
     case), batch 1 (B_eff 2), bf16 mode: CUDA path vs the oracle run in fp32 on this GPU."""
