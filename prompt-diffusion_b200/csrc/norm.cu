@@ -235,6 +235,9 @@ gn_apply_kernel(const T* __restrict__ x, int ldx, TO* __restrict__ out, int ldo,
 // barrier in global memory (all CTAs are co-resident: cudaLaunchCooperativeKernel), folds the image's partials in
 // a fixed order (deterministic) and normalises the chunk it has just read (L2-hot).  Halves the launches of the 88
 // GroupNorms per step and removes the serial "last CTA folds" tail of the two-kernel form.
+#ifndef GN_REVERSE_APPLY
+#define GN_REVERSE_APPLY 0     // 1: apply pass walks its chunk backwards (L2 reuse): 59 -> 55 us at 16 x 4096 x 640 alone, +0.1 ms in the step (profiles/r02_gn_reverse.txt): off
+#endif
 template <typename T, typename TO>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_fused_kernel(const T* __restrict__ x, int ldx, TO* __restrict__ out, int ldo, const float* __restrict__ gamma,
@@ -392,7 +395,17 @@ gn_fused_kernel(const T* __restrict__ x, int ldx, TO* __restrict__ out, int ldo,
       }
     }
 #endif
+#if GN_REVERSE_APPLY
+    // The apply pass walks the chunk BACKWARDS: the rows the statistics pass read last are the ones most likely still in
+    // L2 (a 16 x 4096 x 640 tensor is 84 MB: walked in the same order, every row had been evicted by the time it was
+    // read again — ncu: 8.5 % L2 hits).  Per-element arithmetic: the order changes no bits.
+    const int r_first = r;
+    const int n_it = r < r1 ? (r1 - r + 2 * g.ty_n - 1) / (2 * g.ty_n) : 0;
+    for (int it = n_it - 1; it >= 0; --it) {
+      r = r_first + it * 2 * g.ty_n;
+#else
     for (; r < r1; r += 2 * g.ty_n) {
+#endif
       const bool two = r + g.ty_n < r1;
       float f0[V], f1[V];
       VecIO<T>::ld(xc + (int64_t)r * ldx, f0);
