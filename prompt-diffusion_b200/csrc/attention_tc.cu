@@ -70,6 +70,9 @@ constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or a
 #ifndef FA_HANDOFF_R
 #define FA_HANDOFF_R 15    // (FA_HAND) round of eight scores behind whose exponentials the SFU turn passes to the other group
 #endif
+#ifndef FA_THROTTLE
+#define FA_THROTTLE 0      // (FA_HAND) 1: a data dependency from the consumers of round r - 1 to the exponentials of round r + 1 (bounds the SFU queue): 640 -> 665 us, off
+#endif
 #ifndef FA_CDIST
 #define FA_CDIST 1         // (FA_HAND) the row sum / bf16 pack of round r - FA_CDIST sit between the exponentials of round r
 #endif
@@ -449,7 +452,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             if (consume) C(r - CD, 1, l2, l3);
             if (ex) { ex2_b32_v(s[b + 3]); poly_s2b(s[b + 6], s[b + 7], n0, n1); }
             if (tp) poly_s2b(s[b + 4], s[b + 5], m0, m1);
+#if FA_THROTTLE
+            // the scale-and-subtract of round r + 1 takes its addend through the row sum as it stands behind round r - 1's
+            // consumers: the MUFU.EX2 of round r + 1 cannot be scheduled (or issued) ahead of them, so the SFU queue never
+            // holds more than two rounds and the consumers find their operands ready
+            if (scale_next && r + 1 < 16) {
+              float d0, d1;
+              if (consume) dep_on(d0, d1, l0, l1, nm); else { d0 = nm; d1 = nm; }
+              ffma2_b32_v2(s[b + 8], s[b + 9], sc, d0, d1); ffma2_b32_v2(s[b + 10], s[b + 11], sc, d0, d1);
+            }
+#else
             if (scale_next && r + 1 < 16) { ffma2_b32_v(s[b + 8], s[b + 9], sc, nm); ffma2_b32_v(s[b + 10], s[b + 11], sc, nm); }
+#endif
             if (ex && !tp) ex2_b32_v(s[b + 4]);
             if (ex) poly_s3(q0, q1, s[b + 6], s[b + 7]);
             if (tp) poly_s3(w0, w1, s[b + 4], s[b + 5]);
@@ -457,7 +471,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             if (ex && !tp) ex2_b32_v(s[b + 5]);
             if (ex) poly_s45<4>(q0, q1, s[b + 6], s[b + 7]);
             if (tp) poly_s45<4>(w0, w1, s[b + 4], s[b + 5]);
+#if FA_THROTTLE
+            if (scale_next && r + 1 < 16) {
+              float d0, d1;
+              if (consume) dep_on(d0, d1, l2, l3, nm); else { d0 = nm; d1 = nm; }
+              ffma2_b32_v2(s[b + 12], s[b + 13], sc, d0, d1); ffma2_b32_v2(s[b + 14], s[b + 15], sc, d0, d1);
+            }
+#else
             if (scale_next && r + 1 < 16) { ffma2_b32_v(s[b + 12], s[b + 13], sc, nm); ffma2_b32_v(s[b + 14], s[b + 15], sc, nm); }
+#endif
             if (ex) poly_s45<5>(q0, q1, s[b + 6], s[b + 7]);
             if (tp) poly_s45<5>(w0, w1, s[b + 4], s[b + 5]);
             if (consume) C(r - CD, 3, l2, l3);

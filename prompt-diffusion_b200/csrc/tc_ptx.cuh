@@ -290,6 +290,21 @@ __device__ __forceinline__ void ffma2_b32_v(uint32_t& x0, uint32_t& x1, float a,
                "mov.b64 {%0, %1}, rx;\n\t}"
                : "+r"(x0), "+r"(x1) : "f"(a), "f"(c));
 }
+__device__ __forceinline__ void ffma2_b32_v2(uint32_t& x0, uint32_t& x1, float a, float c0, float c1) {   // per-lane addend
+  asm volatile("{\n\t.reg .b64 rx, ra, rc;\n\t"
+               "mov.b64 rx, {%0, %1};\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rc, {%3, %4};\n\t"
+               "fma.rn.f32x2 rx, rx, ra, rc;\n\t"
+               "mov.b64 {%0, %1}, rx;\n\t}"
+               : "+r"(x0), "+r"(x1) : "f"(a), "f"(c0), "f"(c1));
+}
+// {c0, c1} = {l0, l1} * 0 + c: the value of c with a data dependency on l (a scheduling throttle, see attention_tc.cu)
+__device__ __forceinline__ void dep_on(float& c0, float& c1, float l0, float l1, float c) {
+  asm volatile("{\n\t.reg .b64 rl, rz, rc;\n\t"
+               "mov.b64 rl, {%2, %3};\n\tmov.b64 rz, {0f00000000, 0f00000000};\n\tmov.b64 rc, {%4, %4};\n\t"
+               "fma.rn.f32x2 rc, rl, rz, rc;\n\t"
+               "mov.b64 {%0, %1}, rc;\n\t}"
+               : "=f"(c0), "=f"(c1) : "f"(l0), "f"(l1), "f"(c));
+}
 __device__ __forceinline__ void ex2_b32_v(uint32_t& x) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(x)); }
 __device__ __forceinline__ void fadd2_b32_v(float& l0, float& l1, uint32_t x0, uint32_t x1) {
   asm volatile("{\n\t.reg .b64 rl, rx;\n\t"
