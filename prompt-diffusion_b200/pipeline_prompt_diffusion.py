@@ -99,6 +99,19 @@ class DDIMScheduler:
         return (prev,) if not return_dict else {"prev_sample": prev, "pred_original_sample": pred_x0}
 
 
+    def step_coefficients(self, eta: float = 0.0):
+        """Per timestep of ``self.timesteps``: (alpha_t, alpha_prev, sigma_t, sqrt(1 - alpha_t)) — the four scalars ``step``
+        uses, in the row format of ``pd_cfg_ddim_step`` (the fused CFG + DDIM update kernel)."""
+        rows = []
+        for t in [int(v) for v in self.timesteps.cpu()]:
+            prev_t = t - self.num_train_timesteps // self.num_inference_steps
+            a_t = float(self.alphas_cumprod[t])
+            a_prev = float(self.alphas_cumprod[prev_t]) if prev_t >= 0 else float(self.final_alpha_cumprod)
+            std = eta * ((1.0 - a_prev) / (1.0 - a_t) * (1.0 - a_t / a_prev)) ** 0.5
+            rows.append((a_t, a_prev, std, (1.0 - a_t) ** 0.5))
+        return rows
+
+
 class UNet2DConditionShim:
     """The slice of ``UNet2DConditionModel.__call__`` the pipeline uses (:1257-1266), over ``ControlledUnetModel``
     (ldm ``forward(x, timesteps, context, control)``: control = 12 down residuals + the mid residual, consumed by pop)."""
@@ -158,13 +171,7 @@ class PromptDiffusionPipeline:
         with this scheduler's coefficients)."""
         sch, dev, B = self.scheduler, self.device, latents.shape[0]
         ts = [int(v) for v in sch.timesteps.cpu()]
-        rows = []
-        for t in ts:                                                                    # DDIMScheduler.step, per timestep
-            prev_t = t - sch.num_train_timesteps // sch.num_inference_steps
-            a_t = float(sch.alphas_cumprod[t])
-            a_prev = float(sch.alphas_cumprod[prev_t]) if prev_t >= 0 else float(sch.final_alpha_cumprod)
-            std = eta * ((1.0 - a_prev) / (1.0 - a_t) * (1.0 - a_t / a_prev)) ** 0.5
-            rows.append([a_t, a_prev, std, (1.0 - a_t) ** 0.5, guidance_scale if do_cfg else 1.0, 1.0])
+        rows = [list(r) + [guidance_scale if do_cfg else 1.0, 1.0] for r in sch.step_coefficients(eta)]
         coef = torch.tensor(rows, dtype=torch.float32).to(dev)
         conds = {"c_crossattn": [embeds], "example_pair": [image_pair], "query": [image]}
         old_scales = list(self._fused.control_scales)

@@ -229,3 +229,27 @@ def test_ddim_scheduler_restatement_matches_reference_schedule(golden):
                 ap = float(sch.alphas_cumprod[prev_t]) if prev_t >= 0 else float(sch.final_alpha_cumprod)
                 var = (1 - ap) / (1 - a_t) * (1 - a_t / ap)
                 assert abs(eta * var ** 0.5 - sigma) <= 1e-5 * max(sigma, 1e-6) + 1e-9 and abs(ap - a_prev) <= 2e-6 * a_prev
+
+
+def test_ddim_scheduler_step_coefficients_feed_the_fused_step(golden):
+    """``DDIMScheduler.step_coefficients`` — the rows the pipeline's fused route hands to ``pd_cfg_ddim_step`` — are the
+    reference schedule's own scalars (cldm/ddim_hacked.py:206-214, golden sched_S*_eta*) and reproduce ``step()``."""
+    from prompt_diffusion_b200.pipeline_prompt_diffusion import DDIMScheduler
+    for S, eta in ((20, 0.0), (50, 0.0), (50, 0.5)):
+        tag = f"sched_S{S}_eta{eta}"
+        sch = DDIMScheduler()
+        sch.set_timesteps(S)
+        rows = sch.step_coefficients(eta)
+        assert len(rows) == S
+        g = torch.Generator().manual_seed(100 + S)
+        x, e = torch.randn(2, 4, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+        for i, (t, (a_t, a_prev, sigma, s1m)) in enumerate(zip(sch.timesteps.tolist(), rows)):
+            index = S - 1 - i
+            assert abs(a_t - float(golden[tag + "_alphas"][index])) <= 2e-6 * a_t
+            assert abs(a_prev - float(golden[tag + "_alphas_prev"][index])) <= 2e-6 * a_prev
+            assert abs(sigma - float(golden[tag + "_sigmas"][index])) <= 1e-5 * max(sigma, 1e-3)
+            assert abs(s1m - float(golden[tag + "_sqrt_one_minus"][index])) <= 2e-6
+            if eta == 0.0:
+                fused = a_prev ** 0.5 * ((x - s1m * e) / a_t ** 0.5) + (1.0 - a_prev - sigma ** 2) ** 0.5 * e
+                got = sch.step(e, int(t), x, eta=0.0)[0]
+                assert float((got - fused).abs().max()) <= 1e-5 * float(fused.abs().max())
