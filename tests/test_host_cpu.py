@@ -253,3 +253,12 @@ def test_ddim_scheduler_step_coefficients_feed_the_fused_step(golden):
                 fused = a_prev ** 0.5 * ((x - s1m * e) / a_t ** 0.5) + (1.0 - a_prev - sigma ** 2) ** 0.5 * e
                 got = sch.step(e, int(t), x, eta=0.0)[0]
                 assert float((got - fused).abs().max()) <= 1e-5 * float(fused.abs().max())
+
+
+def test_diffusers_controlnet_refuses_configs_outside_the_path():
+    """Class / additional embeddings (promptdiffusioncontrolnet.py:288-320) are not part of the SD1.5 prompt-diffusion
+    configuration: a config that asks for them is refused at construction, before any device is touched."""
+    from prompt_diffusion_b200.promptdiffusioncontrolnet import PromptDiffusionControlNetModel
+    for kw in ({"class_embed_type": "timestep"}, {"num_class_embeds": 10}, {"addition_embed_type": "text_time"}):
+        with pytest.raises(NotImplementedError):
+            PromptDiffusionControlNetModel(device="cpu", **kw)
