@@ -70,6 +70,16 @@ constexpr float FA_GROW_LIMIT = 1.8446744e19f;   // 2^64: a tile row-sum at or a
 #ifndef FA_HANDOFF_R
 #define FA_HANDOFF_R 15    // (FA_HAND) round of eight scores behind whose exponentials the SFU turn passes to the other group
 #endif
+#ifndef FA_TURN_PER_SMSP
+#define FA_TURN_PER_SMSP 0 // 1: one pair of turn barriers per sub-partition (64 threads: the two softmax warps that share it) instead of one pair for the CTA (256 threads): 639 -> 653 us, off
+#endif
+#if FA_TURN_PER_SMSP
+#define FA_TURN_ID(turn) (3 + 2 * qd4 + (turn))
+#define FA_TURN_N 64
+#else
+#define FA_TURN_ID(turn) (3 + (turn))
+#define FA_TURN_N 256
+#endif
 #ifndef FA_THROTTLE
 #define FA_THROTTLE 0      // (FA_HAND) 1: a data dependency from the consumers of round r - 1 to the exponentials of round r + 1 (bounds the SFU queue): 640 -> 665 us, off
 #endif
@@ -321,7 +331,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const float sc = a.scale_log2;
     float m_ref = -INFINITY, l_run = 0.f;
 #if FA_PINGPONG
-    if constexpr (NG == 2) { if (g == 1) asm volatile("bar.arrive %0, 256;" ::"r"(3) : "memory"); }   // group A goes first
+    if constexpr (NG == 2) { if (g == 1) asm volatile("bar.arrive %0, %1;" ::"r"(FA_TURN_ID(0)), "r"(FA_TURN_N) : "memory"); }   // group A goes first
 #endif
     for (int j = 0; j < a.ntiles; ++j) {
       const bool last = j == a.ntiles - 1;
@@ -489,13 +499,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           };
           X8(0);
 #if FA_PINGPONG
-          if constexpr (NG == 2) asm volatile("bar.sync %0, 256;" ::"r"(3 + g_turn) : "memory");
+          if constexpr (NG == 2) asm volatile("bar.sync %0, %1;" ::"r"(FA_TURN_ID(g_turn)), "r"(FA_TURN_N) : "memory");
 #endif
 #pragma unroll
           for (int r = 0; r < 16 + CD; ++r) {
             round(r, r >= CD, true);
 #if FA_PINGPONG
-            if constexpr (NG == 2) { if (r == FA_HANDOFF_R) asm volatile("bar.arrive %0, 256;" ::"r"(3 + (g_turn ^ 1)) : "memory"); }
+            if constexpr (NG == 2) { if (r == FA_HANDOFF_R) asm volatile("bar.arrive %0, %1;" ::"r"(FA_TURN_ID(g_turn ^ 1)), "r"(FA_TURN_N) : "memory"); }
 #endif
           }
           lt = (l0 + l1) + (l2 + l3);
@@ -523,7 +533,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int g = 0; g <= D; ++g) X(g);
 #if FA_PINGPONG
         // the group's turn on the SFU starts here (the FFMA2 above need no SFU) ...
-        if constexpr (NG == 2) asm volatile("bar.sync %0, 256;" ::"r"(3 + g_turn) : "memory");
+        if constexpr (NG == 2) asm volatile("bar.sync %0, %1;" ::"r"(FA_TURN_ID(g_turn)), "r"(FA_TURN_N) : "memory");
 #endif
 #pragma unroll
         for (int g = 0; g < D; ++g) { E(g, 0); E(g, 1); E(g, 2); E(g, 3); }
@@ -540,7 +550,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
           E(e, 3);
 #if FA_PINGPONG
           // ... and ends behind its last exponential: the remaining FADD2 / F2FP / tcgen05.st overlap the other group's start
-          if constexpr (NG == 2) { if (e == FA_HANDOFF) asm volatile("bar.arrive %0, 256;" ::"r"(3 + (g_turn ^ 1)) : "memory"); }
+          if constexpr (NG == 2) { if (e == FA_HANDOFF) asm volatile("bar.arrive %0, %1;" ::"r"(FA_TURN_ID(g_turn ^ 1)), "r"(FA_TURN_N) : "memory"); }
 #endif
           const uint32_t p1 = pack_bf16x2_b32_v(s[4 * g + 2], s[4 * g + 3]);
           s[c32 + k] = p0; s[c32 + k + 1] = p1;
@@ -582,11 +592,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #if FA_PINGPONG
       // strict alternation of the two groups' exponential sections (named barriers 3 / 4 over the 256 softmax threads):
       // a group exponentiates alone on its sub-partitions' SFUs while the other one does its TMEM / barrier round trip
-      if constexpr (NG == 2 && !SWP_ON) asm volatile("bar.sync %0, 256;" ::"r"(3 + g) : "memory");
+      if constexpr (NG == 2 && !SWP_ON) asm volatile("bar.sync %0, %1;" ::"r"(FA_TURN_ID(g)), "r"(FA_TURN_N) : "memory");
 #endif
       exp_tile();
 #if FA_PINGPONG
-      if constexpr (NG == 2 && !SWP_ON) asm volatile("bar.arrive %0, 256;" ::"r"(3 + (g ^ 1)) : "memory");
+      if constexpr (NG == 2 && !SWP_ON) asm volatile("bar.arrive %0, %1;" ::"r"(FA_TURN_ID(g ^ 1)), "r"(FA_TURN_N) : "memory");
 #endif
       // overflow guard (warp-uniform: the rescale uses warp-collective tcgen05.ld / st)
       if (!SWP_ON && j > 0 && __any_sync(0xffffffffu, !(lt < FA_GROW_LIMIT))) {
